@@ -1,0 +1,44 @@
+"""MPJPE on the GPU through the C-ABI (reference: losses/losses.py:50-61)."""
+from __future__ import annotations
+
+import torch
+
+from . import _cabi
+
+
+def mpjpe(predicted: torch.Tensor, target: torch.Tensor, w=None, dim=-1, reduce_axis=[]):
+    """Mean per-joint position error.  Same call shape as the reference:
+    reduce_axis [] / () -> scalar mean (training loss), (0, 2) -> per-frame (T,), None -> (B, T, V).
+    Inputs: (B, T, V, 3) float32 CUDA tensors."""
+    if predicted.shape != target.shape:
+        raise AssertionError("predicted and target must have the same shape")   # reference asserts (:55)
+    if predicted.dim() != 4 or predicted.shape[-1] != 3 or dim not in (-1, 3):
+        raise ValueError("cistgcn_b200.mpjpe: expected (B, T, V, 3) tensors reduced over the last axis")
+    if predicted.dtype != torch.float32 or target.dtype != torch.float32 or not predicted.is_cuda \
+            or predicted.device != target.device:
+        raise ValueError("cistgcn_b200.mpjpe: float32 CUDA tensors on one device required (no CPU fallback)")
+    lib = _cabi.lib()
+    B, T, V, _ = predicted.shape
+    p, t = predicted.contiguous(), target.contiguous()
+    stream = torch.cuda.current_stream(p.device).cuda_stream
+    if reduce_axis is None:
+        err = torch.empty(B, T, V, device=p.device, dtype=torch.float32)
+        with torch.cuda.device(p.device):
+            _cabi.check(lib.cistgcn_mpjpe_f32(p.data_ptr(), t.data_ptr(), B, T, V, err.data_ptr(), None, stream),
+                        "cistgcn_mpjpe_f32")
+        return err
+    if isinstance(reduce_axis, int):
+        reduce_axis = (reduce_axis,)
+    axes = tuple(sorted(a % 3 for a in reduce_axis))
+    sums = torch.zeros(T, device=p.device, dtype=torch.float64)
+    with torch.cuda.device(p.device):
+        _cabi.check(lib.cistgcn_mpjpe_f32(p.data_ptr(), t.data_ptr(), B, T, V, None, sums.data_ptr(), stream),
+                    "cistgcn_mpjpe_f32")
+    if axes == ():
+        return (sums.sum() / (B * T * V)).to(torch.float32)
+    if axes == (0, 2):
+        return (sums / (B * V)).to(torch.float32)
+    if axes == (0, 1, 2):
+        return (sums.sum() / (B * T * V)).to(torch.float32)
+    raise ValueError(f"cistgcn_b200.mpjpe: reduce_axis {reduce_axis} is not used on this path "
+                     "(supported: [], (0, 2), None)")

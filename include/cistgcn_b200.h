@@ -1,0 +1,192 @@
+/*
+ * cistgcn_b200 -- C-ABI of the B200-native CIST-GCN forward path.
+ *
+ * Plain C: pointers, sizes and int32 descriptor arrays only (no torch / C++ types).  Every
+ * buffer (packed weights, activations, workspace) is allocated and owned by the caller on the
+ * device the call runs on; `stream` is a cudaStream_t passed as void*.  All entry points
+ * return 0 on success and a negative code on error; cistgcn_last_error() returns the message of
+ * the last failing call on the calling thread.  There is no global mutable state besides that.
+ *
+ * What each entry point replaces in the reference (QualityMinds/cistgcn, paths relative to
+ * human_motion_prediction/):
+ *   cistgcn_forward_f32      models/CISTGCN/CISTGCN.py:567-597  CISTGCN.forward, called from
+ *                            environment/train.py:59 and environment/test.py:101,103
+ *                            (+ losses/losses.py:50-61 mpjpe when `target` is given)
+ *   cistgcn_dstd_block_f32   models/CISTGCN/CISTGCN.py:373-390  DSTD_GC.forward (one block)
+ *   cistgcn_fpn_chain_f32    models/CISTGCN/CISTGCN.py:582-589  FPN stack + dim_conversor + cumsum
+ *   cistgcn_tail_f32         models/CISTGCN/CISTGCN.py:591-597  ContextLayer + output assembly
+ *   cistgcn_mpjpe_f32        losses/losses.py:50-61             mpjpe (all three reduce_axis modes)
+ *
+ * Descriptors are flat int32 arrays indexed by the enums below.  Weight fields are offsets (in
+ * floats) into the packed weight blob produced by cistgcn_b200/pack.py (BatchNorm folded,
+ * matrices stored k-major with the output dimension padded to a multiple of CISTGCN_MPAD).
+ */
+#ifndef CISTGCN_B200_H
+#define CISTGCN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CISTGCN_ABI_VERSION 3
+#define CISTGCN_MPAD 8          /* output-dimension padding of every k-major matrix */
+#define CISTGCN_MAX_BLOCKS 8    /* input + output DSTD-GC blocks in one plan */
+#define CISTGCN_MAX_FPN 8
+
+/* ---- one DSTD-GC block (CISTGCN.py:273-390).  *_S/_T pairs: index +0 = dsgn ("space" domain,
+ *      TxT adjacency per joint), +1 = tsgn ("time" domain, VxV adjacency per frame). ---------- */
+enum cistgcn_block_field {
+  CB_CI = 0,      /* input channels */
+  CB_CO,          /* output channels */
+  CB_T,           /* length of the block's "time" axis  (10; V for the output block) */
+  CB_V,           /* length of the block's "joint" axis (V; 25 for the output block) */
+  CB_CH,          /* Map2Adj inter channels = Ci/2            (CISTGCN.py:137) */
+  CB_CG,          /* gate inter channels = max(Co/2,1)        (CISTGCN.py:321) */
+  CB_HS,          /* SE hidden width = max(Co/reduction,1)    (SE.py:28-29)    */
+  CB_HAS_RES,     /* 1 when Ci != Co: residual paths are conv1x1+BN (CISTGCN.py:239-247,310-318) */
+  CB_INTERP,      /* 1: adjacency generated per sample by Map2Adj; 0: static A parameters */
+  CB_IN_MODE,     /* 0: activation tensor with the strides below; 1: raw poses (T,V,3) -> 10 features */
+  CB_IN_SB, CB_IN_SC, CB_IN_ST, CB_IN_SV,      /* input strides in floats: sample, c, t, v */
+  CB_OUT_SB, CB_OUT_SC, CB_OUT_ST, CB_OUT_SV,  /* output strides */
+  CB_GN_S, CB_GN_B,                 /* global_norm folded scale / shift               [Ci]        */
+  CB_G0_WT, CB_G0_B, CB_G0_A,       /* conv_{s,t}.0 stacked: [Ci*T][pad(2Cg)], [2Cg], slopes [2]  */
+  CB_G4_WT, CB_G4_B, CB_G4_A,       /* conv_{s,t}.4: 2 x [Cg*V][pad(Co)], [2][Co], slopes [2]     */
+  CB_M0_WT, CB_M0_B, CB_M0_A,       /* map_{s,t}.0:  2 x [Co+2+2T][pad(Co)], [2][Co], slopes [2]  */
+  CB_M4_WT,                         /* map_{s,t}.4:  2 x [Co][pad(Co)]                            */
+  CB_A0_WT, CB_A0_B, CB_A0_A,       /* Map2Adj first 1x1 convs stacked (dsgn.tc, dsgn.jc, tsgn.tc, tsgn.jc):
+                                       [Ci][pad(4Ch)], [4Ch], slopes [4] */
+  CB_TC3_WT_S, CB_TC3_WT_T,         /* time_compress.3 (+BN .4):  [Ch*T][pad(Ch)] */
+  CB_TC3_B_S, CB_TC3_B_T,           /* [Ch] */
+  CB_TC6_WT_S, CB_TC6_WT_T,         /* time_compress.6:           [Ch][pad(T)]   */
+  CB_JC3_WT_S, CB_JC3_WT_T,         /* joint_compress.3 (+BN .4): [Ch*V][pad(Ch)] */
+  CB_JC3_B_S, CB_JC3_B_T,
+  CB_JC6_WT_S, CB_JC6_WT_T,         /* joint_compress.6:          [Ch][pad(V)]   */
+  CB_E0_WT_S, CB_E0_WT_T,           /* expansor.0 (+BN .1): [n][pad(n)], n = V (dsgn) / T (tsgn) */
+  CB_E0_B_S, CB_E0_B_T,
+  CB_E0_A_S, CB_E0_A_T,             /* expansor.3 PReLU slope */
+  CB_E4_WT_S, CB_E4_WT_T,           /* expansor.4: [n][pad(n)] */
+  CB_ADJ_S, CB_ADJ_T,               /* static adjacency gcn.A: (V,T,T) / (T,V,V); used when !INTERP */
+  CB_TCN_WT_S, CB_TCN_WT_T,         /* tcn.0 (+BN .1) [Ci (+Ci residual rows when HAS_RES)][pad(Co)] */
+  CB_TCN_B_S, CB_TCN_B_T,           /* combined bias [Co] */
+  CB_TCN_A_S, CB_TCN_A_T,           /* Domain_GCNN_layer.prelu slope */
+  CB_P_S_S, CB_P_S_T,               /* prelu{1,2}.0 BN scale [Co] */
+  CB_P_B_S, CB_P_B_T,               /* prelu{1,2}.0 BN shift [Co] */
+  CB_P_A_S, CB_P_A_T,               /* prelu{1,2}.1 slope */
+  CB_CP_WT, CB_CP_B, CB_CP_A,       /* compressor.0 (+BN .1): [2Co][pad(Co)], [Co], slope */
+  CB_SE1_WT, CB_SE2_WT,             /* compressor.3.excitation.{0,2}: [Co][pad(Hs)], [Hs][pad(Co)] */
+  CB_RS_WT, CB_RS_B,                /* block residual conv (+BN): [Ci][pad(Co)], [Co]  (HAS_RES only) */
+  CB_COUNT
+};
+
+/* ---- one FPN layer (CISTGCN.py:38-79) + the caller's PReLU / residual (:584-586) ------------ */
+enum cistgcn_fpn_field {
+  CF_CIN = 0,     /* input channels (= frames): input_n for layer 0, output_n afterwards */
+  CF_COUT,        /* output_n (25) */
+  CF_RESID,       /* 1: x6 = PReLU(FPN(x6)) + x6 (layers >= 1) */
+  CF_W_D1, CF_W_D2, CF_W_D3,   /* block{1,2,3}.0 (+BN .1): [Cin][3][5 otiles][16] (kw-major, 5 outs, 1 pad) */
+  CF_B_D1, CF_B_D2, CF_B_D3,   /* folded bias [Cout] */
+  CF_A_D1, CF_A_D2, CF_A_D3,   /* block{1,2,3}.3 slope */
+  CF_CP_WT,       /* compress weights for the 3*Cout branch channels: [3*Cout][pad(Cout)] */
+  CF_CP_AVG_WT,   /* compress weights for the Cin global-average channels: [Cin][pad(Cout)] */
+  CF_CP_B,        /* compress bias [Cout] */
+  CF_OUT_A,       /* prelus.{i} slope */
+  CF_COUNT
+};
+
+/* ---- FPN chain + dim_conversor + cumsum, ContextLayer, output assembly ---------------------- */
+enum cistgcn_tail_field {
+  CT_TIN = 0,     /* input_n  */
+  CT_TOUT,        /* output_n */
+  CT_V,           /* joints   */
+  CT_F,           /* feature channels leaving the input block stack (in_ch = 10, CISTGCN.py:512) */
+  CT_HID,         /* ContextLayer hidden_dim (64) */
+  CT_SEH1,        /* SELayer1d hidden = Tout / reduction      (SE.py:10)    */
+  CT_SEH2,        /* SELayer2d hidden = max(Tout/reduction,1) (SE.py:28-29) */
+  CT_DC0_WT, CT_DC0_B, CT_DC0_A,    /* dim_conversor.0 (+BN .1): [F][pad(3)], [3], slope */
+  CT_DC3_WT, CT_DC3_A,              /* dim_conversor.3: [3][pad(3)]; dim_conversor.4 slopes [3] */
+  CT_C1_S, CT_C1_B, CT_C1_A,        /* context_conv1 folded per-channel scale/shift [HID], slope */
+  CT_C2_WT, CT_C2_B, CT_C2_A,       /* context_conv2 (+BN): [Tout][pad(HID)], [HID], slope */
+  CT_C3_S, CT_C3_B, CT_C3_A,        /* context_conv3 */
+  CT_MAP_WT, CT_MAP_A,              /* map{1,2,3}.0: 3 x [HID][pad(Tout)]; slopes [3] */
+  CT_FS_WT, CT_FS_B,                /* fmap_s (+BN): [3*Tout][pad(V)], [V] */
+  CT_FT_WT, CT_FT_B,                /* fmap_t (+BN): [3*Tout][pad(Tout)], [Tout] */
+  CT_N0_WT, CT_N0_B, CT_N0_A,       /* norm_map.0 (+BN .1): [Tout][pad(Tout)], [Tout], slope (.3) */
+  CT_NSE1_WT, CT_NSE2_WT,           /* norm_map.4.excitation.{0,2}: [Tout][pad(SEH1)], [SEH1][pad(Tout)] */
+  CT_N5_WT, CT_N5_B, CT_N5_A,       /* norm_map.5 (+BN .6), slope (.8) */
+  CT_FC0_S, CT_FC0_B, CT_FC0_A,     /* fconv.0 (+BN .1): per-dim scale/shift [3], slope */
+  CT_FC3_WT, CT_FC3_B, CT_FC3_A,    /* fconv.3 (+BN .4): [3][pad(3)], [3], slope */
+  CT_SE1_WT, CT_SE2_WT,             /* SE.excitation.{0,2}: [Tout][pad(SEH2)], [SEH2][pad(Tout)] */
+  CT_COUNT
+};
+
+/* ---- whole-model plan: header, then the block / FPN / tail descriptors back to back --------- */
+enum cistgcn_plan_field {
+  CP_ABI = 0,     /* must equal CISTGCN_ABI_VERSION */
+  CP_TIN, CP_TOUT, CP_V,
+  CP_N_IN_BLOCKS, /* DSTD-GC blocks before the FPN stack (5) */
+  CP_N_FPN,       /* FPN layers (4) */
+  CP_N_OUT_BLOCKS,/* DSTD-GC blocks after the ContextLayer (1) */
+  CP_CMAX,        /* widest channel count of any inter-block activation */
+  CP_WEIGHT_FLOATS, /* size of the packed weight blob, for bounds checking */
+  CP_HEADER_COUNT
+};
+/* plan layout: [CP_HEADER_COUNT] [n_in x CB_COUNT] [n_fpn x CF_COUNT] [CT_COUNT] [n_out x CB_COUNT] */
+
+/* Optional interpretability outputs (environment/test.py:146-157 reads them off the module).
+ * Any pointer may be NULL.  Shapes per sample: adj_s (V,T,T), adj_t (T,V,V), w1/w2 (Co). */
+typedef struct cistgcn_block_taps {
+  float* adj_s;
+  float* adj_t;
+  float* w1;
+  float* w2;
+} cistgcn_block_taps;
+
+typedef struct cistgcn_taps {
+  cistgcn_block_taps in_blocks[CISTGCN_MAX_BLOCKS];
+  cistgcn_block_taps out_blocks[CISTGCN_MAX_BLOCKS];
+  float* ctx_joints;          /* (B, V)          context_layer.joints          */
+  float* ctx_displacements;   /* (B, Tout)       context_layer.displacements   */
+  float* ctx_seq_joints_n;    /* (B, Tout, V)    context_layer.seq_joints_n    */
+  float* ctx_seq_joints_dims; /* (B, 3, Tout, V) context_layer.seq_joints_dims */
+} cistgcn_taps;
+
+const char* cistgcn_last_error(void);
+int cistgcn_abi_version(void);
+
+/* Bytes of scratch the forward needs for `batch` samples (it chunks internally above
+ * CISTGCN_MAX_CHUNK samples, so this saturates). */
+size_t cistgcn_workspace_bytes(const int32_t* plan, int64_t batch);
+
+/* Full forward.  x: (B, Tin, V, 3) fp32 contiguous; pred: (B, Tout, V, 3).
+ * target (optional, same shape as pred) + frame_sums (optional, double[Tout], ACCUMULATED into:
+ * the caller zeroes it): sum over samples and joints of ||pred - target||_2 per output frame, from
+ * which mpjpe's `[]` and `(0,2)` reductions follow by dividing by B*V*Tout resp. B*V. */
+int cistgcn_forward_f32(const int32_t* plan, int32_t plan_len, const float* weights,
+                        const float* x, float* pred, const float* target, double* frame_sums,
+                        void* workspace, size_t workspace_bytes, int64_t batch,
+                        const cistgcn_taps* taps, void* stream);
+
+/* One DSTD-GC block on `batch` samples with the strides in the descriptor. */
+int cistgcn_dstd_block_f32(const int32_t* block_desc, const float* weights, const float* in,
+                           float* out, int64_t batch, const cistgcn_block_taps* taps, void* stream);
+
+/* FPN stack + dim_conversor + cumsum.  in: (B, Tin, F, V) (frames as channels); out x7: (B, Tout, V, 3). */
+int cistgcn_fpn_chain_f32(const int32_t* fpn_descs, int32_t n_fpn, const int32_t* tail_desc,
+                          const float* weights, const float* in, float* x7, int64_t batch, void* stream);
+
+/* ContextLayer(x7) + output assembly: pred = x[:, -1:] + x8 + act (+ optional MPJPE partial sums). */
+int cistgcn_tail_f32(const int32_t* tail_desc, const float* weights, const float* x, const float* x7,
+                     const float* x8, float* pred, const float* target, double* frame_sums,
+                     int64_t batch, const cistgcn_taps* taps, void* stream);
+
+/* mpjpe: err (optional): (B, T, V) per-joint L2 error; frame_sums (optional): double[T] accumulated. */
+int cistgcn_mpjpe_f32(const float* pred, const float* target, int64_t batch, int32_t T, int32_t V,
+                      float* err, double* frame_sums, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CISTGCN_B200_H */
