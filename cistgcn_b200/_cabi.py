@@ -34,7 +34,8 @@ class Taps(ctypes.Structure):
 
 
 EXPORTS = ("cistgcn_last_error", "cistgcn_abi_version", "cistgcn_workspace_bytes", "cistgcn_forward_f32",
-           "cistgcn_dstd_block_f32", "cistgcn_fpn_chain_f32", "cistgcn_tail_f32", "cistgcn_mpjpe_f32")
+           "cistgcn_dstd_block_f32", "cistgcn_fpn_chain_f32", "cistgcn_tail_f32", "cistgcn_mpjpe_f32",
+           "cistgcn_profile_enable", "cistgcn_profile_read")
 
 
 def bind(path: str) -> ctypes.CDLL:
@@ -56,6 +57,10 @@ def bind(path: str) -> ctypes.CDLL:
     L.cistgcn_tail_f32.argtypes = [_i32p, _p, _p, _p, _p, _p, _p, _p, ctypes.c_int64, ctypes.POINTER(Taps), _p]
     L.cistgcn_mpjpe_f32.restype = ctypes.c_int
     L.cistgcn_mpjpe_f32.argtypes = [_p, _p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _p, _p, _p]
+    L.cistgcn_profile_enable.restype = ctypes.c_int
+    L.cistgcn_profile_enable.argtypes = [ctypes.c_int]
+    L.cistgcn_profile_read.restype = ctypes.c_int
+    L.cistgcn_profile_read.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]
     if L.cistgcn_abi_version() != ABI_VERSION:
         raise RuntimeError(f"cistgcn_b200: {path} has ABI {L.cistgcn_abi_version()}, header says {ABI_VERSION}; "
                            "rebuild with `python -c 'import __graft_entry__ as g; g.build()'`")

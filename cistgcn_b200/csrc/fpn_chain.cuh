@@ -1,0 +1,204 @@
+// Time-extrapolator stack: 4 x FPN (CISTGCN.py:38-79) with the caller's PReLU / residual (:584-586),
+// then dim_conversor (:541-545) and the cumulative sum over output frames (:588-589), one kernel.
+//
+// Frames are the channel axis here; the 2-D map is (H = 10 feature rows) x (W = V joints).
+// One CTA owns one sample at a time.  The sample's map lives in shared memory, column-padded
+// ([c][h][XS], data at columns 4..4+V, zeros around it; out-of-range rows read a shared zero row),
+// is updated in place layer after layer and never returns to HBM until x7 is written.
+//
+// Hot loop (56 % of the model's FLOPs): each thread owns 5 output channels x one full row of V
+// joints of one dilation branch (5*V accumulators).  Per (input channel, kernel row) it loads the
+// input row once (<= 8 x LDS.128) and 15 weights (4 x LDG.128, warp-uniform per channel tile) and
+// issues 3*5*V FFMAs -- ~27 FFMA per load instruction, so the FP32 pipe, not the LSU, is the limit.
+#pragma once
+#include "../../include/cistgcn_b200.h"
+#include "dstd_block.cuh"
+#include "simt.h"
+
+namespace cg {
+
+constexpr int FPN_XS = 36;        // padded row stride of the resident map (floats)
+constexpr int FPN_LPAD = 4;       // data starts at column 4 (keeps rows float4-aligned)
+constexpr int FPN_NT = 192;       // 6 warps: 2 per dilation branch
+constexpr int FPN_MAX_LAYERS = CISTGCN_MAX_FPN;
+
+struct FpnArgs {
+  int f[FPN_MAX_LAYERS][CF_COUNT];
+  int t[CT_COUNT];
+  int n_layers;
+  const float* w;
+  const float* in;     // (B, Tin, F, V)
+  float* x7;           // (B, Tout, V, 3)
+  int batch;
+  int o_x, o_zero, o_b, o_misc, smem_floats;
+};
+
+inline void fpn_plan(FpnArgs& a) {
+  const int To = a.t[CT_TOUT], F = a.t[CT_F], V = a.t[CT_V];
+  a.o_x = 0;
+  a.o_zero = To * F * FPN_XS;
+  a.o_b = a.o_zero + 40;
+  a.o_misc = a.o_b + pad4i(3 * To * F * V);
+  a.smem_floats = a.o_misc + 2 * pad4i(To) + pad4i(3 * To * V);
+}
+
+// One dilation branch: conv3x3(dil = D, pad = D) + folded BN + PReLU for `To` output channels.
+// Work item = (channel tile of 5, row h); `wib` / `wpb` = this warp's index / warps per branch.
+template <int V, int D>
+CG_DEV void fpn_branch(const float* __restrict__ Wd, const float* __restrict__ bias, float slope,
+                       const float* X, const float* zero_row, float* Bout,
+                       int Cin, int To, int F, int wib, int wpb) {
+  constexpr int NV4 = (FPN_LPAD + V + 3 + 3) / 4;             // float4 chunks covering columns [0, 4+V+3)
+  const int lane = threadIdx.x & 31;
+  const int notile = To / 5;
+  const int items = notile * F;
+  const int chunk = (items + wpb - 1) / wpb;
+  for (int it = lane; it < chunk; it += 32) {
+    const int item = wib * chunk + it;
+    if (item >= items) break;
+    const int ot = item / F, h = item - ot * F;
+    float acc[5][V];
+#pragma unroll
+    for (int m = 0; m < 5; ++m)
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[m][j] = 0.f;
+    for (int c = 0; c < Cin; ++c) {
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int hh = h + (kh - 1) * D;
+        const float* row = (hh >= 0 && hh < F) ? X + (c * F + hh) * FPN_XS : zero_row;
+        float xr[NV4 * 4];
+#pragma unroll
+        for (int q = 0; q < NV4; ++q) {
+          const float4 v4 = *reinterpret_cast<const float4*>(row + 4 * q);
+          xr[4 * q] = v4.x; xr[4 * q + 1] = v4.y; xr[4 * q + 2] = v4.z; xr[4 * q + 3] = v4.w;
+        }
+        float wv[16];
+        load_vec<16>(Wd + (size_t)((c * 3 + kh) * notile + ot) * 16, wv);
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+          for (int m = 0; m < 5; ++m)
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+              acc[m][j] = fmaf(wv[kw * 5 + m], xr[FPN_LPAD + j + (kw - 1) * D], acc[m][j]);
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+      const int o = ot * 5 + m;
+      const float bo = bias[o];
+      float* dst = Bout + ((D - 1) * To + o) * (F * V) + h * V;
+#pragma unroll
+      for (int j = 0; j < V; ++j) dst[j] = prelu(acc[m][j] + bo, slope);
+    }
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(FPN_NT) fpn_chain_kernel(const FpnArgs a) {
+  CG_DYN_SMEM(smem);
+  constexpr int NT = FPN_NT;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const float* __restrict__ W = a.w;
+  const int Tin = a.t[CT_TIN], To = a.t[CT_TOUT], F = a.t[CT_F];
+  const int FV = F * V;
+  float* X = smem + a.o_x;
+  float* zero_row = smem + a.o_zero;
+  float* Bb = smem + a.o_b;
+  float* avg = smem + a.o_misc;
+  float* cst = avg + pad4i(To);
+  float* y6 = cst + pad4i(To);              // dim_conversor output (To, V, 3) before the cumsum
+
+  // zero the padding once: data columns are the only ones ever rewritten
+  for (int i = tid; i < To * F * FPN_XS + 40; i += NT) X[i] = 0.f;
+  __syncthreads();
+
+  for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
+    {   // load (Tin, F, V) into the padded map
+      const float* src = a.in + (size_t)b * Tin * FV;
+      for (int i = tid; i < Tin * FV; i += NT) {
+        const int r = i / V, v = i - r * V;
+        X[r * FPN_XS + FPN_LPAD + v] = src[i];
+      }
+    }
+    __syncthreads();
+    for (int l = 0; l < a.n_layers; ++l) {
+      const int* f = a.f[l];
+      const int Cin = f[CF_CIN];
+      // global-average branch (:69, 76) folded into a per-output constant
+      for (int c = warp; c < Cin; c += NT / 32) {
+        float s = 0.f;
+        for (int i = tid & 31; i < FV; i += 32) { const int h = i / V, v = i - h * V; s += X[(c * F + h) * FPN_XS + FPN_LPAD + v]; }
+        s = warp_sum(s);
+        if ((tid & 31) == 0) avg[c] = s / FV;
+      }
+      __syncthreads();
+      for (int o = tid; o < To; o += NT) {
+        const float* wt = W + f[CF_CP_AVG_WT] + o;
+        float acc = W[f[CF_CP_B] + o];
+        for (int c = 0; c < Cin; ++c) acc = fmaf(wt[c * pad8i(To)], avg[c], acc);
+        cst[o] = acc;
+      }
+      // three dilation branches, two warps each
+      {
+        const int br = warp / 2, wib = warp & 1;
+        if (br == 0) fpn_branch<V, 1>(W + f[CF_W_D1], W + f[CF_B_D1], W[f[CF_A_D1]], X, zero_row, Bb, Cin, To, F, wib, 2);
+        else if (br == 1) fpn_branch<V, 2>(W + f[CF_W_D2], W + f[CF_B_D2], W[f[CF_A_D2]], X, zero_row, Bb, Cin, To, F, wib, 2);
+        else fpn_branch<V, 3>(W + f[CF_W_D3], W + f[CF_B_D3], W[f[CF_A_D3]], X, zero_row, Bb, Cin, To, F, wib, 2);
+      }
+      __syncthreads();
+      // compress 1x1 (:77-78) + caller's PReLU (+ residual), written back in place
+      {
+        const float oa = W[f[CF_OUT_A]];
+        const bool resid = f[CF_RESID] != 0;
+        gemm_rows<4, 2, NT, false>(W + f[CF_CP_WT], pad8i(To), To, FV, Bb, FV, 3 * To, nullptr, 0, 0,
+                                   [&](int m, int n, float acc) {
+                                     const int h = n / V, v = n - h * V;
+                                     float* xp = X + (m * F + h) * FPN_XS + FPN_LPAD + v;
+                                     float val = prelu(acc + cst[m], oa);
+                                     if (resid) val += *xp;
+                                     *xp = val;
+                                   });
+      }
+      __syncthreads();
+    }
+    // dim_conversor on (F channels, To, V): conv1x1 F->3, BN, PReLU, conv1x1 3->3, PReLU(3)  (:541-545)
+    {
+      const float* w0 = W + a.t[CT_DC0_WT];
+      const float* b0 = W + a.t[CT_DC0_B];
+      const float a0 = W[a.t[CT_DC0_A]];
+      const float* w3 = W + a.t[CT_DC3_WT];
+      const float* a3 = W + a.t[CT_DC3_A];
+      for (int i = tid; i < To * V; i += NT) {
+        const int fr = i / V, v = i - fr * V;
+        float y[3] = {b0[0], b0[1], b0[2]};
+        for (int c = 0; c < F; ++c) {
+          const float xv = X[(fr * F + c) * FPN_XS + FPN_LPAD + v];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) y[k] = fmaf(w0[c * 8 + k], xv, y[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) y[k] = prelu(y[k], a0);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          float z = 0.f;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) z = fmaf(w3[j * 8 + k], y[j], z);
+          y6[i * 3 + k] = prelu(z, a3[k]);
+        }
+      }
+    }
+    __syncthreads();
+    {   // x7 = cumsum over frames (:589)
+      float* dst = a.x7 + (size_t)b * To * V * 3;
+      for (int i = tid; i < V * 3; i += NT) {
+        float s = 0.f;
+        for (int fr = 0; fr < To; ++fr) { s += y6[fr * V * 3 + i]; dst[fr * V * 3 + i] = s; }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace cg

@@ -1,0 +1,58 @@
+// Portability shim: the kernels are plain CUDA C++; under -DCISTGCN_EMU (tests/emu only) the same
+// sources are compiled by g++ against a SIMT emulator so kernel logic can be checked without a GPU.
+#pragma once
+#include <stdint.h>
+
+#ifdef CISTGCN_EMU
+#include "simt_emu.h"
+#define CG_LAUNCH(kfn, grid, block, smem, stream, ...) \
+  simt_emu::launch(dim3(grid), dim3(block), (smem), [=]() { kfn(__VA_ARGS__); })
+#define CG_DYN_SMEM(name) float* name = reinterpret_cast<float*>(simt_emu::dyn_smem())
+#define CG_HOST_ONLY_CUDA(...)
+#else
+#include <cuda_runtime.h>
+#define CG_LAUNCH(kfn, grid, block, smem, stream, ...) \
+  kfn<<<dim3(grid), dim3(block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#define CG_DYN_SMEM(name) extern __shared__ __align__(16) float name[]
+#define CG_HOST_ONLY_CUDA(...) __VA_ARGS__
+#endif
+
+#define CG_DEV __device__ __forceinline__
+
+namespace cg {
+
+CG_DEV float prelu(float v, float a) { return v >= 0.f ? v : a * v; }
+CG_DEV float sigmoidf(float v) { return 1.f / (1.f + expf(-v)); }
+
+CG_DEV float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+CG_DEV float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Loads TM consecutive floats (TM in {1,2,4,8}); p must be aligned to min(TM,4) floats.
+template <int TM>
+CG_DEV void load_vec(const float* __restrict__ p, float (&w)[TM]) {
+  if constexpr (TM % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < TM / 4; ++i) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
+      w[4 * i + 0] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+    }
+  } else if constexpr (TM == 2) {
+    float2 v = __ldg(reinterpret_cast<const float2*>(p));
+    w[0] = v.x; w[1] = v.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < TM; ++i) w[i] = __ldg(p + i);
+  }
+}
+
+template <int N> struct IntC { static constexpr int value = N; };
+
+}  // namespace cg

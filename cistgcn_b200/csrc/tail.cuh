@@ -1,0 +1,265 @@
+// ContextLayer (CISTGCN.py:393-475), output assembly (:595-597) and MPJPE (losses/losses.py:50-61).
+//
+// One CTA per sample (persistent).  The three (hidden x Tout x 3V) context maps of the reference
+// (422 KB per sample each in eager mode) are never materialised: every thread streams its channel's
+// values through max / sum accumulators in registers.
+#pragma once
+#include "../../include/cistgcn_b200.h"
+#include "dstd_block.cuh"
+#include "simt.h"
+
+namespace cg {
+
+constexpr int TAIL_NT = 256;
+
+struct TailArgs {
+  int t[CT_COUNT];
+  const float* w;
+  const float* x;        // (B, Tin, V, 3)   model input (for x[:, -1:])
+  const float* x7;       // (B, Tout, V, 3)
+  const float* x8;       // (B, Tout, V, 3)  output DSTD-GC block result, already permuted back
+  float* pred;           // (B, Tout, V, 3)
+  const float* target;   // optional
+  double* frame_sums;    // optional, [Tout]
+  float* tap_joints; float* tap_disp; float* tap_sjn; float* tap_sjd;
+  int batch;
+  int smem_floats;
+};
+
+inline void tail_plan(TailArgs& a) {
+  const int To = a.t[CT_TOUT], V = a.t[CT_V], H = a.t[CT_HID];
+  a.smem_floats = pad4i(To * V * 3) + 3 * pad4i(4 * H) + pad4i(3 * H) + pad4i(3 * To) + pad4i(V) + pad4i(To) +
+                  3 * pad4i(To * V) + pad4i(3 * To * V) + 4 * pad4i(To) + 2 * 8 + 2 * pad4i(To);
+}
+
+__global__ void __launch_bounds__(TAIL_NT) tail_kernel(const TailArgs a) {
+  CG_DYN_SMEM(smem);
+  constexpr int NT = TAIL_NT;
+  const int tid = threadIdx.x;
+  const float* __restrict__ W = a.w;
+  const int* t = a.t;
+  const int Tin = t[CT_TIN], To = t[CT_TOUT], V = t[CT_V], H = t[CT_HID], S1 = t[CT_SEH1], S2 = t[CT_SEH2];
+  const int V3 = V * 3, NZ = To * V3, Top = pad8i(To);
+  float* p = smem;
+  float* z = p;      p += pad4i(NZ);          // x7 as (Tout, 3V)
+  float* part1 = p;  p += pad4i(4 * H);       // partial max of context_conv1
+  float* part2 = p;  p += pad4i(4 * H);       // partial max of context_conv2
+  float* part3 = p;  p += pad4i(4 * H);       // partial sum of context_conv3
+  float* yv = p;     p += pad4i(3 * H);       // y1 | y2 | ym
+  float* y = p;      p += pad4i(3 * To);
+  float* joints = p; p += pad4i(V);
+  float* disp = p;   p += pad4i(To);
+  float* n1 = p;     p += pad4i(To * V);
+  float* n1s = p;    p += pad4i(To * V);
+  float* n2 = p;     p += pad4i(To * V);
+  float* f3 = p;     p += pad4i(3 * To * V);
+  float* mean1 = p;  p += pad4i(To);
+  float* gate1 = p;  p += pad4i(To);
+  float* mean2 = p;  p += pad4i(To);
+  float* gate2 = p;  p += pad4i(To);
+  float* e1 = p;     p += 8;
+  float* e2 = p;     p += 8;
+  float* fsum = p;   p += pad4i(To);          // per-frame error partials of this sample
+  double facc = 0.0;                          // thread tid < To accumulates frame tid over this CTA's samples
+
+  for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
+    const float* x7 = a.x7 + (size_t)b * NZ;
+    for (int i = tid; i < NZ; i += NT) z[i] = x7[i];
+    for (int i = tid; i < To; i += NT) fsum[i] = 0.f;
+    __syncthreads();
+    // ---- context_conv1 (max over all positions), context_conv3 (mean), context_conv2 (max over columns)
+    {
+      const int ch = tid % H, sub = tid / H, nsub = NT / H;      // H = 64 -> 4 position slices per channel
+      const float s1 = W[t[CT_C1_S] + ch], b1 = W[t[CT_C1_B] + ch], a1 = W[t[CT_C1_A]];
+      const float s3 = W[t[CT_C3_S] + ch], b3 = W[t[CT_C3_B] + ch], a3 = W[t[CT_C3_A]];
+      float mx = -INFINITY, sm = 0.f;
+      for (int i = sub; i < NZ; i += nsub) {
+        const float zv = z[i];
+        mx = fmaxf(mx, prelu(fmaf(s1, zv, b1), a1));
+        sm += prelu(fmaf(s3, zv, b3), a3);
+      }
+      float mx2 = -INFINITY;
+      const float b2 = W[t[CT_C2_B] + ch], a2 = W[t[CT_C2_A]];
+      const float* w2 = W + t[CT_C2_WT] + ch;
+      for (int col = sub; col < V3; col += nsub) {
+        float acc = b2;
+        for (int r = 0; r < To; ++r) acc = fmaf(w2[r * pad8i(H)], z[r * V3 + col], acc);
+        mx2 = fmaxf(mx2, prelu(acc, a2));
+      }
+      if (sub < 4) { part1[sub * H + ch] = mx; part2[sub * H + ch] = mx2; part3[sub * H + ch] = sm; }
+    }
+    __syncthreads();
+    for (int ch = tid; ch < H; ch += NT) {
+      const int nsub = NT / H;
+      float mx = -INFINITY, mx2 = -INFINITY, sm = 0.f;
+      for (int s = 0; s < nsub; ++s) { mx = fmaxf(mx, part1[s * H + ch]); mx2 = fmaxf(mx2, part2[s * H + ch]); sm += part3[s * H + ch]; }
+      yv[ch] = mx; yv[H + ch] = mx2; yv[2 * H + ch] = sm / NZ;
+    }
+    __syncthreads();
+    for (int m = tid; m < 3 * To; m += NT) {                     // map{1,2,3}: Linear(H, Tout) + PReLU (:421-432, 468)
+      const int g = m / To, o = m - g * To;
+      const float* wt = W + t[CT_MAP_WT] + (size_t)g * H * Top + o;
+      float acc = 0.f;
+      for (int k = 0; k < H; ++k) acc = fmaf(wt[k * Top], yv[g * H + k], acc);
+      y[m] = prelu(acc, W[t[CT_MAP_A] + g]);
+    }
+    __syncthreads();
+    for (int m = tid; m < V + To; m += NT) {                     // fmap_s / fmap_t (+BN) (:434-440, 469-470)
+      float acc;
+      if (m < V) {
+        const float* wt = W + t[CT_FS_WT] + m;
+        acc = W[t[CT_FS_B] + m];
+        for (int k = 0; k < 3 * To; ++k) acc = fmaf(wt[k * pad8i(V)], y[k], acc);
+        joints[m] = acc;
+        if (a.tap_joints) a.tap_joints[(size_t)b * V + m] = acc;
+      } else {
+        const int o = m - V;
+        const float* wt = W + t[CT_FT_WT] + o;
+        acc = W[t[CT_FT_B] + o];
+        for (int k = 0; k < 3 * To; ++k) acc = fmaf(wt[k * Top], y[k], acc);
+        disp[o] = acc;
+        if (a.tap_disp) a.tap_disp[(size_t)b * To + o] = acc;
+      }
+    }
+    __syncthreads();
+    // ---- norm_map on seq_joints = disp (x) joints: Conv1d(k=1)+BN+PReLU, SE1d, Conv1d+BN+PReLU (:443-451, 471-472)
+    for (int i = tid; i < To * V; i += NT) {
+      const int fo = i / V, v = i - fo * V;
+      const float* wt = W + t[CT_N0_WT] + fo;
+      float acc = W[t[CT_N0_B] + fo];
+      const float jv = joints[v];
+      for (int f = 0; f < To; ++f) acc = fmaf(wt[f * Top], disp[f] * jv, acc);
+      n1[i] = prelu(acc, W[t[CT_N0_A]]);
+    }
+    __syncthreads();
+    for (int f = tid; f < To; f += NT) {
+      float s = 0.f;
+      for (int v = 0; v < V; ++v) s += n1[f * V + v];
+      mean1[f] = s / V;
+    }
+    __syncthreads();
+    for (int h = tid; h < S1; h += NT) {
+      const float* wt = W + t[CT_NSE1_WT] + h;
+      float acc = 0.f;
+      for (int f = 0; f < To; ++f) acc = fmaf(wt[f * pad8i(S1)], mean1[f], acc);
+      e1[h] = fmaxf(acc, 0.f);
+    }
+    __syncthreads();
+    for (int f = tid; f < To; f += NT) {
+      const float* wt = W + t[CT_NSE2_WT] + f;
+      float acc = 0.f;
+      for (int h = 0; h < S1; ++h) acc = fmaf(wt[h * Top], e1[h], acc);
+      gate1[f] = sigmoidf(acc);
+    }
+    __syncthreads();
+    for (int i = tid; i < To * V; i += NT) n1s[i] = n1[i] * gate1[i / V];
+    __syncthreads();
+    for (int i = tid; i < To * V; i += NT) {
+      const int fo = i / V, v = i - fo * V;
+      const float* wt = W + t[CT_N5_WT] + fo;
+      float acc = W[t[CT_N5_B] + fo];
+      for (int f = 0; f < To; ++f) acc = fmaf(wt[f * Top], n1s[f * V + v], acc);
+      const float val = prelu(acc, W[t[CT_N5_A]]);
+      n2[i] = val;
+      if (a.tap_sjn) a.tap_sjn[(size_t)b * To * V + i] = val;
+    }
+    __syncthreads();
+    // ---- fconv 1->3->3 (+BN+PReLU) (:454-460, 473)
+    for (int i = tid; i < To * V; i += NT) {
+      float f0[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) f0[k] = prelu(fmaf(W[t[CT_FC0_S] + k], n2[i], W[t[CT_FC0_B] + k]), W[t[CT_FC0_A]]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float acc = W[t[CT_FC3_B] + k];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc = fmaf(W[t[CT_FC3_WT] + j * 8 + k], f0[j], acc);
+        const float val = prelu(acc, W[t[CT_FC3_A]]);
+        f3[k * To * V + i] = val;
+        if (a.tap_sjd) a.tap_sjd[((size_t)b * 3 + k) * To * V + i] = val;
+      }
+    }
+    __syncthreads();
+    // ---- SE2d with the frames as channels (:461, 474)
+    for (int f = tid; f < To; f += NT) {
+      float s = 0.f;
+      for (int k = 0; k < 3; ++k)
+        for (int v = 0; v < V; ++v) s += f3[k * To * V + f * V + v];
+      mean2[f] = s / V3;
+    }
+    __syncthreads();
+    for (int h = tid; h < S2; h += NT) {
+      const float* wt = W + t[CT_SE1_WT] + h;
+      float acc = 0.f;
+      for (int f = 0; f < To; ++f) acc = fmaf(wt[f * pad8i(S2)], mean2[f], acc);
+      e2[h] = fmaxf(acc, 0.f);
+    }
+    __syncthreads();
+    for (int f = tid; f < To; f += NT) {
+      const float* wt = W + t[CT_SE2_WT] + f;
+      float acc = 0.f;
+      for (int h = 0; h < S2; ++h) acc = fmaf(wt[h * Top], e2[h], acc);
+      gate2[f] = sigmoidf(acc);
+    }
+    __syncthreads();
+    // ---- pred = x[:, -1:] + x8 + act (:595-597); optional per-frame MPJPE partial sums
+    {
+      const float* xl = a.x + ((size_t)b * Tin + (Tin - 1)) * V3;
+      const float* x8 = a.x8 + (size_t)b * NZ;
+      float* pr = a.pred + (size_t)b * NZ;
+      const float* tg = a.target ? a.target + (size_t)b * NZ : nullptr;
+      for (int i = tid; i < To * V; i += NT) {
+        const int f = i / V, v = i - f * V;
+        float e = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int idx = i * 3 + k;
+          const float act = f3[k * To * V + i] * gate2[f];
+          const float val = xl[v * 3 + k] + (x8[idx] + act);
+          pr[idx] = val;
+          if (tg) { const float dd = val - tg[idx]; e = fmaf(dd, dd, e); }
+        }
+        if (tg) atomicAdd(&fsum[f], sqrtf(e));
+      }
+    }
+    __syncthreads();
+    if (a.target && tid < To) facc += (double)fsum[tid];
+    __syncthreads();
+  }
+  if (a.target && a.frame_sums && tid < To) atomicAdd(&a.frame_sums[tid], facc);
+}
+
+// Stand-alone MPJPE: err (B,T,V) and / or per-frame sums.
+struct MpjpeArgs {
+  const float* pred;
+  const float* target;
+  float* err;
+  double* frame_sums;
+  long long n;      // B*T*V
+  int T, V;
+};
+
+__global__ void __launch_bounds__(256) mpjpe_kernel(const MpjpeArgs a) {
+  __shared__ double fs[64];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 64; i += 256) fs[i] = 0.0;
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * 256;
+  for (long long i = (long long)blockIdx.x * 256 + tid; i < a.n; i += stride) {
+    const float* p = a.pred + i * 3;
+    const float* q = a.target + i * 3;
+    const float d0 = p[0] - q[0], d1 = p[1] - q[1], d2 = p[2] - q[2];
+    const float e = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)));
+    if (a.err) a.err[i] = e;
+    if (a.frame_sums) {
+      const int f = (int)((i / a.V) % a.T);
+      if (a.T <= 64) atomicAdd(&fs[f], (double)e);
+      else atomicAdd(&a.frame_sums[f], (double)e);
+    }
+  }
+  __syncthreads();
+  if (a.frame_sums && a.T <= 64)
+    for (int i = tid; i < a.T; i += 256) atomicAdd(&a.frame_sums[i], fs[i]);
+}
+
+}  // namespace cg

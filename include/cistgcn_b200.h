@@ -35,6 +35,7 @@ extern "C" {
 #define CISTGCN_MPAD 8          /* output-dimension padding of every k-major matrix */
 #define CISTGCN_MAX_BLOCKS 8    /* input + output DSTD-GC blocks in one plan */
 #define CISTGCN_MAX_FPN 8
+#define CISTGCN_PROFILE_KINDS 4  /* 0 DSTD-GC block, 1 FPN chain, 2 context+assembly, 3 mpjpe */
 
 /* ---- one DSTD-GC block (CISTGCN.py:273-390).  *_S/_T pairs: index +0 = dsgn ("space" domain,
  *      TxT adjacency per joint), +1 = tsgn ("time" domain, VxV adjacency per frame). ---------- */
@@ -185,6 +186,13 @@ int cistgcn_tail_f32(const int32_t* tail_desc, const float* weights, const float
 /* mpjpe: err (optional): (B, T, V) per-joint L2 error; frame_sums (optional): double[T] accumulated. */
 int cistgcn_mpjpe_f32(const float* pred, const float* target, int64_t batch, int32_t T, int32_t V,
                       float* err, double* frame_sums, void* stream);
+
+/* Optional per-kernel timing for benchmarks (no reference counterpart).  While enabled every launch
+ * is bracketed by CUDA events on its stream; cistgcn_profile_read synchronises the device, sums the
+ * elapsed milliseconds and launch counts per kernel kind (arrays of CISTGCN_PROFILE_KINDS) and
+ * resets the counters.  Not thread-safe; leave disabled in production. */
+int cistgcn_profile_enable(int on);
+int cistgcn_profile_read(double* ms_by_kind, int64_t* launches_by_kind);
 
 #ifdef __cplusplus
 }

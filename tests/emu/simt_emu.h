@@ -1,0 +1,137 @@
+// SIMT emulator for kernel-logic tests on machines without a GPU.  TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the unmodified kernel sources of cistgcn_b200/csrc with g++ (-DCISTGCN_EMU) and runs one
+// CTA at a time with one OS thread per CUDA thread: __syncthreads() is a std::barrier, warp shuffles
+// go through a per-warp exchange buffer.  It exists so that `pytest -m "not gpu"` can check the
+// kernels' indexing and algebra against the oracle; it is never built into, loaded by, or reachable
+// from the cistgcn_b200 package (the product loads only the nvcc-built library and fails without it).
+#pragma once
+#include <atomic>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+struct uint3_emu { unsigned x, y, z; };
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(8) float2 { float x, y; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __launch_bounds__(...)
+#define __shared__ static
+
+namespace simt_emu {
+struct WarpCtx {
+  std::barrier<> bar{32};
+  uint64_t slot[32];
+};
+struct BlockCtx {
+  std::unique_ptr<std::barrier<>> bar;
+  std::vector<std::unique_ptr<WarpCtx>> warps;
+  void* smem = nullptr;
+};
+inline thread_local BlockCtx* tl_block = nullptr;
+inline thread_local WarpCtx* tl_warp = nullptr;
+inline thread_local int tl_lane = 0;
+inline void* dyn_smem() { return tl_block->smem; }
+}  // namespace simt_emu
+
+inline thread_local uint3_emu threadIdx{0, 0, 0};
+inline thread_local uint3_emu blockIdx{0, 0, 0};
+inline thread_local uint3_emu blockDim{1, 1, 1};
+inline thread_local uint3_emu gridDim{1, 1, 1};
+
+static inline void __syncthreads() { simt_emu::tl_block->bar->arrive_and_wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { simt_emu::tl_warp->bar.arrive_and_wait(); }
+
+template <class T>
+static inline T emu_shfl(T v, int src_lane) {
+  static_assert(sizeof(T) <= 8, "shuffle payload");
+  auto* w = simt_emu::tl_warp;
+  uint64_t raw = 0;
+  std::memcpy(&raw, &v, sizeof(T));
+  w->slot[simt_emu::tl_lane] = raw;
+  w->bar.arrive_and_wait();
+  uint64_t got = w->slot[src_lane & 31];
+  w->bar.arrive_and_wait();
+  T r;
+  std::memcpy(&r, &got, sizeof(T));
+  return r;
+}
+template <class T> static inline T __shfl_sync(unsigned, T v, int lane) { return emu_shfl(v, lane); }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_shfl(v, simt_emu::tl_lane ^ m); }
+template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) {
+  int s = simt_emu::tl_lane + d;
+  return emu_shfl(v, s < 32 ? s : simt_emu::tl_lane);
+}
+template <class T> static inline T __ldg(const T* p) { return *p; }
+
+static inline double atomicAdd(double* p, double v) {
+  auto* a = reinterpret_cast<std::atomic<uint64_t>*>(p);
+  uint64_t old = a->load();
+  for (;;) {
+    double cur;
+    std::memcpy(&cur, &old, 8);
+    double nv = cur + v;
+    uint64_t nraw;
+    std::memcpy(&nraw, &nv, 8);
+    if (a->compare_exchange_weak(old, nraw)) return cur;
+  }
+}
+static inline float atomicAdd(float* p, float v) {
+  auto* a = reinterpret_cast<std::atomic<uint32_t>*>(p);
+  uint32_t old = a->load();
+  for (;;) {
+    float cur;
+    std::memcpy(&cur, &old, 4);
+    float nv = cur + v;
+    uint32_t nraw;
+    std::memcpy(&nraw, &nv, 4);
+    if (a->compare_exchange_weak(old, nraw)) return cur;
+  }
+}
+
+namespace simt_emu {
+// Runs `body` for every (block, thread); blocks sequentially, threads of a block concurrently.
+inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body) {
+  const unsigned nt = block.x;
+  if (nt % 32 != 0) std::abort();
+  for (unsigned b = 0; b < grid.x; ++b) {
+    BlockCtx ctx;
+    ctx.bar = std::make_unique<std::barrier<>>(nt);
+    for (unsigned w = 0; w < nt / 32; ++w) ctx.warps.push_back(std::make_unique<WarpCtx>());
+    ctx.smem = std::aligned_alloc(128, ((smem_bytes + 127) / 128 + 1) * 128);
+    std::memset(ctx.smem, 0xCB, smem_bytes);  // poison: uninitialised shared memory shows up as NaN-ish junk
+    std::vector<std::thread> ts;
+    ts.reserve(nt);
+    for (unsigned t = 0; t < nt; ++t) {
+      ts.emplace_back([&, t]() {
+        tl_block = &ctx;
+        tl_warp = ctx.warps[t / 32].get();
+        tl_lane = int(t % 32);
+        threadIdx = {t, 0, 0};
+        blockIdx = {b, 0, 0};
+        blockDim = {nt, 1, 1};
+        gridDim = {grid.x, 1, 1};
+        body();
+      });
+    }
+    for (auto& th : ts) th.join();
+    std::free(ctx.smem);
+  }
+}
+}  // namespace simt_emu

@@ -1,6 +1,5 @@
 """Drop-in boundary: constructor, state_dict layout, init stream, packing."""
 import copy
-import types
 
 import pytest
 import torch
@@ -9,14 +8,9 @@ import _golden as G
 import _reference as R
 from cistgcn_b200 import CISTGCN
 from cistgcn_b200.pack import F
+from _models import make_opt
 
 
-def make_opt(E=8, V=22, interp=True):
-    ns = types.SimpleNamespace
-    mp = ns(input_n=10, output_n=25, joints=V, n_txcnn_layers=4, txc_kernel_size=3, reduction=8, hidden_dim=64,
-            input_gcn=ns(model_complexity=[E] * 4, interpretable=[interp] * 5),
-            output_gcn=ns(model_complexity=[3], interpretable=[interp]), clipping=15)
-    return ns(architecture_config=ns(model="CISTGCN_0", model_params=mp), learning_config=ns(dropout=0.1))
 
 
 @pytest.mark.parametrize("name", G.names())
