@@ -1,0 +1,158 @@
+"""Parity tests proper: the CUDA path, called through the drop-in module / C-ABI on a B200, against the
+committed golden vectors (reference outputs) and against the oracle on seeded inputs.
+
+Tolerances (BASELINE.md section 4 / SURVEY.md 8c): fp32 max-abs <= 1e-4 * max(1, |ref|_inf / 4) on the
+predicted coordinates; MPJPE agreement <= 1e-3 (same scale rule); intermediates rel 1e-4."""
+import pytest
+import torch
+
+import _golden as G
+import _models as M
+from cistgcn_b200 import CISTGCN, mpjpe
+from oracle import cistgcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _scale(ref):
+    return max(1.0, ref.abs().max().item() / 4)
+
+
+@pytest.mark.parametrize("name", G.names())
+def test_forward_matches_golden(name):
+    g = G.load(name)
+    opt = M.make_opt(g["embed"], g["cfg"].joints, g["interpretable"])
+    model = CISTGCN(opt.architecture_config, opt.learning_config).eval()
+    model.load_state_dict(g["sd"])
+    model = model.to(DEV).enable_taps()
+    out = model(g["x"].to(DEV))
+    assert isinstance(out, tuple) and len(out) == 1
+    pred = out[0].cpu()
+    assert (pred - g["pred"]).abs().max().item() <= G.tol(g["pred"])
+    for k, ref in g["taps"].items():
+        got = model.last_taps[k].cpu().reshape(ref.shape)
+        assert (got - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item()), k
+    _, sums = model.forward_mpjpe(g["x"].to(DEV), g["target"].to(DEV))
+    B, To, V = pred.shape[:3]
+    assert abs((sums.sum() / (B * To * V)).item() - g["mpjpe_all"].item()) <= 1e-3 * _scale(g["pred"])
+    assert torch.allclose((sums / (B * V)).float().cpu(), g["mpjpe_frames"], rtol=1e-5, atol=1e-3 * _scale(g["pred"]))
+
+
+@pytest.mark.parametrize("E,V,weights,scale", [
+    (8, 22, "W1", "unit"), (16, 22, "W2", "unit"), (32, 22, "W1", "unit"), (32, 22, "W2", "unit"),
+    (32, 22, "W1", "mm"), (64, 22, "W2", "unit"), (64, 18, "W2", "unit"), (64, 18, "W1", "mm"), (32, 18, "W2", "unit"),
+])
+def test_forward_matches_oracle(E, V, weights, scale):
+    model, sd, cfg = M.build(E, V, weights)
+    x, tgt = O.synth_inputs(48, cfg, scale=scale)
+    taps = {}
+    with torch.no_grad():
+        ref = O.forward(sd, cfg, x, taps=taps)
+    model = model.to(DEV).enable_taps()
+    pred, sums = model.forward_mpjpe(x.to(DEV), tgt.to(DEV))
+    pred = pred.cpu()
+    assert torch.isfinite(pred).all()
+    assert (pred - ref).abs().max().item() <= G.tol(ref)
+    assert abs((sums.sum() / (48 * 25 * V)).item() - O.mpjpe(ref, tgt).item()) <= 1e-3 * _scale(ref)
+    for k in ("st_gcnns.1.dsgn.Adj", "st_gcnns.3.tsgn.Adj", "st_gcnns.2.w1", "st_gcnns.4.w2",
+              "st_gcnns_o.0.dsgn.Adj", "st_gcnns_o.0.tsgn.Adj", "context_layer.joints", "context_layer.displacements"):
+        r = taps[k]
+        got = model.last_taps[k].cpu().reshape(r.shape)
+        assert (got - r).abs().max().item() <= 1e-4 * max(1.0, r.abs().max().item()), k
+
+
+def test_static_adjacency_variant():
+    model, sd, cfg = M.build(16, 22, "W2", interp=False)
+    x, _ = O.synth_inputs(16, cfg)
+    with torch.no_grad():
+        ref = O.forward(sd, cfg, x, interpretable_in=[False] * 5, interpretable_out=[False])
+    pred = model.to(DEV)(x.to(DEV))[0].cpu()
+    assert (pred - ref).abs().max().item() <= G.tol(ref)
+
+
+@pytest.mark.parametrize("B", [1, 2, 149, 297])
+def test_ragged_batch_sizes(B):
+    model, sd, cfg = M.build(8, 22, "W2")
+    x, _ = O.synth_inputs(B, cfg)
+    with torch.no_grad():
+        ref = O.forward(sd, cfg, x)
+    pred = model.to(DEV)(x.to(DEV))[0].cpu()
+    assert (pred - ref).abs().max().item() <= G.tol(ref)
+
+
+def test_empty_batch_and_errors():
+    model, _, cfg = M.build(8, 22)
+    model = model.to(DEV)
+    out = model(torch.zeros(0, 10, 22, 3, device=DEV))[0]
+    assert out.shape == (0, 25, 22, 3)
+    with pytest.raises(ValueError):
+        model(torch.zeros(2, 10, 22, 3))                           # host tensor: no CPU fallback
+    with pytest.raises(ValueError):
+        model(torch.zeros(2, 10, 18, 3, device=DEV))
+    model.train()
+    with pytest.raises(NotImplementedError):
+        model(torch.zeros(2, 10, 22, 3, device=DEV))
+
+
+def test_batch_independence_across_chunks():
+    """Size-independent property at a batch above the internal chunk (32768): every sample's output
+    depends on that sample only, so duplicating inputs across chunk boundaries must duplicate outputs,
+    and a random subset must match the oracle."""
+    model, sd, cfg = M.build(8, 22, "W2")
+    base, _ = O.synth_inputs(512, cfg)
+    B = 33000
+    idx = torch.arange(B) % 512
+    x = base[idx].contiguous()
+    pred = model.to(DEV)(x.to(DEV))[0]
+    first = pred[:512]
+    assert torch.equal(pred[512:1024], first)
+    assert torch.equal(pred[32768:32768 + 232], first[32768 % 512: 32768 % 512 + 232])
+    with torch.no_grad():
+        ref = O.forward(sd, cfg, base[:64])
+    assert (first[:64].cpu() - ref).abs().max().item() <= G.tol(ref)
+
+
+def test_full_size_batch_64k_e32():
+    """BASELINE configs[1] size (E=32, H36M shape, batch 65536): finite outputs, linear MPJPE bookkeeping
+    (sum of per-chunk frame sums == stand-alone MPJPE kernel), and a 64-sample spot check vs the oracle."""
+    model, sd, cfg = M.build(32, 22, "W1")
+    B = 65536
+    x, tgt = O.synth_inputs(B, cfg)
+    model = model.to(DEV)
+    xd, td = x.to(DEV), tgt.to(DEV)
+    pred, sums = model.forward_mpjpe(xd, td)
+    assert torch.isfinite(pred).all()
+    m_all = mpjpe(pred, td)
+    assert abs(m_all.item() - (sums.sum() / (B * 25 * 22)).item()) <= 1e-5
+    m_frames = mpjpe(pred, td, reduce_axis=(0, 2))
+    assert torch.allclose(m_frames.double(), sums / (B * 22), rtol=1e-6, atol=1e-6)
+    sel = torch.randperm(B, generator=torch.Generator().manual_seed(1))[:64]
+    with torch.no_grad():
+        ref = O.forward(sd, cfg, x[sel])
+    assert (pred[sel.to(DEV)].cpu() - ref).abs().max().item() <= G.tol(ref)
+
+
+def test_mpjpe_all_reductions():
+    g = torch.Generator().manual_seed(5)
+    p, t = torch.randn(257, 25, 22, 3, generator=g), torch.randn(257, 25, 22, 3, generator=g)
+    pd, td = p.to(DEV), t.to(DEV)
+    assert torch.allclose(mpjpe(pd, td, reduce_axis=None).cpu(), O.mpjpe(p, t, None), rtol=1e-6, atol=1e-6)
+    assert torch.allclose(mpjpe(pd, td).cpu(), O.mpjpe(p, t), rtol=1e-6, atol=1e-6)
+    assert torch.allclose(mpjpe(pd, td, reduce_axis=(0, 2)).cpu(), O.mpjpe(p, t, (0, 2)), rtol=1e-6, atol=1e-6)
+    with pytest.raises(AssertionError):
+        mpjpe(pd, td[:, :10])
+
+
+def test_load_state_dict_repacks():
+    model, sd, cfg = M.build(8, 22, "W1")
+    x, _ = O.synth_inputs(4, cfg)
+    model = model.to(DEV)
+    a = model(x.to(DEV))[0].clone()
+    sd2 = O.stress_init_({k: v.clone() for k, v in sd.items()})
+    model.load_state_dict(sd2)
+    b = model(x.to(DEV))[0]
+    with torch.no_grad():
+        ref = O.forward(sd2, cfg, x)
+    assert not torch.allclose(a, b)
+    assert (b.cpu() - ref).abs().max().item() <= G.tol(ref)
