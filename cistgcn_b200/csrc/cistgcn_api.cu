@@ -105,6 +105,7 @@ int grid_for(long long batch, int per_sm) {
 
 // ---------------------------------------------------------------------------------------------
 constexpr int DSTD_NT = 256;
+long long* g_phase_clocks = nullptr;   // debug hook, see cistgcn_debug_phase_clocks
 
 template <int T, int V>
 int launch_dstd_tv(const cg::DstdArgs& a, void* stream) {
@@ -131,8 +132,8 @@ int launch_dstd(const int32_t* desc, const float* weights, const float* in, floa
   if ((Co + 7) / 8 > DSTD_NT / 32) return fail(-2, "DSTD-GC block: Co = %d exceeds the %d supported", Co, 8 * (DSTD_NT / 32));
   if (a.d[CB_IN_MODE] == 1 && Ci != 10) return fail(-2, "feature-building input mode needs Ci == 10");
   if (!a.d[CB_INTERP]) { a.tap_adj_s = nullptr; a.tap_adj_t = nullptr; }
-  cg::dstd_plan(a);
-  if ((size_t)a.smem_floats * 4 > (size_t)kMaxSmemBytes)
+  a.phase_clocks = g_phase_clocks;
+  if (!cg::dstd_plan(a, DSTD_NT, kMaxSmemBytes / 4) || (size_t)a.smem_floats * 4 > (size_t)kMaxSmemBytes)
     return fail(-2, "DSTD-GC block (%d->%d, T=%d, V=%d) needs %zu B of shared memory (> %d)", Ci, Co, T, V,
                 (size_t)a.smem_floats * 4, kMaxSmemBytes);
   if (T == 10 && V == 22) return launch_dstd_tv<10, 22>(a, stream);
@@ -153,6 +154,7 @@ int launch_fpn(const int32_t* fpn_descs, int n_fpn, const int32_t* tail_desc, co
   const int To = a.t[CT_TOUT], V = a.t[CT_V], Tin = a.t[CT_TIN];
   if (To % 5 != 0) return fail(-2, "FPN chain: output_n = %d must be a multiple of 5", To);
   if (Tin > To) return fail(-2, "FPN chain: input_n > output_n unsupported");
+  if (a.t[CT_F] != 10) return fail(-2, "FPN chain: feature width %d unsupported (in_ch is fixed at 10)", a.t[CT_F]);
   for (int l = 0; l < n_fpn; ++l) {
     if (a.f[l][CF_COUT] != To || a.f[l][CF_CIN] != (l == 0 ? Tin : To)) return fail(-2, "FPN chain: layer %d channel mismatch", l);
   }
@@ -239,6 +241,11 @@ extern "C" {
 
 const char* cistgcn_last_error(void) { return g_err.c_str(); }
 int cistgcn_abi_version(void) { return CISTGCN_ABI_VERSION; }
+
+int cistgcn_debug_phase_clocks(void* device_buffer) {
+  g_phase_clocks = reinterpret_cast<long long*>(device_buffer);
+  return 0;
+}
 
 int cistgcn_profile_enable(int on) {
 #ifndef CISTGCN_EMU

@@ -1,25 +1,39 @@
 // Fused DSTD-GC block (reference: models/CISTGCN/CISTGCN.py:273-390, restated in SURVEY.md App. A).
 //
-// One CTA owns one sample at a time (persistent loop over the batch).  The sample's normalised
-// activation tile XN (Ci x T*V) stays resident in shared memory for the whole block; every stage
-// (statistics, context gates, Map2Adj adjacency generation, TxT / VxV adjacency products, 1x1 channel
-// mixes with folded BatchNorm + PReLU + residual, gating, compressor, squeeze-excitation, block
-// residual) reads and writes shared memory only.  HBM sees the tile once in and once out.
+// One persistent CTA per SM owns one sample at a time.  The sample's normalised activation tile XN
+// (Ci x T*V) stays resident in shared memory for the whole block; every stage (statistics, context
+// gates, Map2Adj adjacency generation, TxT / VxV adjacency products, 1x1 channel mixes with folded
+// BatchNorm + PReLU + residual, gating, compressor, squeeze-excitation, block residual) reads and
+// writes shared memory only.  HBM sees the tile once in and once out.
 //
-// Shared-memory map (floats; offsets come from dstd_plan()):
-//   XN  [Ci][TV]                      resident input tile (after global_norm)
-//   A   [Cmax][TV]  | B [..]          two work tiles: Map2Adj hidden maps -> g1/g2 -> u1/u2 -> c
-//                                     (B also hosts the expansor's hidden map "mid")
-//   ADJ [TV*max(T,V)]                 row statistics scratch, then o / Adj_s (stored [t][q][v]), then o / Adj_t
-//   SM                                small vectors (stats, gate activations, dseq/dsp, SE)
+// Weights: the CTA processes hundreds of samples with the same weights, so as many weight matrices
+// as fit are copied into shared memory ONCE per launch (host-side greedy plan, dstd_plan()); the
+// rest stream through a double-buffered cp.async ring (GEMM operands) or are read straight from L2
+// with wide split-K loads (single-use matvec operands).  No inner loop waits on an L2 round trip.
+//
+// Shared-memory map (floats):
+//   XN  [Ci][TV]          resident input tile (after global_norm)
+//   A | B [Cmax][TV]      work tiles: Map2Adj hidden maps -> g1/g2 -> u1/u2 -> c ; B also hosts the
+//                         expansor's hidden map
+//   ADJ [TV*max(T,V)]     row statistics / split-K partials, then o / Adj_s ([t][q][v]), then o / Adj_t
+//   SM                    small vectors (stats, gate activations, dseq/dsp, SE)
+//   RES                   resident weights;  RING  2 x ring_floats streaming slots
 #pragma once
 #include "../../include/cistgcn_b200.h"
 #include "simt.h"
 
 namespace cg {
 
+#ifdef CISTGCN_EMU
+#define CG_STAMP(i)
+#else
+#define CG_STAMP(i) do { if (a.phase_clocks && blockIdx.x == 0 && threadIdx.x == 0 && b == (int)blockIdx.x) a.phase_clocks[i] = clock64(); } while (0)
+#endif
+
 struct DstdArgs {
-  int d[CB_COUNT];
+  int d[CB_COUNT];       // descriptor; weight fields are float offsets into the blob
+  int res[CB_COUNT];     // shared-memory float offset of the resident copy of field f, or -1
+  int wsz[CB_COUNT];     // size in floats (multiple of 4) of weight field f, 0 if absent
   const float* w;
   const float* in;
   float* out;
@@ -28,163 +42,308 @@ struct DstdArgs {
   float* tap_w1;
   float* tap_w2;
   int batch;
-  int o_xn, o_ab, tile, o_adj, o_sm, smem_floats;
+  int o_xn, o_ab, tile, o_adj, o_sm, o_ring, ring_floats, smem_floats;
+  long long* phase_clocks;   // optional debug: first CTA / thread 0 stamps clock64() at phase boundaries
 };
 
 __host__ __device__ inline int pad4i(int n) { return (n + 3) & ~3; }
 __host__ __device__ inline int pad8i(int n) { return (n + 7) & ~7; }
 __host__ __device__ inline int imax(int a, int b) { return a > b ? a : b; }
+__host__ __device__ inline int imin(int a, int b) { return a < b ? a : b; }
 
-// Fills the shared-memory plan fields of `a` from the descriptor.
-inline void dstd_plan(DstdArgs& a) {
+// Host: sizes of every weight field, the shared-memory layout and the residency plan.
+// Returns false if even the mandatory small vectors do not fit.
+inline bool dstd_plan(DstdArgs& a, int nt, int max_smem_floats) {
   const int* d = a.d;
   const int Ci = d[CB_CI], Co = d[CB_CO], T = d[CB_T], V = d[CB_V], Ch = d[CB_CH], Cg = d[CB_CG], Hs = d[CB_HS];
-  const int TV = T * V, cmax = imax(Ci, Co), big = TV * imax(T, V);
+  const bool has_res = d[CB_HAS_RES] != 0, interp = d[CB_INTERP] != 0;
+  const int TV = T * V, cmax = imax(Ci, Co), big = TV * imax(T, V), Cop = pad8i(Co);
+  for (int f = 0; f < CB_COUNT; ++f) { a.wsz[f] = 0; a.res[f] = -1; }
+  int* z = a.wsz;
+  z[CB_GN_S] = z[CB_GN_B] = Ci;
+  z[CB_G0_WT] = Ci * T * pad8i(2 * Cg); z[CB_G0_B] = 2 * Cg; z[CB_G0_A] = 2;
+  z[CB_G4_WT] = 2 * Cg * V * Cop; z[CB_G4_B] = 2 * Co; z[CB_G4_A] = 2;
+  z[CB_M0_WT] = 2 * (Co + 2 + 2 * T) * Cop; z[CB_M0_B] = 2 * Co; z[CB_M0_A] = 2;
+  z[CB_M4_WT] = 2 * Co * Cop;
+  if (interp) {
+    z[CB_A0_WT] = Ci * pad8i(4 * Ch); z[CB_A0_B] = 4 * Ch; z[CB_A0_A] = 4;
+    for (int L = 0; L < 2; ++L) {
+      const int n = L == 0 ? V : T;
+      z[CB_TC3_WT_S + L] = Ch * T * pad8i(Ch); z[CB_TC3_B_S + L] = Ch; z[CB_TC6_WT_S + L] = Ch * pad8i(T);
+      z[CB_JC3_WT_S + L] = Ch * V * pad8i(Ch); z[CB_JC3_B_S + L] = Ch; z[CB_JC6_WT_S + L] = Ch * pad8i(V);
+      z[CB_E0_WT_S + L] = n * pad8i(n); z[CB_E0_B_S + L] = n; z[CB_E0_A_S + L] = 1; z[CB_E4_WT_S + L] = n * pad8i(n);
+    }
+  }
+  for (int L = 0; L < 2; ++L) {
+    z[CB_TCN_WT_S + L] = Ci * (has_res ? 2 : 1) * Cop; z[CB_TCN_B_S + L] = Co; z[CB_TCN_A_S + L] = 1;
+    z[CB_P_S_S + L] = Co; z[CB_P_B_S + L] = Co; z[CB_P_A_S + L] = 1;
+  }
+  z[CB_CP_WT] = 2 * Co * Cop; z[CB_CP_B] = Co; z[CB_CP_A] = 1;
+  z[CB_SE1_WT] = Co * pad8i(Hs); z[CB_SE2_WT] = Hs * Cop;
+  if (has_res) { z[CB_RS_WT] = Ci * Cop; z[CB_RS_B] = Co; }
+  for (int f = 0; f < CB_COUNT; ++f) z[f] = pad4i(z[f]);
+
   a.tile = pad4i(cmax * TV);
   a.o_xn = 0;
   a.o_ab = pad4i(Ci * TV);
-  const int ab = a.tile + imax(a.tile, pad4i(big));
-  a.o_adj = a.o_ab + ab;
-  const int adj = imax(pad4i(big), pad4i(2 * Ci * T + 2 * Ci));
+  a.o_adj = a.o_ab + a.tile + imax(a.tile, pad4i(big));
+  const int nw = nt / 32;
+  const int adj = imax(pad4i(big), imax(pad4i(2 * Ci * T + 2 * Ci), nw * 8 * 32 * 2));   // also hosts split-K partials
   a.o_sm = a.o_adj + adj;
-  const int sm = pad4i(2 + 2 * T) + pad4i(2 * Cg * V) + 3 * pad4i(2 * Co) + pad4i(2 * Ch * V) + pad4i(2 * Ch * T) +
+  const int sm = pad4i(2 + 2 * T) + imax(pad4i(2 * Cg * V), pad4i(2 * Ch * V) + pad4i(2 * Ch * T)) + 3 * pad4i(2 * Co) +
                  2 * pad4i(2 * TV) + 2 * pad4i(Co) + pad4i(Hs);
-  a.smem_floats = a.o_sm + sm;
+  a.o_ring = a.o_sm + sm;
+  int budget = max_smem_floats - a.o_ring;
+  a.ring_floats = budget >= 2 * 4096 + 8192 ? 4096 : (budget >= 2 * 2048 ? 2048 : 1024);
+  int cur = a.o_ring + 2 * a.ring_floats;
+  // residency: mandatory small operands first, then by benefit per byte
+  bool ok = true;
+  auto take = [&](int f, bool mandatory) {
+    if (a.wsz[f] == 0 || a.res[f] >= 0) return;
+    if (cur + a.wsz[f] <= max_smem_floats) { a.res[f] = cur; cur += a.wsz[f]; }
+    else if (mandatory) ok = false;
+  };
+  const int vectors[] = {CB_GN_S, CB_GN_B, CB_G0_B, CB_G0_A, CB_G4_B, CB_G4_A, CB_M0_B, CB_M0_A, CB_A0_B, CB_A0_A,
+                         CB_TC3_B_S, CB_TC3_B_T, CB_JC3_B_S, CB_JC3_B_T, CB_E0_B_S, CB_E0_B_T, CB_E0_A_S, CB_E0_A_T,
+                         CB_TCN_B_S, CB_TCN_B_T, CB_TCN_A_S, CB_TCN_A_T, CB_P_S_S, CB_P_S_T, CB_P_B_S, CB_P_B_T,
+                         CB_P_A_S, CB_P_A_T, CB_CP_B, CB_CP_A, CB_RS_B};
+  for (int f : vectors) take(f, true);
+  const int order[] = {CB_SE1_WT, CB_SE2_WT, CB_M0_WT, CB_M4_WT, CB_A0_WT, CB_TCN_WT_S, CB_TCN_WT_T, CB_CP_WT, CB_RS_WT, CB_E0_WT_S, CB_E0_WT_T,
+                       CB_E4_WT_S, CB_E4_WT_T, CB_TC6_WT_S, CB_TC6_WT_T, CB_JC6_WT_S, CB_JC6_WT_T, CB_G0_WT,
+                       CB_TC3_WT_S, CB_TC3_WT_T, CB_JC3_WT_S, CB_JC3_WT_T, CB_G4_WT};
+  for (int f : order) take(f, false);
+  a.smem_floats = cur;
+  return ok && cur <= max_smem_floats && a.ring_floats >= pad8i(4 * Ch) && a.ring_floats >= 2 * Cop;
 }
 
 // ---------------------------------------------------------------------------------------------
-// out(m, n) = sum_k Wt[k*Mp + m] * X(k, n), X given as up to two stacked row blocks in shared memory.
-// Work unit = one warp x (TM output rows) x (32*TN columns); lane owns columns nb + 32*j, so the
-// activation loads are conflict-free and the weight loads are warp-uniform broadcasts.
-// INPLACE: the epilogue may overwrite X; a pass then holds whole column groups only and every
-// thread meets the two barriers of every pass (requires ceil(M/TM) <= NT/32).
+// Weight delivery: body(wc, k0, kc) is called by every thread for consecutive row chunks
+// [k0, k0+kc) of a k-major matrix (row length Mp) with the rows available in shared memory at wc.
+// Resident matrices are one chunk with no barrier; streamed ones go through the cp.async ring
+// (chunk c+1 is in flight while chunk c is consumed; one barrier per chunk).
 // ---------------------------------------------------------------------------------------------
-template <int TM, int TN, int NT, bool INPLACE, class EPI>
-CG_DEV void gemm_rows(const float* __restrict__ Wt, int Mp, int M, int N,
-                      const float* X1, int ld1, int K1, const float* X2, int ld2, int K2, EPI epi) {
+template <int NT, class BODY>
+CG_DEV void for_weight_chunks(const float* __restrict__ g, const float* s, int K, int Mp, float* ring, int rb, BODY body) {
+  if (s != nullptr) { body(s, 0, K); return; }
+  const int kc = rb / Mp;
+  const int nch = (K + kc - 1) / kc;
+  copy_async<NT>(ring, g, imin(kc, K) * Mp);
+  cp_async_commit();
+  for (int c = 0; c < nch; ++c) {
+    cp_async_wait_all();
+    __syncthreads();
+    if (c + 1 < nch) {
+      copy_async<NT>(ring + ((c + 1) & 1) * rb, g + (size_t)(c + 1) * kc * Mp, imin(kc, K - (c + 1) * kc) * Mp);
+      cp_async_commit();
+    }
+    body(ring + (c & 1) * rb, c * kc, imin(kc, K - c * kc));
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Wide GEMM: out(m, n) = sum_k W[k][m] * X[k][n], X = up to two stacked row blocks (row stride LD) in
+// shared memory, N (a multiple of TN) columns.  Work unit = one warp x TM rows x 32 lanes x TN
+// contiguous columns: per k one vector LDS of activations (conflict-free) + TM/4 broadcast LDS.128
+// of weights feed TM*TN FFMAs.  INPLACE: the epilogue may overwrite X; a pass then holds whole column
+// groups and every thread meets the two barriers of the pass (needs ceil(M/TM) <= NT/32).
+// ---------------------------------------------------------------------------------------------
+template <int TM, int TN, int LD, int N, int NT, bool INPLACE, class EPI>
+CG_DEV void gemm_wide(const float* __restrict__ wg_, const float* ws, int Mp, int M,
+                      const float* X1, int K1, const float* X2, int K2, float* ring, int rb, EPI epi) {
+  static_assert(N % TN == 0 && LD % TN == 0, "gemm_wide: columns must tile by TN");
   constexpr int NW = NT / 32;
+  constexpr int NCOLS = N / TN;
+  constexpr int NG = (NCOLS + 31) / 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mtiles = (M + TM - 1) / TM;
-  const int ngroups = (N + 32 * TN - 1) / (32 * TN);
-  const int total = mtiles * ngroups;
+  const int total = mtiles * NG;
   const int per_pass = INPLACE ? (NW / mtiles) * mtiles : NW;
   for (int base = 0; base < total; base += per_pass) {
     const int item = base + warp;
-    const bool active = warp < per_pass && item < total;
+    const int slot = (item / mtiles) * 32 + lane;
+    const bool active = warp < per_pass && item < total && slot < NCOLS;
+    const int m0 = active ? (item % mtiles) * TM : 0;
+    const int n0 = active ? slot * TN : 0;
     float acc[TM][TN];
 #pragma unroll
     for (int i = 0; i < TM; ++i)
 #pragma unroll
       for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-    int m0 = 0, nb = lane;
-    if (active) {
-      m0 = (item % mtiles) * TM;
-      nb = (item / mtiles) * 32 * TN + lane;
-      const float* wp = Wt + m0;
-      int ncl[TN];
-#pragma unroll
-      for (int j = 0; j < TN; ++j) ncl[j] = (nb + 32 * j < N) ? nb + 32 * j : 0;   // clamp: keeps loads in range
+    auto run = [&](const float* xp, const float* wp, int n) {
 #pragma unroll 4
-      for (int k = 0; k < K1; ++k) {
+      for (int kk = 0; kk < n; ++kk) {
         float w[TM], x[TN];
-        load_vec<TM>(wp + (size_t)k * Mp, w);
-#pragma unroll
-        for (int j = 0; j < TN; ++j) x[j] = X1[k * ld1 + ncl[j]];
+        lds_vec<TM>(wp, w);
+        lds_vec<TN>(xp, x);
+        wp += Mp;
+        xp += LD;
 #pragma unroll
         for (int i = 0; i < TM; ++i)
 #pragma unroll
           for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(w[i], x[j], acc[i][j]);
       }
-      wp += (size_t)K1 * Mp;
-#pragma unroll 4
-      for (int k = 0; k < K2; ++k) {
-        float w[TM], x[TN];
-        load_vec<TM>(wp + (size_t)k * Mp, w);
-#pragma unroll
-        for (int j = 0; j < TN; ++j) x[j] = X2[k * ld2 + ncl[j]];
-#pragma unroll
-        for (int i = 0; i < TM; ++i)
-#pragma unroll
-          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(w[i], x[j], acc[i][j]);
-      }
-    }
+    };
+    for_weight_chunks<NT>(wg_, ws, K1 + K2, Mp, ring, rb, [&](const float* wc, int k0, int kc) {
+      if (!active) return;
+      int kb = k0, ke = imin(k0 + kc, K1);
+      if (kb < ke) run(X1 + kb * LD + n0, wc + (kb - k0) * Mp + m0, ke - kb);
+      kb = imax(k0, K1); ke = k0 + kc;
+      if (kb < ke) run(X2 + (kb - K1) * LD + n0, wc + (kb - k0) * Mp + m0, ke - kb);
+    });
     if (INPLACE) __syncthreads();
     if (active) {
 #pragma unroll
       for (int i = 0; i < TM; ++i)
+        if (m0 + i < M) {
 #pragma unroll
-        for (int j = 0; j < TN; ++j)
-          if (m0 + i < M && nb + 32 * j < N) epi(m0 + i, nb + 32 * j, acc[i][j]);
+          for (int j = 0; j < TN; ++j) epi(m0 + i, n0 + j, acc[i][j]);
+        }
     }
     if (INPLACE) __syncthreads();
   }
 }
 
-// Picks the widest column tile that still gives every warp work, then runs gemm_rows.
-template <int NT, bool INPLACE, class EPI>
-CG_DEV void gemm_rows_auto(const float* __restrict__ Wt, int Mp, int M, int N,
-                           const float* X1, int ld1, int K1, const float* X2, int ld2, int K2, EPI epi) {
+// Row-tile dispatch: the widest TM that still gives every warp a work unit.
+template <int TN, int LD, int N, int NT, bool INPLACE, class EPI>
+CG_DEV void gemm_wide_auto(const float* __restrict__ wg_, const float* ws, int Mp, int M,
+                           const float* X1, int K1, const float* X2, int K2, float* ring, int rb, EPI epi) {
   constexpr int NW = NT / 32;
-  const int mtiles = (M + 7) / 8;
-  if (mtiles * ((N + 127) / 128) >= NW)
-    gemm_rows<8, 4, NT, INPLACE>(Wt, Mp, M, N, X1, ld1, K1, X2, ld2, K2, epi);
-  else if (mtiles * ((N + 63) / 64) >= NW)
-    gemm_rows<8, 2, NT, INPLACE>(Wt, Mp, M, N, X1, ld1, K1, X2, ld2, K2, epi);
+  constexpr int NG = ((N / TN) + 31) / 32;
+  if (M % 16 == 0 && (M / 16) * NG >= NW)
+    gemm_wide<16, TN, LD, N, NT, INPLACE>(wg_, ws, Mp, M, X1, K1, X2, K2, ring, rb, epi);
+  else if (M > 32 || ((M + 7) / 8) * NG >= NW)
+    gemm_wide<8, TN, LD, N, NT, INPLACE>(wg_, ws, Mp, M, X1, K1, X2, K2, ring, rb, epi);
+  else if (M > 16 || ((M + 3) / 4) * NG >= NW)
+    gemm_wide<4, TN, LD, N, NT, INPLACE>(wg_, ws, Mp, M, X1, K1, X2, K2, ring, rb, epi);
   else
-    gemm_rows<8, 1, NT, INPLACE>(Wt, Mp, M, N, X1, ld1, K1, X2, ld2, K2, epi);
+    gemm_wide<2, TN, LD, N, NT, INPLACE>(wg_, ws, Mp, M, X1, K1, X2, K2, ring, rb, epi);
 }
 
 // ---------------------------------------------------------------------------------------------
-// Collapsing convolution ((R,1) or (1,R) kernels):
-//   out(m, n) = sum_{c<C, r<R} Wt[(c*R + r)*Mp + m] * X[c*ldc + r*N + n],   n < N (compile time).
-// Lane -> (m sub-tile, n): 32/N sub-tiles share a warp so short rows still fill the lanes.
-// `rot` rotates the warp assignment so that back-to-back calls land on different warps.
+// Narrow GEMM (the collapsing (T,1) / (1,V) convolutions: X is a [K][N] view of a [C][T*V] tile,
+// N = V or T <= 32):  out(m, n) = sum_k W[k][m] * X[k*N + n].
+// Lane -> (row sub-tile, TN-wide column slot); the K range is split over the warps that are left
+// once every row tile has a warp, partial sums meet in `partial` (>= NW*TM*64 floats).
+// Ends with a barrier; epi runs once per output.
 // ---------------------------------------------------------------------------------------------
 template <int TM, int N, int NT, class EPI>
-CG_DEV void kconv(const float* __restrict__ Wt, int Mp, int M, int C, int R,
-                  const float* X, int ldc, int rot, EPI epi) {
+CG_DEV void gemm_narrow(const float* __restrict__ wg_, const float* ws, int Mp, int M, int K,
+                        const float* X, float* partial, float* ring, int rb, EPI epi) {
+  static_assert(N <= 32, "gemm_narrow: row length must fit a warp");
   constexpr int NW = NT / 32;
-  constexpr int MS = (32 / N) > 0 ? (32 / N) : 1;
-  static_assert(N <= 32, "kconv: row length must fit a warp");
-  const int lane = threadIdx.x & 31;
-  const int warp = ((threadIdx.x >> 5) + NW - (rot % NW)) % NW;
-  const int msub = lane / N, n = lane % N;
-  const bool lane_ok = lane < MS * N;
+  constexpr int TN = (N % 2 == 0) ? 2 : 1;
+  constexpr int NP = N / TN;
+  constexpr int MS = 32 / NP;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int msub = lane / NP, np = lane - msub * NP;
   const int mtiles = (M + TM - 1) / TM;
-  const int witems = (mtiles + MS - 1) / MS;
-  for (int item = warp; item < witems; item += NW) {
-    const int mt = item * MS + msub;
-    const bool ok = lane_ok && mt < mtiles;
-    const int m0 = ok ? mt * TM : 0;
-    float acc[TM];
+  const int mgroups = (mtiles + MS - 1) / MS;
+  const int ksplit = imax(1, NW / mgroups);
+  for (int gbase = 0; gbase < mgroups; gbase += NW) {          // (one pass unless mgroups > NW)
+    const int mg = gbase + warp % imin(mgroups, NW);
+    const int ks = warp / imin(mgroups, NW);
+    const int mt = mg * MS + msub;
+    const bool active = ks < ksplit && mg < mgroups && lane < MS * NP && mt < mtiles;
+    const int m0 = active ? mt * TM : 0;
+    const int n0 = active ? np * TN : 0;
+    float acc[TM][TN];
 #pragma unroll
-    for (int i = 0; i < TM; ++i) acc[i] = 0.f;
-    for (int c = 0; c < C; ++c) {
-      const float* xp = X + c * ldc + n;
-      const float* wp = Wt + (size_t)(c * R) * Mp + m0;
-#pragma unroll 2
-      for (int r = 0; r < R; ++r) {
-        float w[TM];
-        load_vec<TM>(wp + (size_t)r * Mp, w);
-        const float x = xp[r * N];
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int i = 0; i < TM; ++i) acc[i] = fmaf(w[i], x, acc[i]);
+      for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for_weight_chunks<NT>(wg_, ws, K, Mp, ring, rb, [&](const float* wc, int k0, int kc) {
+      if (!active) return;
+      const int r0 = (kc * ks) / ksplit, r1 = (kc * (ks + 1)) / ksplit;
+      const float* wp = wc + r0 * Mp + m0;
+      const float* xp = X + (k0 + r0) * N + n0;
+#pragma unroll 4
+      for (int r = r0; r < r1; ++r) {
+        float w[TM], x[TN];
+        lds_vec<TM>(wp, w);
+        lds_vec<TN>(xp, x);
+        wp += Mp;
+        xp += N;
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(w[i], x[j], acc[i][j]);
       }
-    }
-    if (ok) {
+    });
+    if (ksplit == 1) {
+      if (active) {
 #pragma unroll
-      for (int i = 0; i < TM; ++i)
-        if (m0 + i < M) epi(m0 + i, n, acc[i]);
+        for (int i = 0; i < TM; ++i)
+          if (m0 + i < M) {
+#pragma unroll
+            for (int j = 0; j < TN; ++j) epi(m0 + i, n0 + j, acc[i][j]);
+          }
+      }
+      __syncthreads();
+    } else {
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+          if (m0 + i < M) {
+#pragma unroll
+            for (int j = 0; j < TN; ++j) partial[(ks * M + m0 + i) * N + n0 + j] = acc[i][j];
+          }
+      }
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < M * N; idx += NT) {
+        float s = 0.f;
+        for (int q = 0; q < ksplit; ++q) s += partial[q * M * N + idx];
+        epi(idx / N, idx % N, s);
+      }
+      __syncthreads();
     }
   }
 }
 
 template <int N, int NT, class EPI>
-CG_DEV void kconv_auto(const float* __restrict__ Wt, int Mp, int M, int C, int R,
-                       const float* X, int ldc, int rot, EPI epi) {
-  if (M >= 64) kconv<8, N, NT>(Wt, Mp, M, C, R, X, ldc, rot, epi);
-  else if (M >= 32) kconv<4, N, NT>(Wt, Mp, M, C, R, X, ldc, rot, epi);
-  else kconv<2, N, NT>(Wt, Mp, M, C, R, X, ldc, rot, epi);
+CG_DEV void gemm_narrow_auto(const float* __restrict__ wg_, const float* ws, int Mp, int M, int K,
+                             const float* X, float* partial, float* ring, int rb, EPI epi) {
+  if (M >= 16) gemm_narrow<8, N, NT>(wg_, ws, Mp, M, K, X, partial, ring, rb, epi);
+  else if (M >= 8) gemm_narrow<4, N, NT>(wg_, ws, Mp, M, K, X, partial, ring, rb, epi);
+  else gemm_narrow<2, N, NT>(wg_, ws, Mp, M, K, X, partial, ring, rb, epi);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two-gate matvec with split-K over warps: y[g][m] = sum_k W_g[k][m] * x_g[k] (+ optional tail rows
+// multiplying a second vector shared by both gates).  Weights come straight from L2 (or from their
+// resident copy): every lane owns output columns (coalesced 128-byte rows) and keeps UNR independent
+// loads in flight, so the single-use weight matrix streams at bandwidth instead of latency.
+// partial: >= NW * Mtot floats.  Ends with a barrier.
+// ---------------------------------------------------------------------------------------------
+template <int NT, class EPI>
+CG_DEV void gate_matvec(const float* wmat, int Mp, int M, int K1, const float* x1, int x1_stride,
+                        int K2, const float* x2, float* partial, EPI epi) {
+  constexpr int NW = NT / 32, HW = NW / 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = warp / HW, ks = warp % HW;
+  const int K = K1 + K2;
+  const int r0 = (K * ks) / HW, r1 = (K * (ks + 1)) / HW;
+  const float* wgt = wmat + (size_t)g * K * Mp;
+  const float* xa = x1 + g * x1_stride;
+  for (int mb = 0; mb < M; mb += 32) {
+    const int m = mb + lane;
+    const int mc = m < M ? m : M - 1;
+    float acc = 0.f;
+    const int e1 = imin(r1, K1);
+#pragma unroll 16
+    for (int k = r0; k < e1; ++k) acc = fmaf(wgt[(size_t)k * Mp + mc], xa[k], acc);
+#pragma unroll 16
+    for (int k = imax(r0, K1); k < r1; ++k) acc = fmaf(wgt[(size_t)k * Mp + mc], x2[k - K1], acc);
+    if (m < M) partial[(ks * 2 + g) * M + m] = acc;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 2 * M; idx += NT) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < HW; ++q) s += partial[q * 2 * M + idx];
+    epi(idx / M, idx % M, s);
+  }
+  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -202,6 +361,7 @@ CG_DEV void gcn_space(const float* XN, const float* adjT, float* G, int C) {
     for (int i = 0; i < TC; ++i)
 #pragma unroll
       for (int q = 0; q < T; ++q) acc[i][q] = 0.f;
+#pragma unroll 2
     for (int t = 0; t < T; ++t) {
       float xv[TC];
 #pragma unroll
@@ -236,6 +396,7 @@ CG_DEV void gcn_time(const float* XN, const float* adj, float* G, int C) {
     for (int i = 0; i < TC; ++i)
 #pragma unroll
       for (int j = 0; j < TW; ++j) acc[i][j] = 0.f;
+#pragma unroll 2
     for (int v = 0; v < V; ++v) {
       float xv[TC];
 #pragma unroll
@@ -259,9 +420,12 @@ CG_DEV void gcn_time(const float* XN, const float* adj, float* G, int C) {
 
 // ---------------------------------------------------------------------------------------------
 template <int T, int V, int NT>
-__global__ void __launch_bounds__(NT) dstd_block_kernel(const DstdArgs a) {
+__global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
   CG_DYN_SMEM(smem);
   constexpr int TV = T * V, TT = T * T, VV = V * V;
+  constexpr int TNW = (TV % 4 == 0) ? 4 : 2;            // column vector width of the wide GEMMs
+  constexpr int TNS = (TT % 4 == 0) ? 4 : 2;            // ... of the joint-axis expansor (N = T*T)
+  constexpr int TNT = (VV % 4 == 0) ? 4 : (VV % 2 == 0 ? 2 : 1);   // ... of the frame-axis expansor (N = V*V)
   const int tid = threadIdx.x;
   const int* d = a.d;
   const float* __restrict__ W = a.w;
@@ -273,34 +437,51 @@ __global__ void __launch_bounds__(NT) dstd_block_kernel(const DstdArgs a) {
   float* A = smem + a.o_ab;
   float* Bt = A + a.tile;
   float* ADJ = smem + a.o_adj;
+  float* ring = smem + a.o_ring;
+  const int rb = a.ring_floats;
   float* p = smem + a.o_sm;
   float* stats = p;   p += pad4i(2 + 2 * T);
-  float* h1 = p;      p += pad4i(2 * Cg * V);
+  float* h1 = p;                                    // gate hidden map; dead after P4, so it shares its slot
+  float* dseqp = p;                                 // with the Map2Adj collapsed maps of P6-P7
+  float* dspp = dseqp + pad4i(2 * Ch * V);
+  p += imax(pad4i(2 * Cg * V), pad4i(2 * Ch * V) + pad4i(2 * Ch * T));
   float* h2 = p;      p += pad4i(2 * Co);
   float* zg = p;      p += pad4i(2 * Co);
   float* wg = p;      p += pad4i(2 * Co);
-  float* dseqp = p;   p += pad4i(2 * Ch * V);
-  float* dspp = p;    p += pad4i(2 * Ch * T);
   float* dseq = p;    p += pad4i(2 * TV);
   float* dsp = p;     p += pad4i(2 * TV);
   float* semean = p;  p += pad4i(Co);
   float* gate = p;    p += pad4i(Co);
   float* hid = p;
-  // row statistics live in the (still unused) adjacency region
+  // row statistics / split-K partials live in the (still unused) adjacency region
   float* rowmean = ADJ;
   float* rowvar = rowmean + Ci * T;
   float* chmean = rowvar + Ci * T;
   float* chstd = chmean + Ci;
+  float* partial = ADJ;
+
+  // operand accessors: resident copy in shared memory if planned, else the global blob
+  auto RS = [&](int f) -> const float* { return a.res[f] >= 0 ? smem + a.res[f] : nullptr; };
+  auto P = [&](int f) -> const float* { return a.res[f] >= 0 ? smem + a.res[f] : W + d[f]; };
+  auto G = [&](int f) -> const float* { return W + d[f]; };
+
+  // ---------------- once per launch: resident weights -> shared memory
+  for (int f = 0; f < CB_COUNT; ++f)
+    if (a.res[f] >= 0) copy_async<NT>(smem + a.res[f], W + d[f], a.wsz[f]);
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
 
   for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
+    CG_STAMP(0);
     // ---------------- P1: load + global_norm (:375); block 0 builds the 10 features (:568-577)
     if (d[CB_IN_MODE] == 1) {
       const float* src = a.in + (size_t)b * d[CB_IN_SB];
       float* raw = A;
       for (int i = tid; i < TV * 3; i += NT) raw[i] = src[i];
       __syncthreads();
-      const float* gs = W + d[CB_GN_S];
-      const float* gb = W + d[CB_GN_B];
+      const float* gs = P(CB_GN_S);
+      const float* gb = P(CB_GN_B);
       for (int n = tid; n < TV; n += NT) {
         const int t = n / V;
         float f[10];
@@ -328,16 +509,28 @@ __global__ void __launch_bounds__(NT) dstd_block_kernel(const DstdArgs a) {
     } else {
       const float* src = a.in + (size_t)b * d[CB_IN_SB];
       const int sc = d[CB_IN_SC], st = d[CB_IN_ST], sv = d[CB_IN_SV];
-      const float* gs = W + d[CB_GN_S];
-      const float* gb = W + d[CB_GN_B];
-      for (int i = tid; i < Ci * TV; i += NT) {
-        const int c = i / TV, n = i - c * TV, t = n / V, v = n - t * V;
-        XN[i] = fmaf(gs[c], src[c * sc + t * st + v * sv], gb[c]);
+      const float* gs = P(CB_GN_S);
+      const float* gb = P(CB_GN_B);
+      if (sv == 1 && st == V && sc == TV && (TV % 4) == 0) {       // contiguous tile: 128-bit loads
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        for (int i = tid; i < Ci * TV / 4; i += NT) {
+          const int c = (i * 4) / TV;
+          float4 v4 = __ldg(s4 + i);
+          const float g0 = gs[c], b0 = gb[c];
+          v4.x = fmaf(g0, v4.x, b0); v4.y = fmaf(g0, v4.y, b0); v4.z = fmaf(g0, v4.z, b0); v4.w = fmaf(g0, v4.w, b0);
+          reinterpret_cast<float4*>(XN)[i] = v4;
+        }
+      } else {
+        for (int i = tid; i < Ci * TV; i += NT) {
+          const int c = i / TV, n = i - c * TV, t = n / V, v = n - t * V;
+          XN[i] = fmaf(gs[c], src[c * sc + t * st + v * sv], gb[c]);
+        }
       }
     }
     __syncthreads();
+    CG_STAMP(1);
 
-    // ---------------- P2: row statistics | gate conv (T,1) | Map2Adj first 1x1 convs  (all read XN only)
+    // ---------------- P2: statistics (:360-371), all Bessel-corrected like torch.std
     for (int r = tid; r < Ci * T; r += NT) {                  // r = c*T + t, row of V joints
       const float* xp = XN + (r / T) * TV + (r % T) * V;
       float s = 0.f;
@@ -348,30 +541,9 @@ __global__ void __launch_bounds__(NT) dstd_block_kernel(const DstdArgs a) {
 #pragma unroll
       for (int v = 0; v < V; ++v) { const float dd = xp[v] - mu; q = fmaf(dd, dd, q); }
       rowmean[r] = mu;
-      rowvar[r] = q / (V - 1);                                 // Bessel-corrected, like torch.std
-    }
-    {
-      const float* gb = W + d[CB_G0_B];
-      const float* ga = W + d[CB_G0_A];
-      kconv_auto<V, NT>(W + d[CB_G0_WT], pad8i(2 * Cg), 2 * Cg, Ci, T, XN, TV, 0,
-                        [&](int m, int v, float acc) { h1[m * V + v] = prelu(acc + gb[m], ga[m / Cg]); });
-    }
-    if (interp) {
-      const float* ab = W + d[CB_A0_B];
-      const float* aa = W + d[CB_A0_A];
-      gemm_rows<8, 2, NT, false>(W + d[CB_A0_WT], pad8i(4 * Ch), 4 * Ch, TV, XN, TV, Ci, nullptr, 0, 0,
-                                 [&](int m, int n, float acc) {
-                                   const int br = m / Ch, r = m - br * Ch;
-                                   const float val = prelu(acc + ab[m], aa[br]);
-                                   float* tl = A + (br >> 1) * a.tile;
-                                   if ((br & 1) == 0) tl[r * TV + n] = val;                // time_compress map  [c][t][v]
-                                   else { const int t = n / V, v = n - t * V;
-                                          tl[(Ch + r) * TV + v * T + t] = val; }           // joint_compress map [c][v][t]
-                                 });
+      rowvar[r] = q / (V - 1);
     }
     __syncthreads();
-
-    // ---------------- P3: channel statistics | gate conv (1,V) | Map2Adj collapsing convs
     for (int c = tid; c < Ci; c += NT) {
       float s = 0.f;
       for (int t = 0; t < T; ++t) s += rowmean[c * T + t];
@@ -390,31 +562,7 @@ __global__ void __launch_bounds__(NT) dstd_block_kernel(const DstdArgs a) {
       stats[1 + t] = s / Ci;
       stats[2 + T + t] = sqrtf(q / (Ci - 1));
     }
-    for (int m = tid; m < 2 * Co; m += NT) {
-      const int g = m / Co, o = m - g * Co, K = Cg * V;
-      const float* wt = W + d[CB_G4_WT] + (size_t)g * K * Cop + o;
-      const float* hp = h1 + g * K;
-      float acc = 0.f;
-      for (int k = 0; k < K; ++k) acc = fmaf(wt[(size_t)k * Cop], hp[k], acc);
-      h2[m] = prelu(acc + W[d[CB_G4_B] + m], W[d[CB_G4_A] + g]);
-    }
-    if (interp) {
-#pragma unroll
-      for (int L = 0; L < 2; ++L) {
-        const float* tl = A + L * a.tile;
-        const float* tb = W + d[CB_TC3_B_S + L];
-        const float* jb = W + d[CB_JC3_B_S + L];
-        float* dq = dseqp + L * Ch * V;
-        float* dp = dspp + L * Ch * T;
-        kconv_auto<V, NT>(W + d[CB_TC3_WT_S + L], pad8i(Ch), Ch, Ch, T, tl, TV, 2 + 3 * L,
-                          [&](int m, int v, float acc) { dq[m * V + v] = acc + tb[m]; });
-        kconv_auto<T, NT>(W + d[CB_JC3_WT_S + L], pad8i(Ch), Ch, Ch, V, tl + Ch * TV, TV, 4 + 3 * L,
-                          [&](int m, int t, float acc) { dp[m * T + t] = acc + jb[m]; });
-      }
-    }
     __syncthreads();
-
-    // ---------------- P4: scalar statistics + gate MLP layer 0 | dim_seq / dim_space
     if (tid == 0) {
       float s = 0.f, s2 = 0.f;
       for (int c = 0; c < Ci; ++c) { s += chmean[c]; s2 += chstd[c]; }
@@ -424,10 +572,71 @@ __global__ void __launch_bounds__(NT) dstd_block_kernel(const DstdArgs a) {
       stats[0] = s / Ci;
       stats[1 + T] = sqrtf(q / (Ci - 1));
     }
+    __syncthreads();      // row statistics are dead from here on: ADJ becomes split-K scratch
+    CG_STAMP(2);
+
+    // ---------------- P3: gate conv (T,1) + BN + PReLU -> h1  (:323-326)
+    {
+      const float* gb = P(CB_G0_B);
+      const float* ga = P(CB_G0_A);
+      gemm_narrow_auto<V, NT>(G(CB_G0_WT), RS(CB_G0_WT), pad8i(2 * Cg), 2 * Cg, Ci * T, XN, partial, ring, rb,
+                              [&](int m, int v, float acc) { h1[m * V + v] = prelu(acc + gb[m], ga[m / Cg]); });
+    }
+    CG_STAMP(3);
+    // ---------------- P4: gate conv (1,V) -> h2 ; MLP -> w1, w2  (:327-352, 378-384)
+    {
+      const float* b4 = P(CB_G4_B);
+      const float* a4 = P(CB_G4_A);
+      gate_matvec<NT>(P(CB_G4_WT), Cop, Co, Cg * V, h1, Cg * V, 0, nullptr, partial,
+                      [&](int g, int o, float acc) { h2[g * Co + o] = prelu(acc + b4[g * Co + o], a4[g]); });
+      const float* b0 = P(CB_M0_B);
+      const float* a0 = P(CB_M0_A);
+      gate_matvec<NT>(P(CB_M0_WT), Cop, Co, Co, h2, Co, 2 + 2 * T, stats, partial,
+                      [&](int g, int o, float acc) { zg[g * Co + o] = prelu(acc + b0[g * Co + o], a0[g]); });
+      gate_matvec<NT>(P(CB_M4_WT), Cop, Co, Co, zg, Co, 0, nullptr, partial,
+                      [&](int g, int o, float acc) {
+                        wg[g * Co + o] = acc;
+                        float* tp = g == 0 ? a.tap_w1 : a.tap_w2;
+                        if (tp) tp[(size_t)b * Co + o] = acc;
+                      });
+    }
+    CG_STAMP(4);
+
     if (interp) {
+      // ---------------- P5: Map2Adj first 1x1 convs (4 stacked) + BN + PReLU -> A (dsgn maps), B (tsgn maps)
+      {
+        const float* ab = P(CB_A0_B);
+        const float* aa = P(CB_A0_A);
+        gemm_wide_auto<TNW, TV, TV, NT, false>(G(CB_A0_WT), RS(CB_A0_WT), pad8i(4 * Ch), 4 * Ch, XN, Ci, nullptr, 0, ring, rb,
+                                               [&](int m, int n, float acc) {
+                                                 const int br = m / Ch, r = m - br * Ch;
+                                                 const float val = prelu(acc + ab[m], aa[br]);
+                                                 float* tl = A + (br >> 1) * a.tile;
+                                                 if ((br & 1) == 0) tl[r * TV + n] = val;          // time_compress map  [c][t][v]
+                                                 else { const int t = n / V, v = n - t * V;
+                                                        tl[(Ch + r) * TV + v * T + t] = val; }     // joint_compress map [c][v][t]
+                                               });
+      }
+      __syncthreads();
+      CG_STAMP(5);
+      // ---------------- P6: collapsing convs (T,1) / (1,V) + BN  (:141-142, 149-150)
+#pragma unroll
+      for (int L = 0; L < 2; ++L) {
+        const float* tl = A + L * a.tile;
+        const float* tb = P(CB_TC3_B_S + L);
+        const float* jb = P(CB_JC3_B_S + L);
+        float* dq = dseqp + L * Ch * V;
+        float* dp = dspp + L * Ch * T;
+        gemm_narrow_auto<V, NT>(G(CB_TC3_WT_S + L), RS(CB_TC3_WT_S + L), pad8i(Ch), Ch, Ch * T, tl, partial, ring, rb,
+                                [&](int m, int v, float acc) { dq[m * V + v] = acc + tb[m]; });
+        gemm_narrow_auto<T, NT>(G(CB_JC3_WT_S + L), RS(CB_JC3_WT_S + L), pad8i(Ch), Ch, Ch * V, tl + Ch * TV, partial, ring, rb,
+                                [&](int m, int t, float acc) { dp[m * T + t] = acc + jb[m]; });
+      }
+      CG_STAMP(6);
+      // ---------------- P7: dim_seq / dim_space (last 1x1 of each compress branch)  (:144, 152)
       for (int i = tid; i < 2 * TV; i += NT) {                // dim_seq[L][t'][v] = sum_o W6[o][t'] * dseqp[L][o][v]
         const int L = i / TV, r = i - L * TV, tq = r / V, v = r - tq * V;
-        const float* wt = W + d[CB_TC6_WT_S + L] + tq;
+        const float* wt = P(CB_TC6_WT_S + L) + tq;
         const float* xp = dseqp + L * Ch * V + v;
         float acc = 0.f;
         for (int o = 0; o < Ch; ++o) acc = fmaf(wt[o * pad8i(T)], xp[o * V], acc);
@@ -435,63 +644,46 @@ __global__ void __launch_bounds__(NT) dstd_block_kernel(const DstdArgs a) {
       }
       for (int i = tid; i < 2 * TV; i += NT) {                // dim_space[L][v'][t] = sum_o W6[o][v'] * dspp[L][o][t]
         const int L = i / TV, r = i - L * TV, vq = r / T, t = r - vq * T;
-        const float* wt = W + d[CB_JC6_WT_S + L] + vq;
+        const float* wt = P(CB_JC6_WT_S + L) + vq;
         const float* xp = dspp + L * Ch * T + t;
         float acc = 0.f;
         for (int o = 0; o < Ch; ++o) acc = fmaf(wt[o * pad8i(V)], xp[o * T], acc);
         dsp[i] = acc;
       }
-    }
-    __syncthreads();
-    for (int m = tid; m < 2 * Co; m += NT) {                  // map_{s,t}.0 on cat(h2, stats)  (:341-344, 378, 380)
-      const int g = m / Co, o = m - g * Co;
-      const float* wt = W + d[CB_M0_WT] + (size_t)g * (Co + 2 + 2 * T) * Cop + o;
-      float acc = 0.f;
-      for (int k = 0; k < Co; ++k) acc = fmaf(wt[(size_t)k * Cop], h2[g * Co + k], acc);
-      for (int k = 0; k < 2 + 2 * T; ++k) acc = fmaf(wt[(size_t)(Co + k) * Cop], stats[k], acc);
-      zg[m] = prelu(acc + W[d[CB_M0_B] + m], W[d[CB_M0_A] + g]);
-    }
-    // ---------------- P5: space-domain outer product o[v'][t][q] = dsp[v'][t] * dseq[q][v']  (:187)
-    if (interp) {
+      __syncthreads();
+      // ---------------- P8: space-domain outer product o[v'][t][q] = dsp[v'][t] * dseq[q][v']  (:187)
       for (int i = tid; i < V * TT; i += NT) {
         const int vq = i / TT, r = i - vq * TT, t = r / T, q = r - t * T;
         ADJ[i] = dsp[vq * T + t] * dseq[q * V + vq];
       }
-    } else {
-      const float* as = W + d[CB_ADJ_S];                      // static (V,T,T) -> [t][q][v]
-      for (int i = tid; i < V * TT; i += NT) { const int v = i / TT, r = i - v * TT; ADJ[r * V + v] = as[i]; }
-    }
-    __syncthreads();
-    for (int m = tid; m < 2 * Co; m += NT) {                  // map_{s,t}.4 -> gates w1, w2 (:345, 381-382)
-      const int g = m / Co, o = m - g * Co;
-      const float* wt = W + d[CB_M4_WT] + (size_t)g * Co * Cop + o;
-      float acc = 0.f;
-      for (int k = 0; k < Co; ++k) acc = fmaf(wt[(size_t)k * Cop], zg[g * Co + k], acc);
-      wg[m] = acc;
-      float* tp = g == 0 ? a.tap_w1 : a.tap_w2;
-      if (tp) tp[(size_t)b * Co + o] = acc;
-    }
-    // ---------------- P6/P7: expansor over the joint axis -> Adj_s (kept as [t][q][v])
-    if (interp) {
+      __syncthreads();
+      CG_STAMP(7);
+      // ---------------- P9: expansor over the joint axis -> Adj_s (kept as [t][q][v])  (:165-170)
       {
-        const float* eb = W + d[CB_E0_B_S];
-        const float ea = W[d[CB_E0_A_S]];
-        gemm_rows<8, 1, NT, false>(W + d[CB_E0_WT_S], pad8i(V), V, TT, ADJ, TT, V, nullptr, 0, 0,
-                                   [&](int m, int n, float acc) { Bt[m * TT + n] = prelu(acc + eb[m], ea); });
+        const float* eb = P(CB_E0_B_S);
+        const float ea = P(CB_E0_A_S)[0];
+        gemm_wide_auto<TNS, TT, TT, NT, false>(G(CB_E0_WT_S), RS(CB_E0_WT_S), pad8i(V), V, ADJ, V, nullptr, 0, ring, rb,
+                                               [&](int m, int n, float acc) { Bt[m * TT + n] = prelu(acc + eb[m], ea); });
       }
       __syncthreads();
       {
         float* tp = a.tap_adj_s ? a.tap_adj_s + (size_t)b * V * TT : nullptr;
-        gemm_rows<8, 1, NT, false>(W + d[CB_E4_WT_S], pad8i(V), V, TT, Bt, TT, V, nullptr, 0, 0,
-                                   [&](int m, int n, float acc) { ADJ[n * V + m] = acc; if (tp) tp[m * TT + n] = acc; });
+        gemm_wide_auto<TNS, TT, TT, NT, false>(G(CB_E4_WT_S), RS(CB_E4_WT_S), pad8i(V), V, Bt, V, nullptr, 0, ring, rb,
+                                               [&](int m, int n, float acc) { ADJ[n * V + m] = acc; if (tp) tp[m * TT + n] = acc; });
       }
       __syncthreads();
+    } else {
+      const float* as = W + d[CB_ADJ_S];                      // static (V,T,T) -> [t][q][v]
+      for (int i = tid; i < V * TT; i += NT) { const int v = i / TT, r = i - v * TT; ADJ[r * V + v] = as[i]; }
+      __syncthreads();
     }
-    // ---------------- P8: g1 = XN x_t Adj_s -> A
+    CG_STAMP(8);
+    // ---------------- P10: g1 = XN x_t Adj_s -> A
     if (Ci >= 4) gcn_space<T, V, 4, NT>(XN, ADJ, A, Ci);
     else gcn_space<T, V, 1, NT>(XN, ADJ, A, Ci);
     __syncthreads();
-    // ---------------- P9-P11: time-domain outer product + expansor over the frame axis -> Adj_t
+    CG_STAMP(9);
+    // ---------------- P11: time-domain outer product + expansor over the frame axis -> Adj_t
     if (interp) {
       for (int i = tid; i < T * VV; i += NT) {                // o[t'][v][w] = dsp[v][t'] * dseq[t'][w]
         const int tq = i / VV, r = i - tq * VV, v = r / V, w = r - v * V;
@@ -499,52 +691,56 @@ __global__ void __launch_bounds__(NT) dstd_block_kernel(const DstdArgs a) {
       }
       __syncthreads();
       {
-        const float* eb = W + d[CB_E0_B_T];
-        const float ea = W[d[CB_E0_A_T]];
-        gemm_rows<4, 2, NT, false>(W + d[CB_E0_WT_T], pad8i(T), T, VV, ADJ, VV, T, nullptr, 0, 0,
-                                   [&](int m, int n, float acc) { Bt[m * VV + n] = prelu(acc + eb[m], ea); });
+        const float* eb = P(CB_E0_B_T);
+        const float ea = P(CB_E0_A_T)[0];
+        gemm_wide_auto<TNT, VV, VV, NT, false>(G(CB_E0_WT_T), RS(CB_E0_WT_T), pad8i(T), T, ADJ, T, nullptr, 0, ring, rb,
+                                               [&](int m, int n, float acc) { Bt[m * VV + n] = prelu(acc + eb[m], ea); });
       }
       __syncthreads();
       {
         float* tp = a.tap_adj_t ? a.tap_adj_t + (size_t)b * T * VV : nullptr;
-        gemm_rows<4, 2, NT, false>(W + d[CB_E4_WT_T], pad8i(T), T, VV, Bt, VV, T, nullptr, 0, 0,
-                                   [&](int m, int n, float acc) { ADJ[m * VV + n] = acc; if (tp) tp[m * VV + n] = acc; });
+        gemm_wide_auto<TNT, VV, VV, NT, false>(G(CB_E4_WT_T), RS(CB_E4_WT_T), pad8i(T), T, Bt, T, nullptr, 0, ring, rb,
+                                               [&](int m, int n, float acc) { ADJ[m * VV + n] = acc; if (tp) tp[m * VV + n] = acc; });
       }
     } else {
       const float* at = W + d[CB_ADJ_T];
       for (int i = tid; i < T * VV; i += NT) ADJ[i] = at[i];
     }
     __syncthreads();
+    CG_STAMP(10);
     // ---------------- P12: g2 = XN x_v Adj_t -> B
     if (Ci >= 4) gcn_time<T, V, 4, NT>(XN, ADJ, Bt, Ci);
     else gcn_time<T, V, 1, NT>(XN, ADJ, Bt, Ci);
     __syncthreads();
+    CG_STAMP(11);
     // ---------------- P13: x_k = PReLU(BN(W g_k + b) + res); u_k = PReLU(BN(w_k * x_k))   (:266-268, 388)
 #pragma unroll
     for (int L = 0; L < 2; ++L) {
-      float* G = L == 0 ? A : Bt;
-      const float* tb = W + d[CB_TCN_B_S + L];
-      const float ta = W[d[CB_TCN_A_S + L]];
-      const float* ps = W + d[CB_P_S_S + L];
-      const float* pb = W + d[CB_P_B_S + L];
-      const float pa = W[d[CB_P_A_S + L]];
+      float* Gt = L == 0 ? A : Bt;
+      const float* tb = P(CB_TCN_B_S + L);
+      const float ta = P(CB_TCN_A_S + L)[0];
+      const float* ps = P(CB_P_S_S + L);
+      const float* pb = P(CB_P_B_S + L);
+      const float pa = P(CB_P_A_S + L)[0];
       const float* wk = wg + L * Co;
-      gemm_rows_auto<NT, true>(W + d[CB_TCN_WT_S + L], Cop, Co, TV, G, TV, Ci, XN, TV, has_res ? Ci : 0,
-                               [&](int m, int n, float acc) {
-                                 float v = acc + tb[m];
-                                 if (!has_res) v += XN[m * TV + n];
-                                 v = prelu(v, ta);
-                                 v = fmaf(ps[m], wk[m] * v, pb[m]);
-                                 G[m * TV + n] = prelu(v, pa);
-                               });
+      gemm_wide_auto<TNW, TV, TV, NT, true>(G(CB_TCN_WT_S + L), RS(CB_TCN_WT_S + L), Cop, Co, Gt, Ci, XN, has_res ? Ci : 0, ring, rb,
+                                            [&](int m, int n, float acc) {
+                                              float v = acc + tb[m];
+                                              if (!has_res) v += XN[m * TV + n];
+                                              v = prelu(v, ta);
+                                              v = fmaf(ps[m], wk[m] * v, pb[m]);
+                                              Gt[m * TV + n] = prelu(v, pa);
+                                            });
     }
+    CG_STAMP(12);
     // ---------------- P14: compressor 1x1 over cat(u1, u2) + BN + PReLU -> A   (:305-307)
     {
-      const float* cb = W + d[CB_CP_B];
-      const float ca = W[d[CB_CP_A]];
-      gemm_rows_auto<NT, true>(W + d[CB_CP_WT], Cop, Co, TV, A, TV, Co, Bt, TV, Co,
-                               [&](int m, int n, float acc) { A[m * TV + n] = prelu(acc + cb[m], ca); });
+      const float* cb = P(CB_CP_B);
+      const float ca = P(CB_CP_A)[0];
+      gemm_wide_auto<TNW, TV, TV, NT, true>(G(CB_CP_WT), RS(CB_CP_WT), Cop, Co, A, Co, Bt, Co, ring, rb,
+                                            [&](int m, int n, float acc) { A[m * TV + n] = prelu(acc + cb[m], ca); });
     }
+    CG_STAMP(13);
     // ---------------- P15-P17: squeeze-excitation (SE.py:37-41)
     for (int m = tid >> 5; m < Co; m += NT / 32) {
       float s = 0.f;
@@ -554,30 +750,39 @@ __global__ void __launch_bounds__(NT) dstd_block_kernel(const DstdArgs a) {
     }
     __syncthreads();
     for (int h = tid; h < Hs; h += NT) {
-      const float* wt = W + d[CB_SE1_WT] + h;
+      const float* wt = P(CB_SE1_WT) + h;
       float acc = 0.f;
       for (int c = 0; c < Co; ++c) acc = fmaf(wt[c * pad8i(Hs)], semean[c], acc);
       hid[h] = fmaxf(acc, 0.f);
     }
     __syncthreads();
     for (int o = tid; o < Co; o += NT) {
-      const float* wt = W + d[CB_SE2_WT] + o;
+      const float* wt = P(CB_SE2_WT) + o;
       float acc = 0.f;
       for (int h = 0; h < Hs; ++h) acc = fmaf(wt[h * Cop], hid[h], acc);
       gate[o] = sigmoidf(acc);
     }
     __syncthreads();
+    CG_STAMP(14);
     // ---------------- P18: out = c * gate + residual(xn)   (:390)
     {
       float* dst = a.out + (size_t)b * d[CB_OUT_SB];
       const int sc = d[CB_OUT_SC], st = d[CB_OUT_ST], sv = d[CB_OUT_SV];
       if (has_res) {
-        const float* rb = W + d[CB_RS_B];
-        gemm_rows<8, 2, NT, false>(W + d[CB_RS_WT], Cop, Co, TV, XN, TV, Ci, nullptr, 0, 0,
-                                   [&](int m, int n, float acc) {
-                                     const int t = n / V, v = n - t * V;
-                                     dst[m * sc + t * st + v * sv] = fmaf(A[m * TV + n], gate[m], acc + rb[m]);
-                                   });
+        const float* rbias = P(CB_RS_B);
+        gemm_wide_auto<TNW, TV, TV, NT, false>(G(CB_RS_WT), RS(CB_RS_WT), Cop, Co, XN, Ci, nullptr, 0, ring, rb,
+                                               [&](int m, int n, float acc) {
+                                                 const int t = n / V, v = n - t * V;
+                                                 dst[m * sc + t * st + v * sv] = fmaf(A[m * TV + n], gate[m], acc + rbias[m]);
+                                               });
+      } else if (sv == 1 && st == V && sc == TV && (TV % 4) == 0) {
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int i = tid; i < Co * TV / 4; i += NT) {
+          const float gm = gate[(i * 4) / TV];
+          const float4 c4 = reinterpret_cast<const float4*>(A)[i];
+          const float4 x4 = reinterpret_cast<const float4*>(XN)[i];
+          d4[i] = make_float4(fmaf(c4.x, gm, x4.x), fmaf(c4.y, gm, x4.y), fmaf(c4.z, gm, x4.z), fmaf(c4.w, gm, x4.w));
+        }
       } else {
         for (int i = tid; i < Co * TV; i += NT) {
           const int m = i / TV, n = i - m * TV, t = n / V, v = n - t * V;
@@ -586,6 +791,7 @@ __global__ void __launch_bounds__(NT) dstd_block_kernel(const DstdArgs a) {
       }
     }
     __syncthreads();
+    CG_STAMP(15);
   }
 }
 

@@ -1,15 +1,18 @@
 // Time-extrapolator stack: 4 x FPN (CISTGCN.py:38-79) with the caller's PReLU / residual (:584-586),
 // then dim_conversor (:541-545) and the cumulative sum over output frames (:588-589), one kernel.
 //
-// Frames are the channel axis here; the 2-D map is (H = 10 feature rows) x (W = V joints).
-// One CTA owns one sample at a time.  The sample's map lives in shared memory, column-padded
-// ([c][h][XS], data at columns 4..4+V, zeros around it; out-of-range rows read a shared zero row),
-// is updated in place layer after layer and never returns to HBM until x7 is written.
+// Frames are the channel axis here; the 2-D map is (H = F feature rows) x (W = V joints).
+// One CTA owns one sample at a time, two CTAs per SM.  The sample's map lives in shared memory,
+// column-padded ([c][h][XS], data at columns 4..4+V, zeros around it; out-of-range rows read a shared
+// zero row), is updated in place layer after layer and never returns to HBM until x7 is written.
 //
-// Hot loop (56 % of the model's FLOPs): each thread owns 5 output channels x one full row of V
-// joints of one dilation branch (5*V accumulators).  Per (input channel, kernel row) it loads the
-// input row once (<= 8 x LDS.128) and 15 weights (4 x LDG.128, warp-uniform per channel tile) and
-// issues 3*5*V FFMAs -- ~27 FFMA per load instruction, so the FP32 pipe, not the LSU, is the limit.
+// Hot loop (56 % of the model's FLOPs): the three dilation branches run one after another with ALL
+// warps on the same branch, so the inner body (one input channel x one kernel row: 120 FFMAs) is a
+// few KB of code shared by every warp and stays in the instruction cache.  A thread owns 5 output
+// channels x 8 (or 6) joints of one row; per body it loads the input window once (4 x LDS.128) and 15
+// folded weights (4 x LDG.128, warp-uniform per channel tile, L1-resident) for 120 FFMAs.  Each
+// branch's slice of the 1x1 `compress` convolution is accumulated right after the branch, so only one
+// branch output (25 x F x V) is ever staged.
 #pragma once
 #include "../../include/cistgcn_b200.h"
 #include "dstd_block.cuh"
@@ -19,7 +22,7 @@ namespace cg {
 
 constexpr int FPN_XS = 36;        // padded row stride of the resident map (floats)
 constexpr int FPN_LPAD = 4;       // data starts at column 4 (keeps rows float4-aligned)
-constexpr int FPN_NT = 192;       // 6 warps: 2 per dilation branch
+constexpr int FPN_NT = 192;
 constexpr int FPN_MAX_LAYERS = CISTGCN_MAX_FPN;
 
 struct FpnArgs {
@@ -30,7 +33,7 @@ struct FpnArgs {
   const float* in;     // (B, Tin, F, V)
   float* x7;           // (B, Tout, V, 3)
   int batch;
-  int o_x, o_zero, o_b, o_misc, smem_floats;
+  int o_x, o_zero, o_b, o_out, o_ring, ring_floats, o_misc, smem_floats;
 };
 
 inline void fpn_plan(FpnArgs& a) {
@@ -38,49 +41,54 @@ inline void fpn_plan(FpnArgs& a) {
   a.o_x = 0;
   a.o_zero = To * F * FPN_XS;
   a.o_b = a.o_zero + 40;
-  a.o_misc = a.o_b + pad4i(3 * To * F * V);
+  a.o_out = a.o_b + pad4i(To * F * V);
+  a.o_ring = a.o_out + pad4i(To * F * V);
+  a.ring_floats = To * pad8i(To);
+  a.o_misc = a.o_ring + 2 * a.ring_floats;
   a.smem_floats = a.o_misc + 2 * pad4i(To) + pad4i(3 * To * V);
 }
 
-// One dilation branch: conv3x3(dil = D, pad = D) + folded BN + PReLU for `To` output channels.
-// Work item = (channel tile of 5, row h); `wib` / `wpb` = this warp's index / warps per branch.
-template <int V, int D>
+// One dilation branch: conv3x3(dil = D, pad = D) + folded BN + PReLU for `To` output channels into
+// Bout [To][F*V].  Work item = (channel tile of 5, row h, column tile of TN).
+template <int V, int D, int TN, int NT>
 CG_DEV void fpn_branch(const float* __restrict__ Wd, const float* __restrict__ bias, float slope,
-                       const float* X, const float* zero_row, float* Bout,
-                       int Cin, int To, int F, int wib, int wpb) {
-  constexpr int NV4 = (FPN_LPAD + V + 3 + 3) / 4;             // float4 chunks covering columns [0, 4+V+3)
-  const int lane = threadIdx.x & 31;
+                       const float* X, const float* zero_row, float* Bout, int Cin, int To, int F) {
+  constexpr int VW = (TN % 4 == 0) ? 4 : 2;                         // window load width
+  constexpr int WIN = ((FPN_LPAD + TN + 3) + VW - 1) / VW * VW;     // floats of row window per item
+  constexpr int NWT = (V + TN - 1) / TN;                            // column tiles per row
+  static_assert((NWT - 1) * TN + WIN <= FPN_XS, "row padding too small for this joint count");
   const int notile = To / 5;
-  const int items = notile * F;
-  const int chunk = (items + wpb - 1) / wpb;
-  for (int it = lane; it < chunk; it += 32) {
-    const int item = wib * chunk + it;
-    if (item >= items) break;
-    const int ot = item / F, h = item - ot * F;
-    float acc[5][V];
+  const int items = notile * F * NWT;
+  for (int item = threadIdx.x; item < items; item += NT) {
+    const int wt = item % NWT, h = (item / NWT) % F, ot = item / (NWT * F);
+    const int w0 = wt * TN;
+    float acc[5][TN];
 #pragma unroll
     for (int m = 0; m < 5; ++m)
 #pragma unroll
-      for (int j = 0; j < V; ++j) acc[m][j] = 0.f;
+      for (int j = 0; j < TN; ++j) acc[m][j] = 0.f;
+    const float* wp = Wd + (size_t)ot * 16;
     for (int c = 0; c < Cin; ++c) {
-#pragma unroll
+#pragma unroll 1
       for (int kh = 0; kh < 3; ++kh) {
         const int hh = h + (kh - 1) * D;
-        const float* row = (hh >= 0 && hh < F) ? X + (c * F + hh) * FPN_XS : zero_row;
-        float xr[NV4 * 4];
+        const float* row = ((hh >= 0 && hh < F) ? X + (c * F + hh) * FPN_XS : zero_row) + w0;
+        float xr[WIN];
 #pragma unroll
-        for (int q = 0; q < NV4; ++q) {
-          const float4 v4 = *reinterpret_cast<const float4*>(row + 4 * q);
-          xr[4 * q] = v4.x; xr[4 * q + 1] = v4.y; xr[4 * q + 2] = v4.z; xr[4 * q + 3] = v4.w;
+        for (int q = 0; q < WIN / VW; ++q) {
+          float tmp[VW];
+          lds_vec<VW>(row + VW * q, tmp);
+#pragma unroll
+          for (int e = 0; e < VW; ++e) xr[VW * q + e] = tmp[e];
         }
         float wv[16];
-        load_vec<16>(Wd + (size_t)((c * 3 + kh) * notile + ot) * 16, wv);
+        load_vec<16>(wp + (size_t)((c * 3 + kh) * notile) * 16, wv);
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
           for (int m = 0; m < 5; ++m)
 #pragma unroll
-            for (int j = 0; j < V; ++j)
+            for (int j = 0; j < TN; ++j)
               acc[m][j] = fmaf(wv[kw * 5 + m], xr[FPN_LPAD + j + (kw - 1) * D], acc[m][j]);
       }
     }
@@ -88,24 +96,31 @@ CG_DEV void fpn_branch(const float* __restrict__ Wd, const float* __restrict__ b
     for (int m = 0; m < 5; ++m) {
       const int o = ot * 5 + m;
       const float bo = bias[o];
-      float* dst = Bout + ((D - 1) * To + o) * (F * V) + h * V;
+      float* dst = Bout + o * (F * V) + h * V + w0;
 #pragma unroll
-      for (int j = 0; j < V; ++j) dst[j] = prelu(acc[m][j] + bo, slope);
+      for (int j = 0; j < TN; ++j)
+        if (w0 + j < V) dst[j] = prelu(acc[m][j] + bo, slope);
     }
   }
 }
 
 template <int V>
-__global__ void __launch_bounds__(FPN_NT) fpn_chain_kernel(const FpnArgs a) {
+__global__ void __launch_bounds__(FPN_NT, 2) fpn_chain_kernel(const FpnArgs a) {
   CG_DYN_SMEM(smem);
   constexpr int NT = FPN_NT;
+  constexpr int TN = (V % 8 == 0 || V % 8 >= 5) ? 8 : 6;       // 22 -> 8 (3 tiles), 18 -> 6 (3 tiles)
+  constexpr int FVC = 10 * V;                                    // F is fixed at 10 (in_ch, CISTGCN.py:512)
   const int tid = threadIdx.x, warp = tid >> 5;
   const float* __restrict__ W = a.w;
   const int Tin = a.t[CT_TIN], To = a.t[CT_TOUT], F = a.t[CT_F];
   const int FV = F * V;
+  const int Top = pad8i(To);
   float* X = smem + a.o_x;
   float* zero_row = smem + a.o_zero;
   float* Bb = smem + a.o_b;
+  float* OUT = smem + a.o_out;
+  float* ring = smem + a.o_ring;
+  const int rb = a.ring_floats;
   float* avg = smem + a.o_misc;
   float* cst = avg + pad4i(To);
   float* y6 = cst + pad4i(To);              // dim_conversor output (To, V, 3) before the cumsum
@@ -119,13 +134,17 @@ __global__ void __launch_bounds__(FPN_NT) fpn_chain_kernel(const FpnArgs a) {
       const float* src = a.in + (size_t)b * Tin * FV;
       for (int i = tid; i < Tin * FV; i += NT) {
         const int r = i / V, v = i - r * V;
-        X[r * FPN_XS + FPN_LPAD + v] = src[i];
+        X[r * FPN_XS + FPN_LPAD + v] = __ldg(src + i);
       }
     }
     __syncthreads();
     for (int l = 0; l < a.n_layers; ++l) {
       const int* f = a.f[l];
       const int Cin = f[CF_CIN];
+      const float* cpw = W + f[CF_CP_WT];
+      // prefetch the first compress slice while the pooling branch runs
+      copy_async<NT>(ring, cpw, To * Top);
+      cp_async_commit();
       // global-average branch (:69, 76) folded into a per-output constant
       for (int c = warp; c < Cin; c += NT / 32) {
         float s = 0.f;
@@ -137,31 +156,38 @@ __global__ void __launch_bounds__(FPN_NT) fpn_chain_kernel(const FpnArgs a) {
       for (int o = tid; o < To; o += NT) {
         const float* wt = W + f[CF_CP_AVG_WT] + o;
         float acc = W[f[CF_CP_B] + o];
-        for (int c = 0; c < Cin; ++c) acc = fmaf(wt[c * pad8i(To)], avg[c], acc);
+        for (int c = 0; c < Cin; ++c) acc = fmaf(wt[c * Top], avg[c], acc);
         cst[o] = acc;
       }
-      // three dilation branches, two warps each
-      {
-        const int br = warp / 2, wib = warp & 1;
-        if (br == 0) fpn_branch<V, 1>(W + f[CF_W_D1], W + f[CF_B_D1], W[f[CF_A_D1]], X, zero_row, Bb, Cin, To, F, wib, 2);
-        else if (br == 1) fpn_branch<V, 2>(W + f[CF_W_D2], W + f[CF_B_D2], W[f[CF_A_D2]], X, zero_row, Bb, Cin, To, F, wib, 2);
-        else fpn_branch<V, 3>(W + f[CF_W_D3], W + f[CF_B_D3], W[f[CF_A_D3]], X, zero_row, Bb, Cin, To, F, wib, 2);
+      const float oa = W[f[CF_OUT_A]];
+      const bool resid = f[CF_RESID] != 0;
+#pragma unroll 1
+      for (int dil = 1; dil <= 3; ++dil) {
+        if (dil == 1) fpn_branch<V, 1, TN, NT>(W + f[CF_W_D1], W + f[CF_B_D1], W[f[CF_A_D1]], X, zero_row, Bb, Cin, To, F);
+        else if (dil == 2) fpn_branch<V, 2, TN, NT>(W + f[CF_W_D2], W + f[CF_B_D2], W[f[CF_A_D2]], X, zero_row, Bb, Cin, To, F);
+        else fpn_branch<V, 3, TN, NT>(W + f[CF_W_D3], W + f[CF_B_D3], W[f[CF_A_D3]], X, zero_row, Bb, Cin, To, F);
+        cp_async_wait_all();
+        __syncthreads();                                   // branch output + this slice's weights are visible
+        const float* wslice = ring + ((dil - 1) & 1) * rb;
+        if (dil < 3) {                                     // next slice streams in during the compress + next branch
+          copy_async<NT>(ring + (dil & 1) * rb, cpw + (size_t)dil * To * Top, To * Top);
+          cp_async_commit();
+        }
+        // compress 1x1 (:77-78), accumulated branch by branch; the last slice applies the caller's
+        // PReLU (+ residual) and writes the map back in place
+        gemm_wide<4, 4, FVC, FVC, NT, false>(nullptr, wslice, Top, To, Bb, To, nullptr, 0, nullptr, 0,
+                                             [&](int m, int n, float acc) {
+                                               if (dil == 1) { OUT[m * FV + n] = acc; return; }
+                                               const float s = OUT[m * FV + n] + acc;
+                                               if (dil == 2) { OUT[m * FV + n] = s; return; }
+                                               const int h = n / V, v = n - h * V;
+                                               float* xp = X + (m * F + h) * FPN_XS + FPN_LPAD + v;
+                                               float val = prelu(s + cst[m], oa);
+                                               if (resid) val += *xp;
+                                               *xp = val;
+                                             });
+        __syncthreads();
       }
-      __syncthreads();
-      // compress 1x1 (:77-78) + caller's PReLU (+ residual), written back in place
-      {
-        const float oa = W[f[CF_OUT_A]];
-        const bool resid = f[CF_RESID] != 0;
-        gemm_rows<4, 2, NT, false>(W + f[CF_CP_WT], pad8i(To), To, FV, Bb, FV, 3 * To, nullptr, 0, 0,
-                                   [&](int m, int n, float acc) {
-                                     const int h = n / V, v = n - h * V;
-                                     float* xp = X + (m * F + h) * FPN_XS + FPN_LPAD + v;
-                                     float val = prelu(acc + cst[m], oa);
-                                     if (resid) val += *xp;
-                                     *xp = val;
-                                   });
-      }
-      __syncthreads();
     }
     // dim_conversor on (F channels, To, V): conv1x1 F->3, BN, PReLU, conv1x1 3->3, PReLU(3)  (:541-545)
     {

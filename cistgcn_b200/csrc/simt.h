@@ -55,4 +55,47 @@ CG_DEV void load_vec(const float* __restrict__ p, float (&w)[TM]) {
 
 template <int N> struct IntC { static constexpr int value = N; };
 
+// ---- cp.async (LDGSTS): 16-byte global -> shared copies that bypass the register file ---------
+CG_DEV void cp_async16(float* smem_dst, const float* __restrict__ gsrc) {
+#ifdef CISTGCN_EMU
+  smem_dst[0] = gsrc[0]; smem_dst[1] = gsrc[1]; smem_dst[2] = gsrc[2]; smem_dst[3] = gsrc[3];
+#else
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+#endif
+}
+CG_DEV void cp_async_commit() {
+#ifndef CISTGCN_EMU
+  asm volatile("cp.async.commit_group;\n" ::);
+#endif
+}
+CG_DEV void cp_async_wait_all() {
+#ifndef CISTGCN_EMU
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+#endif
+}
+// Block-cooperative async copy of n floats (n % 4 == 0, both pointers 16-byte aligned).
+template <int NT>
+CG_DEV void copy_async(float* dst, const float* __restrict__ src, int n) {
+  for (int i = threadIdx.x * 4; i < n; i += NT * 4) cp_async16(dst + i, src + i);
+}
+
+// Vector loads from shared memory (n floats, n in {1,2,4,8,16}); p aligned to min(n,4) floats.
+template <int N_>
+CG_DEV void lds_vec(const float* p, float (&w)[N_]) {
+  if constexpr (N_ % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N_ / 4; ++i) {
+      const float4 v = *(reinterpret_cast<const float4*>(p) + i);
+      w[4 * i + 0] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+    }
+  } else if constexpr (N_ == 2) {
+    const float2 v = *reinterpret_cast<const float2*>(p);
+    w[0] = v.x; w[1] = v.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < N_; ++i) w[i] = p[i];
+  }
+}
+
 }  // namespace cg

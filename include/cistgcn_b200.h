@@ -192,6 +192,9 @@ int cistgcn_mpjpe_f32(const float* pred, const float* target, int64_t batch, int
  * elapsed milliseconds and launch counts per kernel kind (arrays of CISTGCN_PROFILE_KINDS) and
  * resets the counters.  Not thread-safe; leave disabled in production. */
 int cistgcn_profile_enable(int on);
+/* Debug: while non-NULL, thread 0 of the first CTA of every DSTD-GC launch stamps clock64() at its
+ * phase boundaries into device_buffer (>= 16 x int64).  Pass NULL to switch off. */
+int cistgcn_debug_phase_clocks(void* device_buffer);
 int cistgcn_profile_read(double* ms_by_kind, int64_t* launches_by_kind);
 
 #ifdef __cplusplus
