@@ -8,8 +8,9 @@
 #include <vector>
 
 #include "../../include/cistgcn_b200.h"
-#include "dstd_block.cuh"
-#include "fpn_chain.cuh"
+#include "dstd_launch.h"
+#include "fpn_launch.h"
+#include "host_util.h"
 #include "simt.h"
 #include "tail.cuh"
 
@@ -33,34 +34,19 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr int kMaxSmemBytes = 227 * 1024;
 
-#ifdef CISTGCN_EMU
-int sm_count() { return 2; }
-template <class K> int blocks_per_sm(K, int, size_t) { return 1; }
-template <class K> int prepare(K, size_t) { return 0; }
-int check_launch(const char*) { return 0; }
-#else
-int sm_count() {
-  int dev = 0, n = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  return n > 0 ? n : 148;
-}
+using cg::sm_count;
+using cg::grid_for;
+using cg::blocks_per_sm;
+
 template <class K> int prepare(K kfn, size_t smem_bytes) {
-  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-  if (e != cudaSuccess) return fail(-3, "cudaFuncSetAttribute(%zu B): %s", smem_bytes, cudaGetErrorString(e));
+  if (int e = cg::prepare_kernel(kfn, smem_bytes))
+    return fail(-3, "cudaFuncSetAttribute(%zu B): %s", smem_bytes, cg::launch_error_string(e));
   return 0;
-}
-template <class K> int blocks_per_sm(K kfn, int nt, size_t smem_bytes) {
-  int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, nt, smem_bytes) != cudaSuccess || n < 1) n = 1;
-  return n;
 }
 int check_launch(const char* what) {
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(-4, "%s launch: %s", what, cudaGetErrorString(e));
+  if (int e = cg::last_launch_error()) return fail(-4, "%s launch: %s", what, cg::launch_error_string(e));
   return 0;
 }
-#endif
 
 // ---- optional per-kernel CUDA-event timing (bench.py's live roofline numbers) ------------------
 enum { KIND_DSTD = 0, KIND_FPN = 1, KIND_TAIL = 2, KIND_MPJPE = 3, KIND_COUNT = CISTGCN_PROFILE_KINDS };
@@ -98,24 +84,13 @@ struct ProfScope {
 struct ProfScope { ProfScope(int, void*) {} };
 #endif
 
-int grid_for(long long batch, int per_sm) {
-  long long g = (long long)sm_count() * per_sm;
-  return (int)(batch < g ? batch : g);
-}
-
 // ---------------------------------------------------------------------------------------------
-constexpr int DSTD_NT = 256;
+using cg::DSTD_NT;
 long long* g_phase_clocks = nullptr;   // debug hook, see cistgcn_debug_phase_clocks
 
-template <int T, int V>
-int launch_dstd_tv(const cg::DstdArgs& a, void* stream) {
-  auto kfn = cg::dstd_block_kernel<T, V, DSTD_NT>;
-  const size_t smem = (size_t)a.smem_floats * sizeof(float);
-  if (int rc = prepare(kfn, smem)) return rc;
-  const int grid = grid_for(a.batch, blocks_per_sm(kfn, DSTD_NT, smem));
-  ProfScope prof(KIND_DSTD, stream);
-  CG_LAUNCH(kfn, grid, DSTD_NT, smem, stream, a);
-  return check_launch("dstd_block_kernel");
+int dstd_done(int e) {
+  if (e) return fail(-4, "dstd_block_kernel launch: %s", cg::launch_error_string(e));
+  return 0;
 }
 
 int launch_dstd(const int32_t* desc, const float* weights, const float* in, float* out, long long batch,
@@ -129,17 +104,18 @@ int launch_dstd(const int32_t* desc, const float* weights, const float* in, floa
   a.tap_w2 = taps ? taps->w2 : nullptr;
   const int T = a.d[CB_T], V = a.d[CB_V], Ci = a.d[CB_CI], Co = a.d[CB_CO];
   if (Ci < 2 || Co < 1) return fail(-2, "DSTD-GC block needs Ci >= 2 (got %d -> %d)", Ci, Co);
-  if ((Co + 7) / 8 > DSTD_NT / 32) return fail(-2, "DSTD-GC block: Co = %d exceeds the %d supported", Co, 8 * (DSTD_NT / 32));
+  if ((Co + 7) / 8 > DSTD_NT / 32 || Ci > 64) return fail(-2, "DSTD-GC block: %d -> %d channels exceed the 64 supported", Ci, Co);
   if (a.d[CB_IN_MODE] == 1 && Ci != 10) return fail(-2, "feature-building input mode needs Ci == 10");
   if (!a.d[CB_INTERP]) { a.tap_adj_s = nullptr; a.tap_adj_t = nullptr; }
   a.phase_clocks = g_phase_clocks;
   if (!cg::dstd_plan(a, DSTD_NT, kMaxSmemBytes / 4) || (size_t)a.smem_floats * 4 > (size_t)kMaxSmemBytes)
     return fail(-2, "DSTD-GC block (%d->%d, T=%d, V=%d) needs %zu B of shared memory (> %d)", Ci, Co, T, V,
                 (size_t)a.smem_floats * 4, kMaxSmemBytes);
-  if (T == 10 && V == 22) return launch_dstd_tv<10, 22>(a, stream);
-  if (T == 10 && V == 18) return launch_dstd_tv<10, 18>(a, stream);
-  if (T == 22 && V == 25) return launch_dstd_tv<22, 25>(a, stream);
-  if (T == 18 && V == 25) return launch_dstd_tv<18, 25>(a, stream);
+  ProfScope prof(KIND_DSTD, stream);
+  if (T == 10 && V == 22) return dstd_done(cg::launch_dstd_10_22(a, stream));
+  if (T == 10 && V == 18) return dstd_done(cg::launch_dstd_10_18(a, stream));
+  if (T == 22 && V == 25) return dstd_done(cg::launch_dstd_22_25(a, stream));
+  if (T == 18 && V == 25) return dstd_done(cg::launch_dstd_18_25(a, stream));
   return fail(-2, "DSTD-GC block: (T, V) = (%d, %d) has no compiled kernel "
                   "(built: (10,22), (10,18), (22,25), (18,25))", T, V);
 }
@@ -161,22 +137,16 @@ int launch_fpn(const int32_t* fpn_descs, int n_fpn, const int32_t* tail_desc, co
   cg::fpn_plan(a);
   const size_t smem = (size_t)a.smem_floats * sizeof(float);
   if (smem > (size_t)kMaxSmemBytes) return fail(-2, "FPN chain needs %zu B of shared memory", smem);
-  if (V == 22) {
-    auto kfn = cg::fpn_chain_kernel<22>;
-    if (int rc = prepare(kfn, smem)) return rc;
-    const int grid = grid_for(batch, blocks_per_sm(kfn, cg::FPN_NT, smem));
+  int e;
+  {
     ProfScope prof(KIND_FPN, stream);
-    CG_LAUNCH(kfn, grid, cg::FPN_NT, smem, stream, a);
-  } else if (V == 18) {
-    auto kfn = cg::fpn_chain_kernel<18>;
-    if (int rc = prepare(kfn, smem)) return rc;
-    const int grid = grid_for(batch, blocks_per_sm(kfn, cg::FPN_NT, smem));
-    ProfScope prof(KIND_FPN, stream);
-    CG_LAUNCH(kfn, grid, cg::FPN_NT, smem, stream, a);
-  } else {
-    return fail(-2, "FPN chain: joints = %d has no compiled kernel (built: 22, 18)", V);
+    if (V == 22) e = cg::launch_fpn_22(a, stream);
+    else if (V == 18) e = cg::launch_fpn_18(a, stream);
+    else return fail(-2, "FPN chain: joints = %d has no compiled kernel (built: 22, 18)", V);
   }
-  return check_launch("fpn_chain_kernel");
+  if (e) return fail(-4, "fpn_chain_kernel launch: %s", cg::launch_error_string(e));
+  return 0;
+
 }
 
 int launch_tail(const int32_t* tail_desc, const float* weights, const float* x, const float* x7, const float* x8,

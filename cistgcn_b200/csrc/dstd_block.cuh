@@ -93,9 +93,10 @@ inline bool dstd_plan(DstdArgs& a, int nt, int max_smem_floats) {
   const int sm = pad4i(2 + 2 * T) + imax(pad4i(2 * Cg * V), pad4i(2 * Ch * V) + pad4i(2 * Ch * T)) + 3 * pad4i(2 * Co) +
                  2 * pad4i(2 * TV) + 2 * pad4i(Co) + pad4i(Hs);
   a.o_ring = a.o_sm + sm;
-  int budget = max_smem_floats - a.o_ring;
-  a.ring_floats = budget >= 2 * 4096 + 8192 ? 4096 : (budget >= 2 * 2048 ? 2048 : 1024);
-  int cur = a.o_ring + 2 * a.ring_floats;
+  const int budget = max_smem_floats - a.o_ring;
+  const int widest = imax(pad8i(4 * Ch), imax(Cop, pad8i(2 * Cg)));      // longest streamed row
+  a.ring_floats = imax(widest, budget >= 24576 ? 1024 : (budget >= 8192 ? 512 : 256));   // per slot, 8 slots
+  int cur = a.o_ring + 8 * a.ring_floats;
   // residency: mandatory small operands first, then by benefit per byte
   bool ok = true;
   auto take = [&](int f, bool mandatory) {
@@ -113,7 +114,7 @@ inline bool dstd_plan(DstdArgs& a, int nt, int max_smem_floats) {
                        CB_TC3_WT_S, CB_TC3_WT_T, CB_JC3_WT_S, CB_JC3_WT_T, CB_G4_WT};
   for (int f : order) take(f, false);
   a.smem_floats = cur;
-  return ok && cur <= max_smem_floats && a.ring_floats >= pad8i(4 * Ch) && a.ring_floats >= 2 * Cop;
+  return ok && cur <= max_smem_floats;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -122,102 +123,154 @@ inline bool dstd_plan(DstdArgs& a, int nt, int max_smem_floats) {
 // Resident matrices are one chunk with no barrier; streamed ones go through the cp.async ring
 // (chunk c+1 is in flight while chunk c is consumed; one barrier per chunk).
 // ---------------------------------------------------------------------------------------------
+constexpr int RING_SLOTS = 8;
+
+CG_DEV void cp_async_wait_pending(int n) {      // wait until at most n of this thread's groups are in flight
+#ifndef CISTGCN_EMU
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;\n" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;\n" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;\n" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 3;\n" ::: "memory"); break;
+    case 4: asm volatile("cp.async.wait_group 4;\n" ::: "memory"); break;
+    case 5: asm volatile("cp.async.wait_group 5;\n" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 6;\n" ::: "memory"); break;
+  }
+#else
+  (void)n;
+#endif
+}
+
 template <int NT, class BODY>
 CG_DEV void for_weight_chunks(const float* __restrict__ g, const float* s, int K, int Mp, float* ring, int rb, BODY body) {
   if (s != nullptr) { body(s, 0, K); return; }
+  // ring = RING_SLOTS slots of rb floats; up to RING_SLOTS-1 chunks are in flight ahead of the consumer
   const int kc = rb / Mp;
   const int nch = (K + kc - 1) / kc;
-  copy_async<NT>(ring, g, imin(kc, K) * Mp);
-  cp_async_commit();
+  int issued = 0;
+  auto issue = [&]() {
+    copy_async<NT>(ring + (issued % RING_SLOTS) * rb, g + (size_t)issued * kc * Mp, imin(kc, K - issued * kc) * Mp);
+    cp_async_commit();
+    ++issued;
+  };
+  for (int i = 0; i < imin(nch, RING_SLOTS - 1); ++i) issue();
   for (int c = 0; c < nch; ++c) {
-    cp_async_wait_all();
-    __syncthreads();
-    if (c + 1 < nch) {
-      copy_async<NT>(ring + ((c + 1) & 1) * rb, g + (size_t)(c + 1) * kc * Mp, imin(kc, K - (c + 1) * kc) * Mp);
-      cp_async_commit();
-    }
-    body(ring + (c & 1) * rb, c * kc, imin(kc, K - c * kc));
+    cp_async_wait_pending(issued - c - 1);
+    __syncthreads();                 // chunk c visible to all; everyone is done with chunk c-1, whose slot is reused now
+    if (issued < nch) issue();
+    body(ring + (c % RING_SLOTS) * rb, c * kc, imin(kc, K - c * kc));
   }
   __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------
 // Wide GEMM: out(m, n) = sum_k W[k][m] * X[k][n], X = up to two stacked row blocks (row stride LD) in
-// shared memory, N (a multiple of TN) columns.  Work unit = one warp x TM rows x 32 lanes x TN
-// contiguous columns: per k one vector LDS of activations (conflict-free) + TM/4 broadcast LDS.128
-// of weights feed TM*TN FFMAs.  INPLACE: the epilogue may overwrite X; a pass then holds whole column
-// groups and every thread meets the two barriers of the pass (needs ceil(M/TM) <= NT/32).
+// shared memory, N (a multiple of TN) columns; NP independent problems of the same shape may share
+// the phase.  Work unit = one warp x TM rows x 32 lanes x TN contiguous columns: per k one vector LDS
+// of activations (conflict-free) + TM/4 broadcast LDS.128 of weights feed TM*TN FFMAs; operands are
+// double-buffered in registers so the loads of step k+1 fly under the FFMAs of step k.
+// The epilogue gets whole rows: epi(problem, m, n0, float (&v)[TN]).
+// INPLACE: the epilogue may overwrite X; a pass then holds whole column groups and every thread meets
+// the two barriers of the pass (needs ceil(M/TM) <= NT/32).
 // ---------------------------------------------------------------------------------------------
-template <int TM, int TN, int LD, int N, int NT, bool INPLACE, class EPI>
-CG_DEV void gemm_wide(const float* __restrict__ wg_, const float* ws, int Mp, int M,
-                      const float* X1, int K1, const float* X2, int K2, float* ring, int rb, EPI epi) {
+struct WideOp {
+  const float* wg;   // weights in the global blob
+  const float* ws;   // resident copy in shared memory or nullptr (-> streamed through the ring)
+  const float* X1;   // first K1 rows of activations
+  const float* X2;   // next K2 rows (or nullptr)
+};
+
+template <int TM, int TN, int LD, int N, int NT, bool INPLACE, int NP, class EPI>
+CG_DEV void gemm_wide(const WideOp (&ops)[NP], int Mp, int M, int K1, int K2, float* ring, int rb, EPI epi) {
   static_assert(N % TN == 0 && LD % TN == 0, "gemm_wide: columns must tile by TN");
   constexpr int NW = NT / 32;
   constexpr int NCOLS = N / TN;
   constexpr int NG = (NCOLS + 31) / 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mtiles = (M + TM - 1) / TM;
-  const int total = mtiles * NG;
+  const int total = mtiles * NG * NP;
   const int per_pass = INPLACE ? (NW / mtiles) * mtiles : NW;
   for (int base = 0; base < total; base += per_pass) {
     const int item = base + warp;
-    const int slot = (item / mtiles) * 32 + lane;
+    const int unit = item / mtiles;                  // (column group, problem)
+    const int prob = NP == 1 ? 0 : unit % NP;
+    const int slot = (unit / NP) * 32 + lane;
     const bool active = warp < per_pass && item < total && slot < NCOLS;
     const int m0 = active ? (item % mtiles) * TM : 0;
     const int n0 = active ? slot * TN : 0;
+    const WideOp op = (NP > 1 && active && prob == 1) ? ops[NP - 1] : ops[0];
     float acc[TM][TN];
 #pragma unroll
     for (int i = 0; i < TM; ++i)
 #pragma unroll
       for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-    auto run = [&](const float* xp, const float* wp, int n) {
-#pragma unroll 4
-      for (int kk = 0; kk < n; ++kk) {
-        float w[TM], x[TN];
-        lds_vec<TM>(wp, w);
-        lds_vec<TN>(xp, x);
-        wp += Mp;
-        xp += LD;
+    auto fma_step = [&](const float (&w)[TM], const float (&x)[TN]) {
 #pragma unroll
-        for (int i = 0; i < TM; ++i)
+      for (int i = 0; i < TM; ++i)
 #pragma unroll
-          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(w[i], x[j], acc[i][j]);
-      }
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(w[i], x[j], acc[i][j]);
     };
-    for_weight_chunks<NT>(wg_, ws, K1 + K2, Mp, ring, rb, [&](const float* wc, int k0, int kc) {
+    auto run = [&](const float* xp, const float* wp, int n) {
+      if (n <= 0) return;
+      float w0[TM], x0[TN], w1[TM], x1[TN];
+      lds_vec<TM>(wp, w0);
+      lds_vec<TN>(xp, x0);
+      int kk = 0;
+#pragma unroll 2
+      for (; kk + 2 <= n; kk += 2) {
+        lds_vec<TM>(wp + Mp, w1);
+        lds_vec<TN>(xp + LD, x1);
+        fma_step(w0, x0);
+        wp += 2 * Mp;
+        xp += 2 * LD;
+        if (kk + 2 < n) { lds_vec<TM>(wp, w0); lds_vec<TN>(xp, x0); }
+        fma_step(w1, x1);
+      }
+      if (kk < n) fma_step(w0, x0);
+    };
+    auto body = [&](const float* wc, int k0, int kc) {
       if (!active) return;
       int kb = k0, ke = imin(k0 + kc, K1);
-      if (kb < ke) run(X1 + kb * LD + n0, wc + (kb - k0) * Mp + m0, ke - kb);
+      if (kb < ke) run(op.X1 + kb * LD + n0, wc + (kb - k0) * Mp + m0, ke - kb);
       kb = imax(k0, K1); ke = k0 + kc;
-      if (kb < ke) run(X2 + (kb - K1) * LD + n0, wc + (kb - k0) * Mp + m0, ke - kb);
-    });
+      if (kb < ke) run(op.X2 + (kb - K1) * LD + n0, wc + (kb - k0) * Mp + m0, ke - kb);
+    };
+    if constexpr (NP == 1) for_weight_chunks<NT>(ops[0].wg, ops[0].ws, K1 + K2, Mp, ring, rb, body);
+    else body(op.ws, 0, K1 + K2);                    // multi-problem phases need resident weights
     if (INPLACE) __syncthreads();
     if (active) {
 #pragma unroll
       for (int i = 0; i < TM; ++i)
-        if (m0 + i < M) {
-#pragma unroll
-          for (int j = 0; j < TN; ++j) epi(m0 + i, n0 + j, acc[i][j]);
-        }
+        if (m0 + i < M) epi(prob, m0 + i, n0, acc[i]);
     }
     if (INPLACE) __syncthreads();
   }
 }
 
 // Row-tile dispatch: the widest TM that still gives every warp a work unit.
-template <int TN, int LD, int N, int NT, bool INPLACE, class EPI>
-CG_DEV void gemm_wide_auto(const float* __restrict__ wg_, const float* ws, int Mp, int M,
-                           const float* X1, int K1, const float* X2, int K2, float* ring, int rb, EPI epi) {
+template <int TN, int LD, int N, int NT, bool INPLACE, int NP, class EPI>
+CG_DEV void gemm_wide_auto(const WideOp (&ops)[NP], int Mp, int M, int K1, int K2, float* ring, int rb, EPI epi) {
   constexpr int NW = NT / 32;
-  constexpr int NG = ((N / TN) + 31) / 32;
+  constexpr int NG = (((N / TN) + 31) / 32) * NP;
   if (M % 16 == 0 && (M / 16) * NG >= NW)
-    gemm_wide<16, TN, LD, N, NT, INPLACE>(wg_, ws, Mp, M, X1, K1, X2, K2, ring, rb, epi);
+    gemm_wide<16, TN, LD, N, NT, INPLACE, NP>(ops, Mp, M, K1, K2, ring, rb, epi);
   else if (M > 32 || ((M + 7) / 8) * NG >= NW)
-    gemm_wide<8, TN, LD, N, NT, INPLACE>(wg_, ws, Mp, M, X1, K1, X2, K2, ring, rb, epi);
+    gemm_wide<8, TN, LD, N, NT, INPLACE, NP>(ops, Mp, M, K1, K2, ring, rb, epi);
   else if (M > 16 || ((M + 3) / 4) * NG >= NW)
-    gemm_wide<4, TN, LD, N, NT, INPLACE>(wg_, ws, Mp, M, X1, K1, X2, K2, ring, rb, epi);
+    gemm_wide<4, TN, LD, N, NT, INPLACE, NP>(ops, Mp, M, K1, K2, ring, rb, epi);
   else
-    gemm_wide<2, TN, LD, N, NT, INPLACE>(wg_, ws, Mp, M, X1, K1, X2, K2, ring, rb, epi);
+    gemm_wide<2, TN, LD, N, NT, INPLACE, NP>(ops, Mp, M, K1, K2, ring, rb, epi);
+}
+
+// Vector store of TN contiguous floats to shared / global memory (p aligned to TN floats).
+template <int TN>
+CG_DEV void store_vec(float* p, const float (&v)[TN]) {
+  if constexpr (TN == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  else if constexpr (TN == 2) *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+  else {
+#pragma unroll
+    for (int j = 0; j < TN; ++j) p[j] = v[j];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -423,10 +476,11 @@ template <int T, int V, int NT>
 __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
   CG_DYN_SMEM(smem);
   constexpr int TV = T * V, TT = T * T, VV = V * V;
+  constexpr int NW = NT / 32;
   constexpr int TNW = (TV % 4 == 0) ? 4 : 2;            // column vector width of the wide GEMMs
   constexpr int TNS = (TT % 4 == 0) ? 4 : 2;            // ... of the joint-axis expansor (N = T*T)
   constexpr int TNT = (VV % 4 == 0) ? 4 : (VV % 2 == 0 ? 2 : 1);   // ... of the frame-axis expansor (N = V*V)
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int* d = a.d;
   const float* __restrict__ W = a.w;
   const int Ci = d[CB_CI], Co = d[CB_CO], Ch = d[CB_CH], Cg = d[CB_CG], Hs = d[CB_HS];
@@ -456,8 +510,6 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
   // row statistics / split-K partials live in the (still unused) adjacency region
   float* rowmean = ADJ;
   float* rowvar = rowmean + Ci * T;
-  float* chmean = rowvar + Ci * T;
-  float* chstd = chmean + Ci;
   float* partial = ADJ;
 
   // operand accessors: resident copy in shared memory if planned, else the global blob
@@ -478,7 +530,7 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
     if (d[CB_IN_MODE] == 1) {
       const float* src = a.in + (size_t)b * d[CB_IN_SB];
       float* raw = A;
-      for (int i = tid; i < TV * 3; i += NT) raw[i] = src[i];
+      for (int i = tid; i < TV * 3; i += NT) raw[i] = __ldg(src + i);
       __syncthreads();
       const float* gs = P(CB_GN_S);
       const float* gb = P(CB_GN_B);
@@ -523,7 +575,7 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
       } else {
         for (int i = tid; i < Ci * TV; i += NT) {
           const int c = i / TV, n = i - c * TV, t = n / V, v = n - t * V;
-          XN[i] = fmaf(gs[c], src[c * sc + t * st + v * sv], gb[c]);
+          XN[i] = fmaf(gs[c], __ldg(src + c * sc + t * st + v * sv), gb[c]);
         }
       }
     }
@@ -533,44 +585,62 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
     // ---------------- P2: statistics (:360-371), all Bessel-corrected like torch.std
     for (int r = tid; r < Ci * T; r += NT) {                  // r = c*T + t, row of V joints
       const float* xp = XN + (r / T) * TV + (r % T) * V;
+      float xv[V];
       float s = 0.f;
 #pragma unroll
-      for (int v = 0; v < V; ++v) s += xp[v];
+      for (int v = 0; v < V; ++v) { xv[v] = xp[v]; s += xv[v]; }
       const float mu = s / V;
       float q = 0.f;
 #pragma unroll
-      for (int v = 0; v < V; ++v) { const float dd = xp[v] - mu; q = fmaf(dd, dd, q); }
+      for (int v = 0; v < V; ++v) { const float dd = xv[v] - mu; q = fmaf(dd, dd, q); }
       rowmean[r] = mu;
       rowvar[r] = q / (V - 1);
     }
     __syncthreads();
-    for (int c = tid; c < Ci; c += NT) {
-      float s = 0.f;
-      for (int t = 0; t < T; ++t) s += rowmean[c * T + t];
-      const float cm = s / T;
-      float ss = 0.f;
-      for (int t = 0; t < T; ++t) { const float dm = rowmean[c * T + t] - cm; ss += (V - 1) * rowvar[c * T + t] + V * dm * dm; }
-      chmean[c] = cm;
-      chstd[c] = sqrtf(ss / (TV - 1));
-    }
-    for (int t = tid - 64; t >= 0 && t < T; t += NT) {        // (threads 64.. so they overlap the loop above)
-      float s = 0.f, s2 = 0.f;
-      for (int c = 0; c < Ci; ++c) { s += rowmean[c * T + t]; s2 += sqrtf(rowvar[c * T + t]); }
-      const float m2 = s2 / Ci;
+    if (warp == NW - 1) {
+      // channel level: mean / std over (T,V) per channel, then mean / std over channels (lanes own channels)
+      float sm = 0.f, ssd = 0.f;
+      float sdv[2] = {0.f, 0.f};
+      for (int c = lane, it = 0; c < Ci; c += 32, ++it) {
+        float rm[T];
+        float s = 0.f;
+#pragma unroll
+        for (int t = 0; t < T; ++t) { rm[t] = rowmean[c * T + t]; s += rm[t]; }
+        const float cm = s / T;
+        float ss = 0.f;
+#pragma unroll
+        for (int t = 0; t < T; ++t) { const float dm = rm[t] - cm; ss += (V - 1) * rowvar[c * T + t] + V * dm * dm; }
+        const float sd = sqrtf(ss / (TV - 1));
+        sm += cm;
+        ssd += sd;
+        if (it < 2) sdv[it] = sd;
+      }
+      sm = warp_sum(sm);
+      ssd = warp_sum(ssd);
+      const float m2 = ssd / Ci;
       float q = 0.f;
-      for (int c = 0; c < Ci; ++c) { const float dd = sqrtf(rowvar[c * T + t]) - m2; q = fmaf(dd, dd, q); }
-      stats[1 + t] = s / Ci;
-      stats[2 + T + t] = sqrtf(q / (Ci - 1));
-    }
-    __syncthreads();
-    if (tid == 0) {
-      float s = 0.f, s2 = 0.f;
-      for (int c = 0; c < Ci; ++c) { s += chmean[c]; s2 += chstd[c]; }
-      const float m2 = s2 / Ci;
-      float q = 0.f;
-      for (int c = 0; c < Ci; ++c) { const float dd = chstd[c] - m2; q = fmaf(dd, dd, q); }
-      stats[0] = s / Ci;
-      stats[1 + T] = sqrtf(q / (Ci - 1));
+      for (int c = lane, it = 0; c < Ci; c += 32, ++it) { const float dd = sdv[it < 2 ? it : 1] - m2; q = fmaf(dd, dd, q); }
+      q = warp_sum(q);
+      if (lane == 0) { stats[0] = sm / Ci; stats[1 + T] = sqrtf(q / (Ci - 1)); }
+    } else {
+      // frame level: per t, mean over channels of the row means and std over channels of the row stds
+      for (int t = warp; t < T; t += NW - 1) {
+        float s = 0.f, s2 = 0.f;
+        float sdv[2] = {0.f, 0.f};
+        for (int c = lane, it = 0; c < Ci; c += 32, ++it) {
+          s += rowmean[c * T + t];
+          const float sd = sqrtf(rowvar[c * T + t]);
+          s2 += sd;
+          if (it < 2) sdv[it] = sd;
+        }
+        s = warp_sum(s);
+        s2 = warp_sum(s2);
+        const float m2 = s2 / Ci;
+        float q = 0.f;
+        for (int c = lane, it = 0; c < Ci; c += 32, ++it) { const float dd = sdv[it < 2 ? it : 1] - m2; q = fmaf(dd, dd, q); }
+        q = warp_sum(q);
+        if (lane == 0) { stats[1 + t] = s / Ci; stats[2 + T + t] = sqrtf(q / (Ci - 1)); }
+      }
     }
     __syncthreads();      // row statistics are dead from here on: ADJ becomes split-K scratch
     CG_STAMP(2);
@@ -607,15 +677,26 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
       {
         const float* ab = P(CB_A0_B);
         const float* aa = P(CB_A0_A);
-        gemm_wide_auto<TNW, TV, TV, NT, false>(G(CB_A0_WT), RS(CB_A0_WT), pad8i(4 * Ch), 4 * Ch, XN, Ci, nullptr, 0, ring, rb,
-                                               [&](int m, int n, float acc) {
-                                                 const int br = m / Ch, r = m - br * Ch;
-                                                 const float val = prelu(acc + ab[m], aa[br]);
-                                                 float* tl = A + (br >> 1) * a.tile;
-                                                 if ((br & 1) == 0) tl[r * TV + n] = val;          // time_compress map  [c][t][v]
-                                                 else { const int t = n / V, v = n - t * V;
-                                                        tl[(Ch + r) * TV + v * T + t] = val; }     // joint_compress map [c][v][t]
-                                               });
+        const WideOp ops[1] = {{G(CB_A0_WT), RS(CB_A0_WT), XN, nullptr}};
+        gemm_wide_auto<TNW, TV, TV, NT, false, 1>(ops, pad8i(4 * Ch), 4 * Ch, Ci, 0, ring, rb,
+          [&](int, int m, int n0, float (&v)[TNW]) {
+            const int br = m / Ch, r = m - br * Ch;
+            const float bias = ab[m], sl = aa[br];
+            float* tl = A + (br >> 1) * a.tile;
+#pragma unroll
+            for (int j = 0; j < TNW; ++j) v[j] = prelu(v[j] + bias, sl);
+            if ((br & 1) == 0) {
+              store_vec<TNW>(tl + r * TV + n0, v);                          // time_compress map  [c][t][v]
+            } else {
+              float* dst = tl + (Ch + r) * TV;                              // joint_compress map [c][v][t]
+              int t = n0 / V, vv = n0 - t * V;
+#pragma unroll
+              for (int j = 0; j < TNW; ++j) {
+                dst[vv * T + t] = v[j];
+                if (++vv == V) { vv = 0; ++t; }
+              }
+            }
+          });
       }
       __syncthreads();
       CG_STAMP(5);
@@ -639,6 +720,7 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
         const float* wt = P(CB_TC6_WT_S + L) + tq;
         const float* xp = dseqp + L * Ch * V + v;
         float acc = 0.f;
+#pragma unroll 4
         for (int o = 0; o < Ch; ++o) acc = fmaf(wt[o * pad8i(T)], xp[o * V], acc);
         dseq[i] = acc;
       }
@@ -647,6 +729,7 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
         const float* wt = P(CB_JC6_WT_S + L) + vq;
         const float* xp = dspp + L * Ch * T + t;
         float acc = 0.f;
+#pragma unroll 4
         for (int o = 0; o < Ch; ++o) acc = fmaf(wt[o * pad8i(V)], xp[o * T], acc);
         dsp[i] = acc;
       }
@@ -662,19 +745,33 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
       {
         const float* eb = P(CB_E0_B_S);
         const float ea = P(CB_E0_A_S)[0];
-        gemm_wide_auto<TNS, TT, TT, NT, false>(G(CB_E0_WT_S), RS(CB_E0_WT_S), pad8i(V), V, ADJ, V, nullptr, 0, ring, rb,
-                                               [&](int m, int n, float acc) { Bt[m * TT + n] = prelu(acc + eb[m], ea); });
+        const WideOp ops[1] = {{G(CB_E0_WT_S), RS(CB_E0_WT_S), ADJ, nullptr}};
+        gemm_wide_auto<TNS, TT, TT, NT, false, 1>(ops, pad8i(V), V, V, 0, ring, rb,
+          [&](int, int m, int n0, float (&v)[TNS]) {
+            const float bias = eb[m];
+#pragma unroll
+            for (int j = 0; j < TNS; ++j) v[j] = prelu(v[j] + bias, ea);
+            store_vec<TNS>(Bt + m * TT + n0, v);
+          });
       }
       __syncthreads();
       {
         float* tp = a.tap_adj_s ? a.tap_adj_s + (size_t)b * V * TT : nullptr;
-        gemm_wide_auto<TNS, TT, TT, NT, false>(G(CB_E4_WT_S), RS(CB_E4_WT_S), pad8i(V), V, Bt, V, nullptr, 0, ring, rb,
-                                               [&](int m, int n, float acc) { ADJ[n * V + m] = acc; if (tp) tp[m * TT + n] = acc; });
+        const WideOp ops[1] = {{G(CB_E4_WT_S), RS(CB_E4_WT_S), Bt, nullptr}};
+        gemm_wide_auto<TNS, TT, TT, NT, false, 1>(ops, pad8i(V), V, V, 0, ring, rb,
+          [&](int, int m, int n0, float (&v)[TNS]) {
+#pragma unroll
+            for (int j = 0; j < TNS; ++j) ADJ[(n0 + j) * V + m] = v[j];
+            if (tp) {
+#pragma unroll
+              for (int j = 0; j < TNS; ++j) tp[m * TT + n0 + j] = v[j];
+            }
+          });
       }
       __syncthreads();
     } else {
       const float* as = W + d[CB_ADJ_S];                      // static (V,T,T) -> [t][q][v]
-      for (int i = tid; i < V * TT; i += NT) { const int v = i / TT, r = i - v * TT; ADJ[r * V + v] = as[i]; }
+      for (int i = tid; i < V * TT; i += NT) { const int v = i / TT, r = i - v * TT; ADJ[r * V + v] = __ldg(as + i); }
       __syncthreads();
     }
     CG_STAMP(8);
@@ -693,18 +790,31 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
       {
         const float* eb = P(CB_E0_B_T);
         const float ea = P(CB_E0_A_T)[0];
-        gemm_wide_auto<TNT, VV, VV, NT, false>(G(CB_E0_WT_T), RS(CB_E0_WT_T), pad8i(T), T, ADJ, T, nullptr, 0, ring, rb,
-                                               [&](int m, int n, float acc) { Bt[m * VV + n] = prelu(acc + eb[m], ea); });
+        const WideOp ops[1] = {{G(CB_E0_WT_T), RS(CB_E0_WT_T), ADJ, nullptr}};
+        gemm_wide_auto<TNT, VV, VV, NT, false, 1>(ops, pad8i(T), T, T, 0, ring, rb,
+          [&](int, int m, int n0, float (&v)[TNT]) {
+            const float bias = eb[m];
+#pragma unroll
+            for (int j = 0; j < TNT; ++j) v[j] = prelu(v[j] + bias, ea);
+            store_vec<TNT>(Bt + m * VV + n0, v);
+          });
       }
       __syncthreads();
       {
         float* tp = a.tap_adj_t ? a.tap_adj_t + (size_t)b * T * VV : nullptr;
-        gemm_wide_auto<TNT, VV, VV, NT, false>(G(CB_E4_WT_T), RS(CB_E4_WT_T), pad8i(T), T, Bt, T, nullptr, 0, ring, rb,
-                                               [&](int m, int n, float acc) { ADJ[m * VV + n] = acc; if (tp) tp[m * VV + n] = acc; });
+        const WideOp ops[1] = {{G(CB_E4_WT_T), RS(CB_E4_WT_T), Bt, nullptr}};
+        gemm_wide_auto<TNT, VV, VV, NT, false, 1>(ops, pad8i(T), T, T, 0, ring, rb,
+          [&](int, int m, int n0, float (&v)[TNT]) {
+            store_vec<TNT>(ADJ + m * VV + n0, v);
+            if (tp) {
+#pragma unroll
+              for (int j = 0; j < TNT; ++j) tp[m * VV + n0 + j] = v[j];
+            }
+          });
       }
     } else {
       const float* at = W + d[CB_ADJ_T];
-      for (int i = tid; i < T * VV; i += NT) ADJ[i] = at[i];
+      for (int i = tid; i < T * VV; i += NT) ADJ[i] = __ldg(at + i);
     }
     __syncthreads();
     CG_STAMP(10);
@@ -714,46 +824,64 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
     __syncthreads();
     CG_STAMP(11);
     // ---------------- P13: x_k = PReLU(BN(W g_k + b) + res); u_k = PReLU(BN(w_k * x_k))   (:266-268, 388)
+    {
+      auto tcn_epi = [&](int L, int m, int n0, float (&v)[TNW]) {
+        float* Gt = L == 0 ? A : Bt;
+        const float tbm = P(CB_TCN_B_S + L)[m], ta = P(CB_TCN_A_S + L)[0];
+        const float sc = P(CB_P_S_S + L)[m] * wg[L * Co + m], pbm = P(CB_P_B_S + L)[m], pa = P(CB_P_A_S + L)[0];
+        float r[TNW];
+        if (!has_res) lds_vec<TNW>(XN + m * TV + n0, r);
 #pragma unroll
-    for (int L = 0; L < 2; ++L) {
-      float* Gt = L == 0 ? A : Bt;
-      const float* tb = P(CB_TCN_B_S + L);
-      const float ta = P(CB_TCN_A_S + L)[0];
-      const float* ps = P(CB_P_S_S + L);
-      const float* pb = P(CB_P_B_S + L);
-      const float pa = P(CB_P_A_S + L)[0];
-      const float* wk = wg + L * Co;
-      gemm_wide_auto<TNW, TV, TV, NT, true>(G(CB_TCN_WT_S + L), RS(CB_TCN_WT_S + L), Cop, Co, Gt, Ci, XN, has_res ? Ci : 0, ring, rb,
-                                            [&](int m, int n, float acc) {
-                                              float v = acc + tb[m];
-                                              if (!has_res) v += XN[m * TV + n];
-                                              v = prelu(v, ta);
-                                              v = fmaf(ps[m], wk[m] * v, pb[m]);
-                                              Gt[m * TV + n] = prelu(v, pa);
-                                            });
+        for (int j = 0; j < TNW; ++j) {
+          float x = v[j] + tbm;
+          if (!has_res) x += r[j];
+          x = prelu(x, ta);
+          v[j] = prelu(fmaf(sc, x, pbm), pa);
+        }
+        store_vec<TNW>(Gt + m * TV + n0, v);
+      };
+      const int K2 = has_res ? Ci : 0;
+      if (RS(CB_TCN_WT_S) && RS(CB_TCN_WT_T)) {            // both resident: one phase for both domains
+        const WideOp ops[2] = {{G(CB_TCN_WT_S), RS(CB_TCN_WT_S), A, XN}, {G(CB_TCN_WT_T), RS(CB_TCN_WT_T), Bt, XN}};
+        gemm_wide_auto<TNW, TV, TV, NT, true, 2>(ops, Cop, Co, Ci, K2, ring, rb, tcn_epi);
+      } else {
+#pragma unroll
+        for (int L = 0; L < 2; ++L) {
+          const WideOp ops[1] = {{G(CB_TCN_WT_S + L), RS(CB_TCN_WT_S + L), L == 0 ? A : Bt, XN}};
+          gemm_wide_auto<TNW, TV, TV, NT, true, 1>(ops, Cop, Co, Ci, K2, ring, rb,
+            [&](int, int m, int n0, float (&v)[TNW]) { tcn_epi(L, m, n0, v); });
+        }
+      }
     }
     CG_STAMP(12);
     // ---------------- P14: compressor 1x1 over cat(u1, u2) + BN + PReLU -> A   (:305-307)
     {
       const float* cb = P(CB_CP_B);
       const float ca = P(CB_CP_A)[0];
-      gemm_wide_auto<TNW, TV, TV, NT, true>(G(CB_CP_WT), RS(CB_CP_WT), Cop, Co, A, Co, Bt, Co, ring, rb,
-                                            [&](int m, int n, float acc) { A[m * TV + n] = prelu(acc + cb[m], ca); });
+      const WideOp ops[1] = {{G(CB_CP_WT), RS(CB_CP_WT), A, Bt}};
+      gemm_wide_auto<TNW, TV, TV, NT, true, 1>(ops, Cop, Co, Co, Co, ring, rb,
+        [&](int, int m, int n0, float (&v)[TNW]) {
+          const float bias = cb[m];
+#pragma unroll
+          for (int j = 0; j < TNW; ++j) v[j] = prelu(v[j] + bias, ca);
+          store_vec<TNW>(A + m * TV + n0, v);
+        });
     }
     CG_STAMP(13);
     // ---------------- P15-P17: squeeze-excitation (SE.py:37-41)
-    for (int m = tid >> 5; m < Co; m += NT / 32) {
+    for (int m = warp; m < Co; m += NW) {
       float s = 0.f;
-      for (int n = tid & 31; n < TV; n += 32) s += A[m * TV + n];
+      for (int n = lane; n < TV; n += 32) s += A[m * TV + n];
       s = warp_sum(s);
-      if ((tid & 31) == 0) semean[m] = s / TV;
+      if (lane == 0) semean[m] = s / TV;
     }
     __syncthreads();
-    for (int h = tid; h < Hs; h += NT) {
+    for (int h = warp; h < Hs; h += NW) {
       const float* wt = P(CB_SE1_WT) + h;
       float acc = 0.f;
-      for (int c = 0; c < Co; ++c) acc = fmaf(wt[c * pad8i(Hs)], semean[c], acc);
-      hid[h] = fmaxf(acc, 0.f);
+      for (int c = lane; c < Co; c += 32) acc = fmaf(wt[c * pad8i(Hs)], semean[c], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) hid[h] = fmaxf(acc, 0.f);
     }
     __syncthreads();
     for (int o = tid; o < Co; o += NT) {
@@ -768,14 +896,28 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
     {
       float* dst = a.out + (size_t)b * d[CB_OUT_SB];
       const int sc = d[CB_OUT_SC], st = d[CB_OUT_ST], sv = d[CB_OUT_SV];
+      const bool contiguous = sv == 1 && st == V && sc == TV && (TV % 4) == 0;
       if (has_res) {
         const float* rbias = P(CB_RS_B);
-        gemm_wide_auto<TNW, TV, TV, NT, false>(G(CB_RS_WT), RS(CB_RS_WT), Cop, Co, XN, Ci, nullptr, 0, ring, rb,
-                                               [&](int m, int n, float acc) {
-                                                 const int t = n / V, v = n - t * V;
-                                                 dst[m * sc + t * st + v * sv] = fmaf(A[m * TV + n], gate[m], acc + rbias[m]);
-                                               });
-      } else if (sv == 1 && st == V && sc == TV && (TV % 4) == 0) {
+        const WideOp ops[1] = {{G(CB_RS_WT), RS(CB_RS_WT), XN, nullptr}};
+        gemm_wide_auto<TNW, TV, TV, NT, false, 1>(ops, Cop, Co, Ci, 0, ring, rb,
+          [&](int, int m, int n0, float (&v)[TNW]) {
+            const float gm = gate[m], bias = rbias[m];
+            float c[TNW];
+            lds_vec<TNW>(A + m * TV + n0, c);
+#pragma unroll
+            for (int j = 0; j < TNW; ++j) v[j] = fmaf(c[j], gm, v[j] + bias);
+            if (contiguous) { store_vec<TNW>(dst + m * TV + n0, v); }
+            else {
+              int t = n0 / V, vv = n0 - t * V;
+#pragma unroll
+              for (int j = 0; j < TNW; ++j) {
+                dst[m * sc + t * st + vv * sv] = v[j];
+                if (++vv == V) { vv = 0; ++t; }
+              }
+            }
+          });
+      } else if (contiguous) {
         float4* d4 = reinterpret_cast<float4*>(dst);
         for (int i = tid; i < Co * TV / 4; i += NT) {
           const float gm = gate[(i * 4) / TV];

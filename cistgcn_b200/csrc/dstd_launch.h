@@ -1,0 +1,26 @@
+// Launchers of the fused DSTD-GC kernel, one translation unit per (T, V) instantiation so that nvcc
+// can compile them in parallel (dstd_inst_*.cu).  Return 0 or a CUDA error code.
+#pragma once
+#include "dstd_block.cuh"
+#include "host_util.h"
+
+namespace cg {
+
+constexpr int DSTD_NT = 256;
+
+int launch_dstd_10_22(const DstdArgs& a, void* stream);
+int launch_dstd_10_18(const DstdArgs& a, void* stream);
+int launch_dstd_22_25(const DstdArgs& a, void* stream);
+int launch_dstd_18_25(const DstdArgs& a, void* stream);
+
+template <int T, int V>
+inline int launch_dstd_impl(const DstdArgs& a, void* stream) {
+  auto kfn = dstd_block_kernel<T, V, DSTD_NT>;
+  const size_t smem = (size_t)a.smem_floats * sizeof(float);
+  if (int rc = prepare_kernel(kfn, smem)) return rc;
+  const int grid = grid_for(a.batch, blocks_per_sm(kfn, DSTD_NT, smem));
+  CG_LAUNCH(kfn, grid, DSTD_NT, smem, stream, a);
+  return last_launch_error();
+}
+
+}  // namespace cg

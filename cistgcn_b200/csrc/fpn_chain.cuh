@@ -68,30 +68,40 @@ CG_DEV void fpn_branch(const float* __restrict__ Wd, const float* __restrict__ b
 #pragma unroll
       for (int j = 0; j < TN; ++j) acc[m][j] = 0.f;
     const float* wp = Wd + (size_t)ot * 16;
-    for (int c = 0; c < Cin; ++c) {
-#pragma unroll 1
-      for (int kh = 0; kh < 3; ++kh) {
-        const int hh = h + (kh - 1) * D;
-        const float* row = ((hh >= 0 && hh < F) ? X + (c * F + hh) * FPN_XS : zero_row) + w0;
-        float xr[WIN];
+    const int wstride = notile * 16;
+    const int nit = Cin * 3;                                   // (input channel, kernel row) pairs
+    auto step = [&](int it, const float (&wv)[16]) {
+      const int c = it / 3, kh = it - c * 3;
+      const int hh = h + (kh - 1) * D;
+      const float* row = ((hh >= 0 && hh < F) ? X + (c * F + hh) * FPN_XS : zero_row) + w0;
+      float xr[WIN];
 #pragma unroll
-        for (int q = 0; q < WIN / VW; ++q) {
-          float tmp[VW];
-          lds_vec<VW>(row + VW * q, tmp);
+      for (int q = 0; q < WIN / VW; ++q) {
+        float tmp[VW];
+        lds_vec<VW>(row + VW * q, tmp);
 #pragma unroll
-          for (int e = 0; e < VW; ++e) xr[VW * q + e] = tmp[e];
-        }
-        float wv[16];
-        load_vec<16>(wp + (size_t)((c * 3 + kh) * notile) * 16, wv);
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw)
-#pragma unroll
-          for (int m = 0; m < 5; ++m)
-#pragma unroll
-            for (int j = 0; j < TN; ++j)
-              acc[m][j] = fmaf(wv[kw * 5 + m], xr[FPN_LPAD + j + (kw - 1) * D], acc[m][j]);
+        for (int e = 0; e < VW; ++e) xr[VW * q + e] = tmp[e];
       }
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+        for (int m = 0; m < 5; ++m)
+#pragma unroll
+          for (int j = 0; j < TN; ++j)
+            acc[m][j] = fmaf(wv[kw * 5 + m], xr[FPN_LPAD + j + (kw - 1) * D], acc[m][j]);
+    };
+    // weights are double-buffered in registers: the (L1-resident) loads of step it+1 fly under step it
+    float wa[16], wb[16];
+    load_vec<16>(wp, wa);
+    int it = 0;
+#pragma unroll 1
+    for (; it + 2 <= nit; it += 2) {
+      load_vec<16>(wp + (size_t)(it + 1) * wstride, wb);
+      step(it, wa);
+      if (it + 2 < nit) load_vec<16>(wp + (size_t)(it + 2) * wstride, wa);
+      step(it + 1, wb);
     }
+    if (it < nit) step(it, wa);
 #pragma unroll
     for (int m = 0; m < 5; ++m) {
       const int o = ot * 5 + m;
@@ -175,17 +185,27 @@ __global__ void __launch_bounds__(FPN_NT, 2) fpn_chain_kernel(const FpnArgs a) {
         }
         // compress 1x1 (:77-78), accumulated branch by branch; the last slice applies the caller's
         // PReLU (+ residual) and writes the map back in place
-        gemm_wide<4, 4, FVC, FVC, NT, false>(nullptr, wslice, Top, To, Bb, To, nullptr, 0, nullptr, 0,
-                                             [&](int m, int n, float acc) {
-                                               if (dil == 1) { OUT[m * FV + n] = acc; return; }
-                                               const float s = OUT[m * FV + n] + acc;
-                                               if (dil == 2) { OUT[m * FV + n] = s; return; }
-                                               const int h = n / V, v = n - h * V;
-                                               float* xp = X + (m * F + h) * FPN_XS + FPN_LPAD + v;
-                                               float val = prelu(s + cst[m], oa);
-                                               if (resid) val += *xp;
-                                               *xp = val;
-                                             });
+        const WideOp ops[1] = {{nullptr, wslice, Bb, nullptr}};
+        gemm_wide<4, 4, FVC, FVC, NT, false, 1>(ops, Top, To, To, 0, nullptr, 0,
+          [&](int, int m, int n0, float (&v)[4]) {
+            float* op = OUT + m * FV + n0;
+            if (dil == 1) { store_vec<4>(op, v); return; }
+            float s[4];
+            lds_vec<4>(op, s);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[j] += v[j];
+            if (dil == 2) { store_vec<4>(op, s); return; }
+            const float cm = cst[m];
+            int h = n0 / V, vv = n0 - h * V;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float* xp = X + (m * F + h) * FPN_XS + FPN_LPAD + vv;
+              float val = prelu(s[j] + cm, oa);
+              if (resid) val += *xp;
+              *xp = val;
+              if (++vv == V) { vv = 0; ++h; }
+            }
+          });
         __syncthreads();
       }
     }

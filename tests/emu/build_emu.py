@@ -9,8 +9,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(HERE, "_build", "libcistgcn_emu.so")
-SRCS = [os.path.join(ROOT, "cistgcn_b200", "csrc", f) for f in
-        ("cistgcn_api.cu", "dstd_block.cuh", "fpn_chain.cuh", "tail.cuh", "simt.h")] + \
+CSRC = os.path.join(ROOT, "cistgcn_b200", "csrc")
+UNITS = ["cistgcn_api.cu", "dstd_inst_10_22.cu", "dstd_inst_10_18.cu", "dstd_inst_22_25.cu", "dstd_inst_18_25.cu",
+         "fpn_inst_22.cu", "fpn_inst_18.cu"]
+SRCS = [os.path.join(CSRC, f) for f in UNITS + ["dstd_block.cuh", "fpn_chain.cuh", "tail.cuh", "simt.h", "host_util.h",
+                                                 "dstd_launch.h", "fpn_launch.h"]] + \
        [os.path.join(HERE, "simt_emu.h"), os.path.join(ROOT, "include", "cistgcn_b200.h")]
 
 
@@ -18,9 +21,19 @@ def build(force: bool = False) -> str:
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     if not force and os.path.isfile(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(s) for s in SRCS):
         return OUT
-    cmd = ["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-pthread", "-DCISTGCN_EMU", "-Wno-unknown-pragmas",
-           "-I", HERE, "-x", "c++", SRCS[0], "-o", OUT]
-    subprocess.check_call(cmd)
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(os.path.dirname(OUT), "obj")
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_one(unit):
+        obj = os.path.join(objdir, os.path.splitext(unit)[0] + ".o")
+        subprocess.check_call(["g++", "-std=c++20", "-O2", "-fPIC", "-pthread", "-DCISTGCN_EMU", "-Wno-unknown-pragmas",
+                               "-I", HERE, "-x", "c++", "-c", os.path.join(CSRC, unit), "-o", obj])
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, UNITS))
+    subprocess.check_call(["g++", "-shared", "-pthread", "-o", OUT] + objs)
     return OUT
 
 
