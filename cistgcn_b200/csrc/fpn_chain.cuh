@@ -185,8 +185,8 @@ __global__ void __launch_bounds__(FPN_NT, 2) fpn_chain_kernel(const FpnArgs a) {
         }
         // compress 1x1 (:77-78), accumulated branch by branch; the last slice applies the caller's
         // PReLU (+ residual) and writes the map back in place
-        const WideOp ops[1] = {{nullptr, wslice, Bb, nullptr}};
-        gemm_wide<4, 4, FVC, FVC, NT, false, 1>(ops, Top, To, To, 0, nullptr, 0,
+        const WideOp ops[2] = {{nullptr, wslice, Bb, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+        gemm_wide<4, 4, NT>(ops, 1, false, Top, To, To, 0, FVC, FVC, nullptr, 0,
           [&](int, int m, int n0, float (&v)[4]) {
             float* op = OUT + m * FV + n0;
             if (dil == 1) { store_vec<4>(op, v); return; }

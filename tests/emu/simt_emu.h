@@ -32,6 +32,7 @@ static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
 #define __launch_bounds__(...)
+#define __noinline__ __attribute__((noinline))
 #define __shared__ static
 
 namespace simt_emu {
