@@ -51,6 +51,8 @@ __host__ __device__ inline int pad8i(int n) { return (n + 7) & ~7; }
 __host__ __device__ inline int imax(int a, int b) { return a > b ? a : b; }
 __host__ __device__ inline int imin(int a, int b) { return a < b ? a : b; }
 
+constexpr int RING_SLOTS = 4;   // cp.async streaming ring: slots in flight
+
 // Host: sizes of every weight field, the shared-memory layout and the residency plan.
 // Returns false if even the mandatory small vectors do not fit.
 inline bool dstd_plan(DstdArgs& a, int nt, int max_smem_floats) {
@@ -88,15 +90,15 @@ inline bool dstd_plan(DstdArgs& a, int nt, int max_smem_floats) {
   a.o_ab = pad4i(Ci * TV);
   a.o_adj = a.o_ab + a.tile + imax(a.tile, pad4i(big));
   const int nw = nt / 32;
-  const int adj = imax(imax(pad4i(big), pad4i(T * T * (V | 1))), imax(pad4i(2 * Ci * T + 2 * Ci), nw * 8 * 32));   // also hosts split-K partials
+  const int adj = imax(imax(pad4i(big), pad4i(T * T * (V | 1))), imax(pad4i(2 * Ci * T + 2 * Ci), nw * 8 * 32 * 2));   // also hosts split-K partials
   a.o_sm = a.o_adj + adj;
   const int sm = pad4i(2 + 2 * T) + imax(pad4i(2 * Cg * V), pad4i(2 * Ch * V) + pad4i(2 * Ch * T)) + 3 * pad4i(2 * Co) +
                  2 * pad4i(2 * TV) + 2 * pad4i(Co) + pad4i(Hs);
   a.o_ring = a.o_sm + sm;
   const int budget = max_smem_floats - a.o_ring;
   const int widest = imax(pad8i(4 * Ch), imax(Cop, pad8i(2 * Cg)));      // longest streamed row
-  a.ring_floats = imax(widest, budget >= 24576 ? 1024 : (budget >= 8192 ? 512 : 256));   // per slot, 8 slots
-  int cur = a.o_ring + 8 * a.ring_floats;
+  a.ring_floats = imax(widest, budget >= 24576 ? 2048 : (budget >= 8192 ? 1024 : 512));  // per slot
+  int cur = a.o_ring + RING_SLOTS * a.ring_floats;
   // residency: mandatory small operands first, then by benefit per byte
   bool ok = true;
   auto take = [&](int f, bool mandatory) {
@@ -109,8 +111,8 @@ inline bool dstd_plan(DstdArgs& a, int nt, int max_smem_floats) {
                          CB_TCN_B_S, CB_TCN_B_T, CB_TCN_A_S, CB_TCN_A_T, CB_P_S_S, CB_P_S_T, CB_P_B_S, CB_P_B_T,
                          CB_P_A_S, CB_P_A_T, CB_CP_B, CB_CP_A, CB_RS_B};
   for (int f : vectors) take(f, true);
-  const int order[] = {CB_SE1_WT, CB_SE2_WT, CB_M0_WT, CB_M4_WT, CB_A0_WT, CB_TCN_WT_S, CB_TCN_WT_T, CB_CP_WT, CB_RS_WT, CB_E0_WT_S, CB_E0_WT_T,
-                       CB_E4_WT_S, CB_E4_WT_T, CB_TC6_WT_S, CB_TC6_WT_T, CB_JC6_WT_S, CB_JC6_WT_T, CB_G0_WT,
+  const int order[] = {CB_SE1_WT, CB_SE2_WT, CB_A0_WT, CB_TCN_WT_S, CB_TCN_WT_T, CB_CP_WT, CB_RS_WT, CB_E0_WT_S, CB_E0_WT_T,
+                       CB_E4_WT_S, CB_E4_WT_T, CB_TC6_WT_S, CB_TC6_WT_T, CB_JC6_WT_S, CB_JC6_WT_T, CB_G0_WT, CB_M0_WT, CB_M4_WT,
                        CB_TC3_WT_S, CB_TC3_WT_T, CB_JC3_WT_S, CB_JC3_WT_T, CB_G4_WT};
   for (int f : order) take(f, false);
   a.smem_floats = cur;
@@ -123,7 +125,6 @@ inline bool dstd_plan(DstdArgs& a, int nt, int max_smem_floats) {
 // Resident matrices are one chunk with no barrier; streamed ones go through the cp.async ring
 // (chunk c+1 is in flight while chunk c is consumed; one barrier per chunk).
 // ---------------------------------------------------------------------------------------------
-constexpr int RING_SLOTS = 8;
 
 CG_DEV void cp_async_wait_pending(int n) {      // wait until at most n of this thread's groups are in flight
 #ifndef CISTGCN_EMU
@@ -165,13 +166,13 @@ CG_DEV void for_weight_chunks(const float* __restrict__ g, const float* s, int K
 
 // ---------------------------------------------------------------------------------------------
 // Wide GEMM: out(m, n) = sum_k W[k][m] * X[k][n], X = up to two stacked row blocks (row stride LD) in
-// shared memory, N (a multiple of TN) columns; NP (1 or 2) independent problems of the same shape may
-// share the phase.  Work unit = one warp x TM rows x 32 lanes x TN contiguous columns: per k one
-// vector LDS of activations (conflict-free) + TM/4 broadcast LDS.128 of weights feed TM*TN FFMAs;
-// operands are double-buffered in registers so the loads of step k+1 fly under the FFMAs of step k.
+// shared memory, N (a multiple of TN) columns; NP independent problems of the same shape may share
+// the phase.  Work unit = one warp x TM rows x 32 lanes x TN contiguous columns: per k one vector LDS
+// of activations (conflict-free) + TM/4 broadcast LDS.128 of weights feed TM*TN FFMAs; the k loop
+// is unrolled 4x (measured: the compiler's own pipelining beats manual register double-buffering).
 // The epilogue gets whole rows: epi(problem, m, n0, float (&v)[TN]).
-// inplace: the epilogue may overwrite X; a pass then holds whole column groups and every thread
-// meets the two barriers of the pass (needs ceil(M/TM) <= NT/32).
+// INPLACE: the epilogue may overwrite X; a pass then holds whole column groups and every thread meets
+// the two barriers of the pass (needs ceil(M/TM) <= NT/32).
 // ---------------------------------------------------------------------------------------------
 struct WideOp {
   const float* wg;   // weights in the global blob
@@ -180,26 +181,25 @@ struct WideOp {
   const float* X2;   // next K2 rows (or nullptr)
 };
 
-template <int TM, int TN, int NT, class EPI>
-CG_DEV void gemm_wide(const WideOp (&ops)[2], int np, bool inplace, int Mp, int M, int K1, int K2, int LD, int N,
-                      float* ring, int rb, EPI epi) {
+template <int TM, int TN, int LD, int N, int NT, bool INPLACE, int NP, class EPI>
+CG_DEV void gemm_wide(const WideOp (&ops)[NP], int Mp, int M, int K1, int K2, float* ring, int rb, EPI epi) {
+  static_assert(N % TN == 0 && LD % TN == 0, "gemm_wide: columns must tile by TN");
   constexpr int NW = NT / 32;
-  const int ncols = N / TN;
-  const int ng = (ncols + 31) / 32;
+  constexpr int NCOLS = N / TN;
+  constexpr int NG = (NCOLS + 31) / 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mtiles = (M + TM - 1) / TM;
-  const int total = mtiles * ng * np;
-  const int per_pass = inplace ? (NW / mtiles) * mtiles : NW;
-#pragma unroll 1
+  const int total = mtiles * NG * NP;
+  const int per_pass = INPLACE ? (NW / mtiles) * mtiles : NW;
   for (int base = 0; base < total; base += per_pass) {
     const int item = base + warp;
     const int unit = item / mtiles;                  // (column group, problem)
-    const int prob = np == 1 ? 0 : unit % np;
-    const int slot = (unit / np) * 32 + lane;
-    const bool active = warp < per_pass && item < total && slot < ncols;
+    const int prob = NP == 1 ? 0 : unit % NP;
+    const int slot = (unit / NP) * 32 + lane;
+    const bool active = warp < per_pass && item < total && slot < NCOLS;
     const int m0 = active ? (item % mtiles) * TM : 0;
     const int n0 = active ? slot * TN : 0;
-    const WideOp op = (active && prob == 1) ? ops[1] : ops[0];
+    const WideOp op = (NP > 1 && active && prob == 1) ? ops[NP - 1] : ops[0];
     float acc[TM][TN];
 #pragma unroll
     for (int i = 0; i < TM; ++i)
@@ -212,22 +212,15 @@ CG_DEV void gemm_wide(const WideOp (&ops)[2], int np, bool inplace, int Mp, int 
         for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(w[i], x[j], acc[i][j]);
     };
     auto run = [&](const float* xp, const float* wp, int n) {
-      if (n <= 0) return;
-      float w0[TM], x0[TN], w1[TM], x1[TN];
-      lds_vec<TM>(wp, w0);
-      lds_vec<TN>(xp, x0);
-      int kk = 0;
-#pragma unroll 1
-      for (; kk + 2 <= n; kk += 2) {
-        lds_vec<TM>(wp + Mp, w1);
-        lds_vec<TN>(xp + LD, x1);
-        fma_step(w0, x0);
-        wp += 2 * Mp;
-        xp += 2 * LD;
-        if (kk + 2 < n) { lds_vec<TM>(wp, w0); lds_vec<TN>(xp, x0); }
-        fma_step(w1, x1);
+#pragma unroll 4
+      for (int kk = 0; kk < n; ++kk) {
+        float w[TM], x[TN];
+        lds_vec<TM>(wp, w);
+        lds_vec<TN>(xp, x);
+        wp += Mp;
+        xp += LD;
+        fma_step(w, x);
       }
-      if (kk < n) fma_step(w0, x0);
     };
     auto body = [&](const float* wc, int k0, int kc) {
       if (!active) return;
@@ -236,16 +229,31 @@ CG_DEV void gemm_wide(const WideOp (&ops)[2], int np, bool inplace, int Mp, int 
       kb = imax(k0, K1); ke = k0 + kc;
       if (kb < ke) run(op.X2 + (kb - K1) * LD + n0, wc + (kb - k0) * Mp + m0, ke - kb);
     };
-    if (np == 1) for_weight_chunks<NT>(ops[0].wg, ops[0].ws, K1 + K2, Mp, ring, rb, body);
-    else body(op.ws, 0, K1 + K2);                    // two-problem phases need resident weights
-    if (inplace) __syncthreads();
+    if constexpr (NP == 1) for_weight_chunks<NT>(ops[0].wg, ops[0].ws, K1 + K2, Mp, ring, rb, body);
+    else body(op.ws, 0, K1 + K2);                    // multi-problem phases need resident weights
+    if (INPLACE) __syncthreads();
     if (active) {
 #pragma unroll
       for (int i = 0; i < TM; ++i)
         if (m0 + i < M) epi(prob, m0 + i, n0, acc[i]);
     }
-    if (inplace) __syncthreads();
+    if (INPLACE) __syncthreads();
   }
+}
+
+// Row-tile dispatch: the widest TM that still gives every warp a work unit.
+template <int TN, int LD, int N, int NT, bool INPLACE, int NP, class EPI>
+CG_DEV void gemm_wide_auto(const WideOp (&ops)[NP], int Mp, int M, int K1, int K2, float* ring, int rb, EPI epi) {
+  constexpr int NW = NT / 32;
+  constexpr int NG = (((N / TN) + 31) / 32) * NP;
+  if (M % 16 == 0 && (M / 16) * NG >= NW)
+    gemm_wide<16, TN, LD, N, NT, INPLACE, NP>(ops, Mp, M, K1, K2, ring, rb, epi);
+  else if (M > 32 || ((M + 7) / 8) * NG >= NW)
+    gemm_wide<8, TN, LD, N, NT, INPLACE, NP>(ops, Mp, M, K1, K2, ring, rb, epi);
+  else if (M > 16 || ((M + 3) / 4) * NG >= NW)
+    gemm_wide<4, TN, LD, N, NT, INPLACE, NP>(ops, Mp, M, K1, K2, ring, rb, epi);
+  else
+    gemm_wide<2, TN, LD, N, NT, INPLACE, NP>(ops, Mp, M, K1, K2, ring, rb, epi);
 }
 
 // Vector store of TN contiguous floats to shared / global memory (p aligned to TN floats).
@@ -259,199 +267,129 @@ CG_DEV void store_vec(float* p, const float (&v)[TN]) {
   }
 }
 
-// ---- the block kernel calls ONE non-inlined instance of the wide GEMM; the epilogue is selected at
-//      run time (keeps the per-sample instruction footprint small enough for the instruction cache) ----
-enum WideEpi { WE_BIAS_PRELU = 0, WE_A0, WE_STORE_TAP, WE_STORE_T_TAP, WE_TCN, WE_OUT };
-
-struct WideCall {
-  WideOp ops[2];
-  int np, inplace, Mp, M, K1, K2, LD, N;
-  int kind;
-  const float* bias[2];      // per-row bias (per problem)
-  const float* slope[2];     // PReLU slope(s)
-  const float* scale[2];     // WE_TCN: prelu{1,2}.0 BN scale;          WE_OUT: SE gate
-  const float* shift[2];     // WE_TCN: prelu{1,2}.0 BN shift
-  const float* slope2[2];    // WE_TCN: prelu{1,2}.1 slope
-  const float* gatew[2];     // WE_TCN: context gate w_k
-  const float* resid;        // WE_TCN: identity residual tile (or nullptr); WE_OUT: compressor output tile
-  float* dst[2];             // destination tile(s)
-  float* tap;                // optional global copy (interpretability)
-  int i0, i1, i2, i3;        // kind-specific integers
-  int contiguous;
-};
-
-template <int TN, int NT>
-__device__ __noinline__ void wide_call(const WideCall& c, float* ring, int rb) {
-  gemm_wide<8, TN, NT>(c.ops, c.np, c.inplace != 0, c.Mp, c.M, c.K1, c.K2, c.LD, c.N, ring, rb,
-    [&](int p, int m, int n0, float (&v)[TN]) {
-      switch (c.kind) {
-        case WE_BIAS_PRELU: {                       // dst[m][n] = PReLU(v + bias[m])
-          const float b = c.bias[0][m], a = c.slope[0][0];
-#pragma unroll
-          for (int j = 0; j < TN; ++j) v[j] = prelu(v[j] + b, a);
-          store_vec<TN>(c.dst[0] + m * c.LD + n0, v);
-        } break;
-        case WE_A0: {                               // 4 stacked Map2Adj convs: i0 = Ch, i1 = tile stride
-          const int br = m / c.i0;
-          const float b = c.bias[0][m], a = c.slope[0][br];
-#pragma unroll
-          for (int j = 0; j < TN; ++j) v[j] = prelu(v[j] + b, a);
-          store_vec<TN>(c.dst[0] + (br >> 1) * c.i1 + (m - (br >> 1) * 2 * c.i0) * c.LD + n0, v);
-        } break;
-        case WE_STORE_TAP: {
-          store_vec<TN>(c.dst[0] + m * c.LD + n0, v);
-          if (c.tap) {
-#pragma unroll
-            for (int j = 0; j < TN; ++j) c.tap[m * c.LD + n0 + j] = v[j];
-          }
-        } break;
-        case WE_STORE_T_TAP: {                      // transposed store with row stride i0 (odd: fewer bank conflicts)
-#pragma unroll
-          for (int j = 0; j < TN; ++j) c.dst[0][(n0 + j) * c.i0 + m] = v[j];
-          if (c.tap) {
-#pragma unroll
-            for (int j = 0; j < TN; ++j) c.tap[m * c.LD + n0 + j] = v[j];
-          }
-        } break;
-        case WE_TCN: {                              // x = PReLU(v + b (+ xn)); u = PReLU(BN(w_k * x))
-          const float b = c.bias[p][m], a = c.slope[p][0];
-          const float sc = c.scale[p][m] * c.gatew[p][m], sh = c.shift[p][m], a2 = c.slope2[p][0];
-          float r[TN];
-          if (c.resid) lds_vec<TN>(c.resid + m * c.LD + n0, r);
-#pragma unroll
-          for (int j = 0; j < TN; ++j) {
-            float x = v[j] + b;
-            if (c.resid) x += r[j];
-            x = prelu(x, a);
-            v[j] = prelu(fmaf(sc, x, sh), a2);
-          }
-          store_vec<TN>(c.dst[p] + m * c.LD + n0, v);
-        } break;
-        default: {                                  // WE_OUT: out = c * gate + (v + bias) -> global, strides i0..i2, V = i3
-          const float g = c.scale[0][m], b = c.bias[0][m];
-          float cc[TN];
-          lds_vec<TN>(c.resid + m * c.LD + n0, cc);
-#pragma unroll
-          for (int j = 0; j < TN; ++j) v[j] = fmaf(cc[j], g, v[j] + b);
-          if (c.contiguous) store_vec<TN>(c.dst[0] + m * c.LD + n0, v);
-          else {
-            int t = n0 / c.i3, vv = n0 - t * c.i3;
-#pragma unroll
-            for (int j = 0; j < TN; ++j) {
-              c.dst[0][m * c.i0 + t * c.i1 + vv * c.i2] = v[j];
-              if (++vv == c.i3) { vv = 0; ++t; }
-            }
-          }
-        } break;
-      }
-    });
-}
-
 // ---------------------------------------------------------------------------------------------
-// Narrow GEMM (the collapsing (T,1) / (1,V) convolutions):  out(m, n) = sum_k W[k][m] * X(k, n) for
-// n < N <= 32, where k = (c, r), r < R and X(k, n) = X[c*CS + r*KS + n*NS].
-// Lane -> (row sub-tile, column); the K range is split over the warps left once every row tile has a
-// warp, partial sums meet in `partial` (>= NW*TM*32 floats).  out = acc + bias[m], optionally PReLU with
-// slope[m / slope_div], stored at dst[m*N + n].  Ends with a barrier.  One non-inlined instance.
+// Narrow GEMM (the collapsing (T,1) / (1,V) convolutions: X is a [K][N] view of a [C][T*V] tile,
+// N = V or T <= 32):  out(m, n) = sum_k W[k][m] * X[k*N + n].
+// Lane -> (row sub-tile, TN-wide column slot); the K range is split over the warps that are left
+// once every row tile has a warp, partial sums meet in `partial` (>= NW*TM*64 floats).
+// Ends with a barrier; epi runs once per output.
 // ---------------------------------------------------------------------------------------------
-struct NarrowCall {
-  const float* wg; const float* ws;
-  int Mp, M, K, N, R, CS, KS, NS;
-  const float* X;
-  const float* bias; const float* slope; int slope_div;     // slope == nullptr: no activation
-  float* dst;
-};
-
-template <int NT>
-__device__ __noinline__ void narrow_call(const NarrowCall& c, float* partial, float* ring, int rb) {
-  constexpr int NW = NT / 32, TM = 8;
+template <int TM, int N, bool STRIDED, int NT, class EPI>
+CG_DEV void gemm_narrow(const float* __restrict__ wg_, const float* ws, int Mp, int M, int K,
+                        const float* X, int R, int CS, float* partial, float* ring, int rb, EPI epi) {
+  // X(k, n): contiguous mode  X[k*N + n]  (the (T,1) conv over a [c][t][v] tile, N = V);
+  //          strided mode     X[(k / R)*CS + (k % R) + n*R]  (the (1,V) conv over the same layout: k = (c, v), n = t, R = V)
+  static_assert(N <= 32, "gemm_narrow: row length must fit a warp");
+  constexpr int NW = NT / 32;
+  constexpr int TN = (!STRIDED && N % 2 == 0) ? 2 : 1;
+  constexpr int NP = N / TN;
+  constexpr int MS = 32 / NP;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int N = c.N, M = c.M, Mp = c.Mp;
-  const int MS = 32 / N;
-  const int msub = lane / N, n = lane - msub * N;
+  const int msub = lane / NP, np = lane - msub * NP;
   const int mtiles = (M + TM - 1) / TM;
   const int mgroups = (mtiles + MS - 1) / MS;
-  const int wpg = imin(mgroups, NW);
   const int ksplit = imax(1, NW / mgroups);
-#pragma unroll 1
   for (int gbase = 0; gbase < mgroups; gbase += NW) {          // (one pass unless mgroups > NW)
-    const int mg = gbase + warp % wpg, ks = warp / wpg;
+    const int mg = gbase + warp % imin(mgroups, NW);
+    const int ks = warp / imin(mgroups, NW);
     const int mt = mg * MS + msub;
-    const bool active = ks < ksplit && mg < mgroups && msub < MS && mt < mtiles;
+    const bool active = ks < ksplit && mg < mgroups && lane < MS * NP && mt < mtiles;
     const int m0 = active ? mt * TM : 0;
-    float acc[TM];
+    const int n0 = active ? np * TN : 0;
+    float acc[TM][TN];
 #pragma unroll
-    for (int i = 0; i < TM; ++i) acc[i] = 0.f;
-    for_weight_chunks<NT>(c.wg, c.ws, c.K, Mp, ring, rb, [&](const float* wc, int k0, int kc) {
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for_weight_chunks<NT>(wg_, ws, K, Mp, ring, rb, [&](const float* wc, int k0, int kc) {
       if (!active) return;
       const int r0 = (kc * ks) / ksplit, r1 = (kc * (ks + 1)) / ksplit;
       const float* wp = wc + r0 * Mp + m0;
-      int cc = (k0 + r0) / c.R, rr = (k0 + r0) - cc * c.R;
-      const float* xp = c.X + cc * c.CS + rr * c.KS + (active ? n : 0) * c.NS;
-      const int wrap = c.CS - c.R * c.KS;
+      if constexpr (!STRIDED) {
+        const float* xp = X + (k0 + r0) * N + n0;
 #pragma unroll 4
-      for (int r = r0; r < r1; ++r) {
-        float w[TM];
-        lds_vec<TM>(wp, w);
-        const float x = *xp;
-        wp += Mp;
-        xp += c.KS;
-        if (++rr == c.R) { rr = 0; xp += wrap; }
+        for (int r = r0; r < r1; ++r) {
+          float w[TM], x[TN];
+          lds_vec<TM>(wp, w);
+          lds_vec<TN>(xp, x);
+          wp += Mp;
+          xp += N;
 #pragma unroll
-        for (int i = 0; i < TM; ++i) acc[i] = fmaf(w[i], x, acc[i]);
+          for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(w[i], x[j], acc[i][j]);
+        }
+      } else {
+        int cc = (k0 + r0) / R, rr = (k0 + r0) - cc * R;
+        const float* xp = X + cc * CS + rr + n0 * R;
+#pragma unroll 4
+        for (int r = r0; r < r1; ++r) {
+          float w[TM];
+          lds_vec<TM>(wp, w);
+          const float x = *xp;
+          wp += Mp;
+          ++xp;
+          if (++rr == R) { rr = 0; xp += CS - R; }
+#pragma unroll
+          for (int i = 0; i < TM; ++i) acc[i][0] = fmaf(w[i], x, acc[i][0]);
+        }
       }
     });
-    if (ksplit > 1) {
+    if (ksplit == 1) {
       if (active) {
 #pragma unroll
         for (int i = 0; i < TM; ++i)
-          if (m0 + i < M) partial[(ks * M + m0 + i) * N + n] = acc[i];
+          if (m0 + i < M) {
+#pragma unroll
+            for (int j = 0; j < TN; ++j) epi(m0 + i, n0 + j, acc[i][j]);
+          }
+      }
+      __syncthreads();
+    } else {
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+          if (m0 + i < M) {
+#pragma unroll
+            for (int j = 0; j < TN; ++j) partial[(ks * M + m0 + i) * N + n0 + j] = acc[i][j];
+          }
       }
       __syncthreads();
       for (int idx = threadIdx.x; idx < M * N; idx += NT) {
         float s = 0.f;
         for (int q = 0; q < ksplit; ++q) s += partial[q * M * N + idx];
-        const int m = idx / N;
-        s += c.bias[m];
-        if (c.slope) s = prelu(s, c.slope[m / c.slope_div]);
-        c.dst[idx] = s;
+        epi(idx / N, idx % N, s);
       }
-    } else if (active) {
-#pragma unroll
-      for (int i = 0; i < TM; ++i)
-        if (m0 + i < M) {
-          float s = acc[i] + c.bias[m0 + i];
-          if (c.slope) s = prelu(s, c.slope[(m0 + i) / c.slope_div]);
-          c.dst[(m0 + i) * N + n] = s;
-        }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Two-gate matvec with split-K over warps: y[g][m] = PReLU?(sum_k W_g[k][m] * x_g[k] + bias) with an
-// optional tail of rows multiplying a second vector shared by both gates.  Weights come straight from
-// L2 (or from their resident copy): every lane owns output columns (coalesced 128-byte rows) and keeps
-// 16 independent loads in flight, so the single-use weight matrix streams at bandwidth, not latency.
-// partial: >= NW * M floats.  Ends with a barrier.  One non-inlined instance.
-// ---------------------------------------------------------------------------------------------
-struct MatvecCall {
-  const float* wmat; int Mp, M, K1; const float* x1; int K2; const float* x2;
-  const float* bias; const float* slope;      // bias == nullptr: plain product
-  float* dst; float* tap0; float* tap1;       // dst[g*M + m]; optional global taps per gate
-};
+template <int N, bool STRIDED, int NT, class EPI>
+CG_DEV void gemm_narrow_auto(const float* __restrict__ wg_, const float* ws, int Mp, int M, int K,
+                             const float* X, int R, int CS, float* partial, float* ring, int rb, EPI epi) {
+  if (M >= 16) gemm_narrow<8, N, STRIDED, NT>(wg_, ws, Mp, M, K, X, R, CS, partial, ring, rb, epi);
+  else if (M >= 8) gemm_narrow<4, N, STRIDED, NT>(wg_, ws, Mp, M, K, X, R, CS, partial, ring, rb, epi);
+  else gemm_narrow<2, N, STRIDED, NT>(wg_, ws, Mp, M, K, X, R, CS, partial, ring, rb, epi);
+}
 
-template <int NT>
-__device__ __noinline__ void matvec_call(const MatvecCall& c, float* partial) {
+// ---------------------------------------------------------------------------------------------
+// Two-gate matvec with split-K over warps: y[g][m] = sum_k W_g[k][m] * x_g[k] (+ optional tail rows
+// multiplying a second vector shared by both gates).  Weights come straight from L2 (or from their
+// resident copy): every lane owns output columns (coalesced 128-byte rows) and keeps UNR independent
+// loads in flight, so the single-use weight matrix streams at bandwidth instead of latency.
+// partial: >= NW * Mtot floats.  Ends with a barrier.
+// ---------------------------------------------------------------------------------------------
+template <int NT, class EPI>
+CG_DEV void gate_matvec(const float* wmat, int Mp, int M, int K1, const float* x1, int x1_stride,
+                        int K2, const float* x2, float* partial, EPI epi) {
   constexpr int NW = NT / 32, HW = NW / 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = warp / HW, ks = warp % HW;
-  const int M = c.M, Mp = c.Mp, K1 = c.K1, K = c.K1 + c.K2;
+  const int K = K1 + K2;
   const int r0 = (K * ks) / HW, r1 = (K * (ks + 1)) / HW;
-  const float* wgt = c.wmat + (size_t)g * K * Mp;
-  const float* xa = c.x1 + g * K1;
-#pragma unroll 1
+  const float* wgt = wmat + (size_t)g * K * Mp;
+  const float* xa = x1 + g * x1_stride;
   for (int mb = 0; mb < M; mb += 32) {
     const int m = mb + lane;
     const int mc = m < M ? m : M - 1;
@@ -459,8 +397,8 @@ __device__ __noinline__ void matvec_call(const MatvecCall& c, float* partial) {
     const int e1 = imin(r1, K1);
 #pragma unroll 16
     for (int k = r0; k < e1; ++k) acc = fmaf(wgt[(size_t)k * Mp + mc], xa[k], acc);
-#pragma unroll 4
-    for (int k = imax(r0, K1); k < r1; ++k) acc = fmaf(wgt[(size_t)k * Mp + mc], c.x2[k - K1], acc);
+#pragma unroll 16
+    for (int k = imax(r0, K1); k < r1; ++k) acc = fmaf(wgt[(size_t)k * Mp + mc], x2[k - K1], acc);
     if (m < M) partial[(ks * 2 + g) * M + m] = acc;
   }
   __syncthreads();
@@ -468,11 +406,7 @@ __device__ __noinline__ void matvec_call(const MatvecCall& c, float* partial) {
     float s = 0.f;
 #pragma unroll
     for (int q = 0; q < HW; ++q) s += partial[q * 2 * M + idx];
-    const int gg = idx / M;
-    if (c.bias) s = prelu(s + c.bias[idx], c.slope[gg]);
-    c.dst[idx] = s;
-    float* tp = gg == 0 ? c.tap0 : c.tap1;
-    if (tp) tp[idx - gg * M] = s;
+    epi(idx / M, idx % M, s);
   }
   __syncthreads();
 }
@@ -480,12 +414,11 @@ __device__ __noinline__ void matvec_call(const MatvecCall& c, float* partial) {
 // ---------------------------------------------------------------------------------------------
 // adjacency products (ConvTemporalGraphical, CISTGCN.py:110,117,123)
 // ---------------------------------------------------------------------------------------------
-// "space" domain: g1[c][q][v] = sum_t XN[c][t][v] * Adj_s[v][t][q], Adj_s held as adjT[(t*T+q)*VP + v].
-template <int T, int V, int NT>
-__device__ __noinline__ void gcn_space(const float* XN, const float* adjT, float* G, int C) {
-  constexpr int TV = T * V, TC = 4, VP = V | 1;
+// "space" domain: g1[c][q][v] = sum_t XN[c][t][v] * Adj_s[v][t][q], Adj_s held as adjT[(t*T+q)*VP + v], VP = V|1.
+template <int T, int V, int TC, int NT>
+CG_DEV void gcn_space(const float* XN, const float* adjT, float* G, int C) {
+  constexpr int TV = T * V, VP = V | 1;
   const int nct = (C + TC - 1) / TC;
-#pragma unroll 1
   for (int item = threadIdx.x; item < nct * V; item += NT) {
     const int v = item % V, c0 = (item / V) * TC;
     float acc[TC][T];
@@ -493,7 +426,7 @@ __device__ __noinline__ void gcn_space(const float* XN, const float* adjT, float
     for (int i = 0; i < TC; ++i)
 #pragma unroll
       for (int q = 0; q < T; ++q) acc[i][q] = 0.f;
-#pragma unroll 1
+#pragma unroll 2
     for (int t = 0; t < T; ++t) {
       float xv[TC];
 #pragma unroll
@@ -515,13 +448,12 @@ __device__ __noinline__ void gcn_space(const float* XN, const float* adjT, float
 }
 
 // "time" domain: g2[c][t][w] = sum_v XN[c][t][v] * Adj_t[t][v][w]  (natural layout).
-template <int T, int V, int NT>
-__device__ __noinline__ void gcn_time(const float* XN, const float* adj, float* G, int C) {
-  constexpr int TV = T * V, VV = V * V, TC = 4;
+template <int T, int V, int TC, int NT>
+CG_DEV void gcn_time(const float* XN, const float* adj, float* G, int C) {
+  constexpr int TV = T * V, VV = V * V;
   constexpr int TW = (V % 11 == 0) ? 11 : ((V % 9 == 0) ? 9 : ((V % 5 == 0) ? 5 : 1));
   constexpr int NWG = V / TW;
   const int nct = (C + TC - 1) / TC;
-#pragma unroll 1
   for (int item = threadIdx.x; item < nct * T * NWG; item += NT) {
     const int w0 = (item % NWG) * TW, t = (item / NWG) % T, c0 = (item / (NWG * T)) * TC;
     float acc[TC][TW];
@@ -529,7 +461,7 @@ __device__ __noinline__ void gcn_time(const float* XN, const float* adj, float* 
     for (int i = 0; i < TC; ++i)
 #pragma unroll
       for (int j = 0; j < TW; ++j) acc[i][j] = 0.f;
-#pragma unroll 1
+#pragma unroll 2
     for (int v = 0; v < V; ++v) {
       float xv[TC];
 #pragma unroll
@@ -555,7 +487,7 @@ __device__ __noinline__ void gcn_time(const float* XN, const float* adj, float* 
 template <int T, int V, int NT>
 __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
   CG_DYN_SMEM(smem);
-  constexpr int TV = T * V, TT = T * T, VV = V * V, VP = V | 1;
+  constexpr int TV = T * V, TT = T * T, VV = V * V, VP = V | 1;   // VP: odd row stride of the transposed Adj_s
   constexpr int NW = NT / 32;
   constexpr int TNW = (TV % 4 == 0) ? 4 : 2;            // column vector width of the wide GEMMs
   constexpr int TNS = (TT % 4 == 0) ? 4 : 2;            // ... of the joint-axis expansor (N = T*T)
@@ -604,7 +536,6 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
   cp_async_wait_all();
   __syncthreads();
 
-#pragma unroll 1
   for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
     CG_STAMP(0);
     // ---------------- P1: load + global_norm (:375); block 0 builds the 10 features (:568-577)
@@ -646,7 +577,6 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
       const float* gb = P(CB_GN_B);
       if (sv == 1 && st == V && sc == TV && (TV % 4) == 0) {       // contiguous tile: 128-bit loads
         const float4* s4 = reinterpret_cast<const float4*>(src);
-#pragma unroll 4
         for (int i = tid; i < Ci * TV / 4; i += NT) {
           const int c = (i * 4) / TV;
           float4 v4 = __ldg(s4 + i);
@@ -667,13 +597,14 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
     // ---------------- P2: statistics (:360-371), all Bessel-corrected like torch.std
     for (int r = tid; r < Ci * T; r += NT) {                  // r = c*T + t, row of V joints
       const float* xp = XN + (r / T) * TV + (r % T) * V;
+      float xv[V];
       float s = 0.f;
-#pragma unroll 2
-      for (int v = 0; v < V; ++v) s += xp[v];
+#pragma unroll
+      for (int v = 0; v < V; ++v) { xv[v] = xp[v]; s += xv[v]; }
       const float mu = s / V;
       float q = 0.f;
-#pragma unroll 2
-      for (int v = 0; v < V; ++v) { const float dd = xp[v] - mu; q = fmaf(dd, dd, q); }
+#pragma unroll
+      for (int v = 0; v < V; ++v) { const float dd = xv[v] - mu; q = fmaf(dd, dd, q); }
       rowmean[r] = mu;
       rowvar[r] = q / (V - 1);
     }
@@ -682,40 +613,43 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
       // channel level: mean / std over (T,V) per channel, then mean / std over channels (lanes own channels)
       float sm = 0.f, ssd = 0.f;
       float sdv[2] = {0.f, 0.f};
-#pragma unroll 1
       for (int c = lane, it = 0; c < Ci; c += 32, ++it) {
+        float rm[T];
         float s = 0.f;
-        for (int t = 0; t < T; ++t) s += rowmean[c * T + t];
+#pragma unroll
+        for (int t = 0; t < T; ++t) { rm[t] = rowmean[c * T + t]; s += rm[t]; }
         const float cm = s / T;
         float ss = 0.f;
-        for (int t = 0; t < T; ++t) { const float dm = rowmean[c * T + t] - cm; ss += (V - 1) * rowvar[c * T + t] + V * dm * dm; }
+#pragma unroll
+        for (int t = 0; t < T; ++t) { const float dm = rm[t] - cm; ss += (V - 1) * rowvar[c * T + t] + V * dm * dm; }
         const float sd = sqrtf(ss / (TV - 1));
         sm += cm;
         ssd += sd;
-        if (it == 0) sdv[0] = sd; else sdv[1] = sd;
+        if (it < 2) sdv[it] = sd;
       }
       sm = warp_sum(sm);
       ssd = warp_sum(ssd);
       const float m2 = ssd / Ci;
       float q = 0.f;
-      if (lane < Ci) { const float dd = sdv[0] - m2; q = dd * dd; }
-      if (lane + 32 < Ci) { const float dd = sdv[1] - m2; q = fmaf(dd, dd, q); }
+      for (int c = lane, it = 0; c < Ci; c += 32, ++it) { const float dd = sdv[it < 2 ? it : 1] - m2; q = fmaf(dd, dd, q); }
       q = warp_sum(q);
       if (lane == 0) { stats[0] = sm / Ci; stats[1 + T] = sqrtf(q / (Ci - 1)); }
     } else {
       // frame level: per t, mean over channels of the row means and std over channels of the row stds
-#pragma unroll 1
       for (int t = warp; t < T; t += NW - 1) {
         float s = 0.f, s2 = 0.f;
         float sdv[2] = {0.f, 0.f};
-        if (lane < Ci) { s = rowmean[lane * T + t]; sdv[0] = sqrtf(rowvar[lane * T + t]); s2 = sdv[0]; }
-        if (lane + 32 < Ci) { s += rowmean[(lane + 32) * T + t]; sdv[1] = sqrtf(rowvar[(lane + 32) * T + t]); s2 += sdv[1]; }
+        for (int c = lane, it = 0; c < Ci; c += 32, ++it) {
+          s += rowmean[c * T + t];
+          const float sd = sqrtf(rowvar[c * T + t]);
+          s2 += sd;
+          if (it < 2) sdv[it] = sd;
+        }
         s = warp_sum(s);
         s2 = warp_sum(s2);
         const float m2 = s2 / Ci;
         float q = 0.f;
-        if (lane < Ci) { const float dd = sdv[0] - m2; q = dd * dd; }
-        if (lane + 32 < Ci) { const float dd = sdv[1] - m2; q = fmaf(dd, dd, q); }
+        for (int c = lane, it = 0; c < Ci; c += 32, ++it) { const float dd = sdv[it < 2 ? it : 1] - m2; q = fmaf(dd, dd, q); }
         q = warp_sum(q);
         if (lane == 0) { stats[1 + t] = s / Ci; stats[2 + T + t] = sqrtf(q / (Ci - 1)); }
       }
@@ -725,59 +659,61 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
 
     // ---------------- P3: gate conv (T,1) + BN + PReLU -> h1  (:323-326)
     {
-      NarrowCall c;
-      c.wg = G(CB_G0_WT); c.ws = RS(CB_G0_WT); c.Mp = pad8i(2 * Cg); c.M = 2 * Cg; c.K = Ci * T;
-      c.N = V; c.R = T; c.CS = TV; c.KS = V; c.NS = 1; c.X = XN;
-      c.bias = P(CB_G0_B); c.slope = P(CB_G0_A); c.slope_div = Cg; c.dst = h1;
-      narrow_call<NT>(c, partial, ring, rb);
+      const float* gb = P(CB_G0_B);
+      const float* ga = P(CB_G0_A);
+      gemm_narrow_auto<V, false, NT>(G(CB_G0_WT), RS(CB_G0_WT), pad8i(2 * Cg), 2 * Cg, Ci * T, XN, T, TV, partial, ring, rb,
+                              [&](int m, int v, float acc) { h1[m * V + v] = prelu(acc + gb[m], ga[m / Cg]); });
     }
     CG_STAMP(3);
     // ---------------- P4: gate conv (1,V) -> h2 ; MLP -> w1, w2  (:327-352, 378-384)
     {
-      MatvecCall c;
-      c.wmat = P(CB_G4_WT); c.Mp = Cop; c.M = Co; c.K1 = Cg * V; c.x1 = h1; c.K2 = 0; c.x2 = nullptr;
-      c.bias = P(CB_G4_B); c.slope = P(CB_G4_A); c.dst = h2; c.tap0 = nullptr; c.tap1 = nullptr;
-      matvec_call<NT>(c, partial);
-      c.wmat = P(CB_M0_WT); c.K1 = Co; c.x1 = h2; c.K2 = 2 + 2 * T; c.x2 = stats;
-      c.bias = P(CB_M0_B); c.slope = P(CB_M0_A); c.dst = zg;
-      matvec_call<NT>(c, partial);
-      c.wmat = P(CB_M4_WT); c.K1 = Co; c.x1 = zg; c.K2 = 0; c.x2 = nullptr;
-      c.bias = nullptr; c.slope = nullptr; c.dst = wg;
-      c.tap0 = a.tap_w1 ? a.tap_w1 + (size_t)b * Co : nullptr;
-      c.tap1 = a.tap_w2 ? a.tap_w2 + (size_t)b * Co : nullptr;
-      matvec_call<NT>(c, partial);
+      const float* b4 = P(CB_G4_B);
+      const float* a4 = P(CB_G4_A);
+      gate_matvec<NT>(P(CB_G4_WT), Cop, Co, Cg * V, h1, Cg * V, 0, nullptr, partial,
+                      [&](int g, int o, float acc) { h2[g * Co + o] = prelu(acc + b4[g * Co + o], a4[g]); });
+      const float* b0 = P(CB_M0_B);
+      const float* a0 = P(CB_M0_A);
+      gate_matvec<NT>(P(CB_M0_WT), Cop, Co, Co, h2, Co, 2 + 2 * T, stats, partial,
+                      [&](int g, int o, float acc) { zg[g * Co + o] = prelu(acc + b0[g * Co + o], a0[g]); });
+      gate_matvec<NT>(P(CB_M4_WT), Cop, Co, Co, zg, Co, 0, nullptr, partial,
+                      [&](int g, int o, float acc) {
+                        wg[g * Co + o] = acc;
+                        float* tp = g == 0 ? a.tap_w1 : a.tap_w2;
+                        if (tp) tp[(size_t)b * Co + o] = acc;
+                      });
     }
     CG_STAMP(4);
 
-    WideCall wc;
-    wc.np = 1; wc.inplace = 0; wc.tap = nullptr; wc.resid = nullptr; wc.contiguous = 0;
-    wc.ops[1].wg = nullptr; wc.ops[1].ws = nullptr; wc.ops[1].X1 = nullptr; wc.ops[1].X2 = nullptr;
-    auto set_op = [&](int i, int f, const float* x1, const float* x2) {
-      wc.ops[i].wg = G(f); wc.ops[i].ws = RS(f); wc.ops[i].X1 = x1; wc.ops[i].X2 = x2;
-    };
-
     if (interp) {
       // ---------------- P5: Map2Adj first 1x1 convs (4 stacked) + BN + PReLU -> A (dsgn maps), B (tsgn maps)
-      set_op(0, CB_A0_WT, XN, nullptr);
-      wc.kind = WE_A0; wc.Mp = pad8i(4 * Ch); wc.M = 4 * Ch; wc.K1 = Ci; wc.K2 = 0; wc.LD = TV; wc.N = TV;
-      wc.bias[0] = P(CB_A0_B); wc.slope[0] = P(CB_A0_A); wc.dst[0] = A; wc.i0 = Ch; wc.i1 = a.tile;
-      wide_call<TNW, NT>(wc, ring, rb);
+      {
+        const float* ab = P(CB_A0_B);
+        const float* aa = P(CB_A0_A);
+        const WideOp ops[1] = {{G(CB_A0_WT), RS(CB_A0_WT), XN, nullptr}};
+        gemm_wide_auto<TNW, TV, TV, NT, false, 1>(ops, pad8i(4 * Ch), 4 * Ch, Ci, 0, ring, rb,
+          [&](int, int m, int n0, float (&v)[TNW]) {
+            const int br = m / Ch, r = m - br * Ch;
+            const float bias = ab[m], sl = aa[br];
+            float* tl = A + (br >> 1) * a.tile;
+#pragma unroll
+            for (int j = 0; j < TNW; ++j) v[j] = prelu(v[j] + bias, sl);
+            store_vec<TNW>(tl + ((br & 1) * Ch + r) * TV + n0, v);       // both maps stay [c][t][v]
+          });
+      }
       __syncthreads();
       CG_STAMP(5);
-      // ---------------- P6: collapsing convs (T,1) / (1,V) + BN  (:141-142, 149-150); maps are [c][t][v]
-#pragma unroll 1
+      // ---------------- P6: collapsing convs (T,1) / (1,V) + BN  (:141-142, 149-150)
+#pragma unroll
       for (int L = 0; L < 2; ++L) {
         const float* tl = A + L * a.tile;
-        NarrowCall c;
-        c.Mp = pad8i(Ch); c.M = Ch; c.slope = nullptr; c.slope_div = 1;
-        c.wg = G(CB_TC3_WT_S + L); c.ws = RS(CB_TC3_WT_S + L); c.K = Ch * T;
-        c.N = V; c.R = T; c.CS = TV; c.KS = V; c.NS = 1; c.X = tl;
-        c.bias = P(CB_TC3_B_S + L); c.dst = dseqp + L * Ch * V;
-        narrow_call<NT>(c, partial, ring, rb);
-        c.wg = G(CB_JC3_WT_S + L); c.ws = RS(CB_JC3_WT_S + L); c.K = Ch * V;
-        c.N = T; c.R = V; c.CS = TV; c.KS = 1; c.NS = V; c.X = tl + Ch * TV;
-        c.bias = P(CB_JC3_B_S + L); c.dst = dspp + L * Ch * T;
-        narrow_call<NT>(c, partial, ring, rb);
+        const float* tb = P(CB_TC3_B_S + L);
+        const float* jb = P(CB_JC3_B_S + L);
+        float* dq = dseqp + L * Ch * V;
+        float* dp = dspp + L * Ch * T;
+        gemm_narrow_auto<V, false, NT>(G(CB_TC3_WT_S + L), RS(CB_TC3_WT_S + L), pad8i(Ch), Ch, Ch * T, tl, T, TV, partial, ring, rb,
+                                [&](int m, int v, float acc) { dq[m * V + v] = acc + tb[m]; });
+        gemm_narrow_auto<T, true, NT>(G(CB_JC3_WT_S + L), RS(CB_JC3_WT_S + L), pad8i(Ch), Ch, Ch * V, tl + Ch * TV, V, TV, partial, ring, rb,
+                                [&](int m, int t, float acc) { dp[m * T + t] = acc + jb[m]; });
       }
       CG_STAMP(6);
       // ---------------- P7: dim_seq / dim_space (last 1x1 of each compress branch)  (:144, 152)
@@ -807,17 +743,33 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
       }
       __syncthreads();
       CG_STAMP(7);
-      // ---------------- P9: expansor over the joint axis -> Adj_s (kept as [t][q][v], row stride VP)  (:165-170)
-      set_op(0, CB_E0_WT_S, ADJ, nullptr);
-      wc.kind = WE_BIAS_PRELU; wc.Mp = pad8i(V); wc.M = V; wc.K1 = V; wc.K2 = 0; wc.LD = TT; wc.N = TT;
-      wc.bias[0] = P(CB_E0_B_S); wc.slope[0] = P(CB_E0_A_S); wc.dst[0] = Bt;
-      wide_call<TNS, NT>(wc, ring, rb);
+      // ---------------- P9: expansor over the joint axis -> Adj_s (kept as [t][q][v])  (:165-170)
+      {
+        const float* eb = P(CB_E0_B_S);
+        const float ea = P(CB_E0_A_S)[0];
+        const WideOp ops[1] = {{G(CB_E0_WT_S), RS(CB_E0_WT_S), ADJ, nullptr}};
+        gemm_wide_auto<TNS, TT, TT, NT, false, 1>(ops, pad8i(V), V, V, 0, ring, rb,
+          [&](int, int m, int n0, float (&v)[TNS]) {
+            const float bias = eb[m];
+#pragma unroll
+            for (int j = 0; j < TNS; ++j) v[j] = prelu(v[j] + bias, ea);
+            store_vec<TNS>(Bt + m * TT + n0, v);
+          });
+      }
       __syncthreads();
-      set_op(0, CB_E4_WT_S, Bt, nullptr);
-      wc.kind = WE_STORE_T_TAP; wc.dst[0] = ADJ; wc.i0 = VP;
-      wc.tap = a.tap_adj_s ? a.tap_adj_s + (size_t)b * V * TT : nullptr;
-      wide_call<TNS, NT>(wc, ring, rb);
-      wc.tap = nullptr;
+      {
+        float* tp = a.tap_adj_s ? a.tap_adj_s + (size_t)b * V * TT : nullptr;
+        const WideOp ops[1] = {{G(CB_E4_WT_S), RS(CB_E4_WT_S), Bt, nullptr}};
+        gemm_wide_auto<TNS, TT, TT, NT, false, 1>(ops, pad8i(V), V, V, 0, ring, rb,
+          [&](int, int m, int n0, float (&v)[TNS]) {
+#pragma unroll
+            for (int j = 0; j < TNS; ++j) ADJ[(n0 + j) * VP + m] = v[j];
+            if (tp) {
+#pragma unroll
+              for (int j = 0; j < TNS; ++j) tp[m * TT + n0 + j] = v[j];
+            }
+          });
+      }
       __syncthreads();
     } else {
       const float* as = W + d[CB_ADJ_S];                      // static (V,T,T) -> [t][q][v]
@@ -826,7 +778,8 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
     }
     CG_STAMP(8);
     // ---------------- P10: g1 = XN x_t Adj_s -> A
-    gcn_space<T, V, NT>(XN, ADJ, A, Ci);
+    if (Ci >= 4) gcn_space<T, V, 4, NT>(XN, ADJ, A, Ci);
+    else gcn_space<T, V, 1, NT>(XN, ADJ, A, Ci);
     __syncthreads();
     CG_STAMP(9);
     // ---------------- P11: time-domain outer product + expansor over the frame axis -> Adj_t
@@ -836,16 +789,31 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
         ADJ[i] = dsp[TV + v * T + tq] * dseq[TV + tq * V + w];
       }
       __syncthreads();
-      set_op(0, CB_E0_WT_T, ADJ, nullptr);
-      wc.kind = WE_BIAS_PRELU; wc.Mp = pad8i(T); wc.M = T; wc.K1 = T; wc.K2 = 0; wc.LD = VV; wc.N = VV;
-      wc.bias[0] = P(CB_E0_B_T); wc.slope[0] = P(CB_E0_A_T); wc.dst[0] = Bt;
-      wide_call<TNT, NT>(wc, ring, rb);
+      {
+        const float* eb = P(CB_E0_B_T);
+        const float ea = P(CB_E0_A_T)[0];
+        const WideOp ops[1] = {{G(CB_E0_WT_T), RS(CB_E0_WT_T), ADJ, nullptr}};
+        gemm_wide_auto<TNT, VV, VV, NT, false, 1>(ops, pad8i(T), T, T, 0, ring, rb,
+          [&](int, int m, int n0, float (&v)[TNT]) {
+            const float bias = eb[m];
+#pragma unroll
+            for (int j = 0; j < TNT; ++j) v[j] = prelu(v[j] + bias, ea);
+            store_vec<TNT>(Bt + m * VV + n0, v);
+          });
+      }
       __syncthreads();
-      set_op(0, CB_E4_WT_T, Bt, nullptr);
-      wc.kind = WE_STORE_TAP; wc.dst[0] = ADJ;
-      wc.tap = a.tap_adj_t ? a.tap_adj_t + (size_t)b * T * VV : nullptr;
-      wide_call<TNT, NT>(wc, ring, rb);
-      wc.tap = nullptr;
+      {
+        float* tp = a.tap_adj_t ? a.tap_adj_t + (size_t)b * T * VV : nullptr;
+        const WideOp ops[1] = {{G(CB_E4_WT_T), RS(CB_E4_WT_T), Bt, nullptr}};
+        gemm_wide_auto<TNT, VV, VV, NT, false, 1>(ops, pad8i(T), T, T, 0, ring, rb,
+          [&](int, int m, int n0, float (&v)[TNT]) {
+            store_vec<TNT>(ADJ + m * VV + n0, v);
+            if (tp) {
+#pragma unroll
+              for (int j = 0; j < TNT; ++j) tp[m * VV + n0 + j] = v[j];
+            }
+          });
+      }
     } else {
       const float* at = W + d[CB_ADJ_T];
       for (int i = tid; i < T * VV; i += NT) ADJ[i] = __ldg(at + i);
@@ -853,45 +821,56 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
     __syncthreads();
     CG_STAMP(10);
     // ---------------- P12: g2 = XN x_v Adj_t -> B
-    gcn_time<T, V, NT>(XN, ADJ, Bt, Ci);
+    if (Ci >= 4) gcn_time<T, V, 4, NT>(XN, ADJ, Bt, Ci);
+    else gcn_time<T, V, 1, NT>(XN, ADJ, Bt, Ci);
     __syncthreads();
     CG_STAMP(11);
     // ---------------- P13: x_k = PReLU(BN(W g_k + b) + res); u_k = PReLU(BN(w_k * x_k))   (:266-268, 388)
     {
-      wc.kind = WE_TCN; wc.inplace = 1; wc.Mp = Cop; wc.M = Co; wc.K1 = Ci; wc.K2 = has_res ? Ci : 0; wc.LD = TV; wc.N = TV;
-      wc.resid = has_res ? nullptr : XN;
+      auto tcn_epi = [&](int L, int m, int n0, float (&v)[TNW]) {
+        float* Gt = L == 0 ? A : Bt;
+        const float tbm = P(CB_TCN_B_S + L)[m], ta = P(CB_TCN_A_S + L)[0];
+        const float sc = P(CB_P_S_S + L)[m] * wg[L * Co + m], pbm = P(CB_P_B_S + L)[m], pa = P(CB_P_A_S + L)[0];
+        float r[TNW];
+        if (!has_res) lds_vec<TNW>(XN + m * TV + n0, r);
 #pragma unroll
-      for (int L = 0; L < 2; ++L) {
-        wc.bias[L] = P(CB_TCN_B_S + L); wc.slope[L] = P(CB_TCN_A_S + L); wc.scale[L] = P(CB_P_S_S + L);
-        wc.shift[L] = P(CB_P_B_S + L); wc.slope2[L] = P(CB_P_A_S + L); wc.gatew[L] = wg + L * Co;
-        wc.dst[L] = L == 0 ? A : Bt;
-      }
+        for (int j = 0; j < TNW; ++j) {
+          float x = v[j] + tbm;
+          if (!has_res) x += r[j];
+          x = prelu(x, ta);
+          v[j] = prelu(fmaf(sc, x, pbm), pa);
+        }
+        store_vec<TNW>(Gt + m * TV + n0, v);
+      };
+      const int K2 = has_res ? Ci : 0;
       if (RS(CB_TCN_WT_S) && RS(CB_TCN_WT_T)) {            // both resident: one phase for both domains
-        set_op(0, CB_TCN_WT_S, A, XN);
-        set_op(1, CB_TCN_WT_T, Bt, XN);
-        wc.np = 2;
-        wide_call<TNW, NT>(wc, ring, rb);
-        wc.np = 1;
+        const WideOp ops[2] = {{G(CB_TCN_WT_S), RS(CB_TCN_WT_S), A, XN}, {G(CB_TCN_WT_T), RS(CB_TCN_WT_T), Bt, XN}};
+        gemm_wide_auto<TNW, TV, TV, NT, true, 2>(ops, Cop, Co, Ci, K2, ring, rb, tcn_epi);
       } else {
-        set_op(0, CB_TCN_WT_S, A, XN);
-        wide_call<TNW, NT>(wc, ring, rb);
-        set_op(0, CB_TCN_WT_T, Bt, XN);                    // problem 0 slot, tsgn operands
-        wc.bias[0] = wc.bias[1]; wc.slope[0] = wc.slope[1]; wc.scale[0] = wc.scale[1]; wc.shift[0] = wc.shift[1];
-        wc.slope2[0] = wc.slope2[1]; wc.gatew[0] = wc.gatew[1]; wc.dst[0] = Bt;
-        wide_call<TNW, NT>(wc, ring, rb);
+#pragma unroll
+        for (int L = 0; L < 2; ++L) {
+          const WideOp ops[1] = {{G(CB_TCN_WT_S + L), RS(CB_TCN_WT_S + L), L == 0 ? A : Bt, XN}};
+          gemm_wide_auto<TNW, TV, TV, NT, true, 1>(ops, Cop, Co, Ci, K2, ring, rb,
+            [&](int, int m, int n0, float (&v)[TNW]) { tcn_epi(L, m, n0, v); });
+        }
       }
-      wc.resid = nullptr;
     }
     CG_STAMP(12);
     // ---------------- P14: compressor 1x1 over cat(u1, u2) + BN + PReLU -> A   (:305-307)
-    set_op(0, CB_CP_WT, A, Bt);
-    wc.kind = WE_BIAS_PRELU; wc.inplace = 1; wc.Mp = Cop; wc.M = Co; wc.K1 = Co; wc.K2 = Co; wc.LD = TV; wc.N = TV;
-    wc.bias[0] = P(CB_CP_B); wc.slope[0] = P(CB_CP_A); wc.dst[0] = A;
-    wide_call<TNW, NT>(wc, ring, rb);
-    wc.inplace = 0;
+    {
+      const float* cb = P(CB_CP_B);
+      const float ca = P(CB_CP_A)[0];
+      const WideOp ops[1] = {{G(CB_CP_WT), RS(CB_CP_WT), A, Bt}};
+      gemm_wide_auto<TNW, TV, TV, NT, true, 1>(ops, Cop, Co, Co, Co, ring, rb,
+        [&](int, int m, int n0, float (&v)[TNW]) {
+          const float bias = cb[m];
+#pragma unroll
+          for (int j = 0; j < TNW; ++j) v[j] = prelu(v[j] + bias, ca);
+          store_vec<TNW>(A + m * TV + n0, v);
+        });
+    }
     CG_STAMP(13);
     // ---------------- P15-P17: squeeze-excitation (SE.py:37-41)
-#pragma unroll 1
     for (int m = warp; m < Co; m += NW) {
       float s = 0.f;
       for (int n = lane; n < TV; n += 32) s += A[m * TV + n];
@@ -899,7 +878,6 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
       if (lane == 0) semean[m] = s / TV;
     }
     __syncthreads();
-#pragma unroll 1
     for (int h = warp; h < Hs; h += NW) {
       const float* wt = P(CB_SE1_WT) + h;
       float acc = 0.f;
@@ -922,14 +900,27 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
       const int sc = d[CB_OUT_SC], st = d[CB_OUT_ST], sv = d[CB_OUT_SV];
       const bool contiguous = sv == 1 && st == V && sc == TV && (TV % 4) == 0;
       if (has_res) {
-        set_op(0, CB_RS_WT, XN, nullptr);
-        wc.kind = WE_OUT; wc.Mp = Cop; wc.M = Co; wc.K1 = Ci; wc.K2 = 0; wc.LD = TV; wc.N = TV;
-        wc.bias[0] = P(CB_RS_B); wc.scale[0] = gate; wc.resid = A; wc.dst[0] = dst;
-        wc.i0 = sc; wc.i1 = st; wc.i2 = sv; wc.i3 = V; wc.contiguous = contiguous ? 1 : 0;
-        wide_call<TNW, NT>(wc, ring, rb);
+        const float* rbias = P(CB_RS_B);
+        const WideOp ops[1] = {{G(CB_RS_WT), RS(CB_RS_WT), XN, nullptr}};
+        gemm_wide_auto<TNW, TV, TV, NT, false, 1>(ops, Cop, Co, Ci, 0, ring, rb,
+          [&](int, int m, int n0, float (&v)[TNW]) {
+            const float gm = gate[m], bias = rbias[m];
+            float c[TNW];
+            lds_vec<TNW>(A + m * TV + n0, c);
+#pragma unroll
+            for (int j = 0; j < TNW; ++j) v[j] = fmaf(c[j], gm, v[j] + bias);
+            if (contiguous) { store_vec<TNW>(dst + m * TV + n0, v); }
+            else {
+              int t = n0 / V, vv = n0 - t * V;
+#pragma unroll
+              for (int j = 0; j < TNW; ++j) {
+                dst[m * sc + t * st + vv * sv] = v[j];
+                if (++vv == V) { vv = 0; ++t; }
+              }
+            }
+          });
       } else if (contiguous) {
         float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll 2
         for (int i = tid; i < Co * TV / 4; i += NT) {
           const float gm = gate[(i * 4) / TV];
           const float4 c4 = reinterpret_cast<const float4*>(A)[i];

@@ -6,7 +6,7 @@
 
 namespace cg {
 
-constexpr int DSTD_NT = 512;
+constexpr int DSTD_NT = 256;
 
 int launch_dstd_10_22(const DstdArgs& a, void* stream);
 int launch_dstd_10_18(const DstdArgs& a, void* stream);

@@ -60,7 +60,8 @@ CG_DEV void fpn_branch(const float* __restrict__ Wd, const float* __restrict__ b
   const int notile = To / 5;
   const int items = notile * F * NWT;
   for (int item = threadIdx.x; item < items; item += NT) {
-    const int wt = item % NWT, h = (item / NWT) % F, ot = item / (NWT * F);
+    // channel tile fastest: neighbouring lanes read the same input window (broadcast), fewer LSU wavefronts
+    const int ot = item % notile, wt = (item / notile) % NWT, h = item / (notile * NWT);
     const int w0 = wt * TN;
     float acc[5][TN];
 #pragma unroll
@@ -185,8 +186,8 @@ __global__ void __launch_bounds__(FPN_NT, 2) fpn_chain_kernel(const FpnArgs a) {
         }
         // compress 1x1 (:77-78), accumulated branch by branch; the last slice applies the caller's
         // PReLU (+ residual) and writes the map back in place
-        const WideOp ops[2] = {{nullptr, wslice, Bb, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
-        gemm_wide<4, 4, NT>(ops, 1, false, Top, To, To, 0, FVC, FVC, nullptr, 0,
+        const WideOp ops[1] = {{nullptr, wslice, Bb, nullptr}};
+        gemm_wide<4, 4, FVC, FVC, NT, false, 1>(ops, Top, To, To, 0, nullptr, 0,
           [&](int, int m, int n0, float (&v)[4]) {
             float* op = OUT + m * FV + n0;
             if (dil == 1) { store_vec<4>(op, v); return; }
