@@ -234,32 +234,43 @@ def run_native(args, rank, world, local_rank):
         return
 
     hbm_peak, peak_src = measured_peaks()
-    launches = sum(int(v) for v in kln)
+    launches = sum(int(v) for v in kln)                     # launches of OUR kernels inside the timed region
     names = ["dstd_block_kernel", "fpn_chain_kernel", "tail_kernel", "mpjpe_kernel"]
     kshare = {names[i]: {"ms_per_step": kms[i] / args.steps, "launches_per_step": int(kln[i]) / args.steps}
               for i in range(4) if kln[i]}
     dom = max(range(4), key=lambda i: kms[i])
     total_kms = sum(kms)
-    # dominant kernel, per launch: algorithmic bytes its launch moves / CUDA-event duration
     n_launch_dom = max(int(kln[dom]), 1)
-    seq_per_launch = B * args.steps * (5 if dom == 0 else 1) / n_launch_dom     # dstd: 5 of its 6 launches carry E-wide tiles
-    if dom == 1:      # FPN chain: reads (10,10,V), writes (25,V,3)
-        bytes_launch = 4 * V * (100 + 75) * (B * args.steps / n_launch_dom)
-        flops_launch = FPN_FLOPS_PER_SEQ[V] * (B * args.steps / n_launch_dom)
-    else:             # report the whole-forward figure against the summed kernel time instead
-        bytes_launch = bytes_per_seq(V, E) * B * args.steps / n_launch_dom
-        flops_launch = FLOPS_PER_SEQ.get((V, E), 0.0) * B * args.steps / n_launch_dom
-    dur_s = kms[dom] / 1e3 / n_launch_dom
+    seqs = B * args.steps                                   # sequences pushed through every kernel kind
+    # Algorithmic (compulsory) HBM bytes and FLOPs per sequence of each kernel kind -- DESIGN.md section 5:
+    # every kernel reads its input activation once and writes its output once; weights are amortised.
+    TV = 10 * V
+    dstd_bytes = 4 * ((3 * TV + E * TV) + 3 * 2 * E * TV + (E * TV + 10 * TV) + 2 * 75 * V)   # 5 input blocks + output block
+    kind_bytes = [dstd_bytes, 4 * (10 * TV + 75 * V), 4 * (30 * V + 3 * 75 * V), 4 * 2 * 75 * V]
+    fl_total = FLOPS_PER_SEQ.get((V, E), 0.0)
+    kind_flops = [fl_total - FPN_FLOPS_PER_SEQ[V] - 0.7e6 * V / 22, FPN_FLOPS_PER_SEQ[V], 0.7e6 * V / 22, 0.0]
+    dur_s = kms[dom] / 1e3 / n_launch_dom                   # average launch duration, CUDA events on the launch stream
+    bytes_launch = kind_bytes[dom] * seqs / n_launch_dom
+    flops_launch = kind_flops[dom] * seqs / n_launch_dom
     achieved = bytes_launch / dur_s / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.isfile(tpath):                               # ncu --set full capture of the same launch shape, bytes / sequence
+        tj = json.load(open(tpath)).get(f"E{E}_V{V}", {}).get(names[dom])
+        if tj is not None:
+            traffic = tj * seqs / n_launch_dom
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "share_of_step": kms[dom] / total_kms if total_kms else None,
-                "note": "fp32 path is bound by the FP32 FMA pipe, not HBM (SURVEY.md 0.3 / 8d); see roofline_fp32_fma"}
+                "bytes_per_launch": bytes_launch, "launch_ms": dur_s * 1e3,
+                "note": "the fp32 path is bound by the FP32 FMA pipe, not HBM (SURVEY.md 0.3 / 8d): see roofline_fp32_fma"}
     tf = flops_launch / dur_s / 1e12
     roofline_fma = {"bound": "fp32_fma", "kernel": names[dom], "achieved": tf, "peak": FP32_FMA_PEAK_TFLOPS,
                     "unit": "TFLOP/s", "frac": tf / FP32_FMA_PEAK_TFLOPS,
-                    "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz",
-                    "whole_forward": {"achieved": FLOPS_PER_SEQ.get((V, E), 0.0) * (value / world) / 1e12,
+                    "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz; measured ceiling of a pure FFMA loop on this "
+                                   "pool is 92/128 of it (profiles/microbench_r1.log)",
+                    "whole_forward": {"achieved": fl_total * (value / world) / 1e12,
+                                      "frac": fl_total * (value / world) / 1e12 / FP32_FMA_PEAK_TFLOPS,
                                       "hbm_frac_survey_bytes": bytes_per_seq(V, E) * (value / world) / 1e9 / hbm_peak}}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -16,7 +16,7 @@ import torch
 from .pack import DEFINES, ABI_VERSION
 
 _LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib")
-LIB_PATH = os.path.join(_LIB_DIR, "libcistgcn_b200.so")
+LIB_PATH = os.environ.get("CISTGCN_B200_LIB") or os.path.join(_LIB_DIR, "libcistgcn_b200.so")   # env: explicit path to another build of the same CUDA library
 MAXB = DEFINES["CISTGCN_MAX_BLOCKS"]
 
 _p = ctypes.c_void_p

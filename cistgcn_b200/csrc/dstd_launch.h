@@ -6,7 +6,10 @@
 
 namespace cg {
 
-constexpr int DSTD_NT = 256;
+#ifndef CISTGCN_DSTD_NT
+#define CISTGCN_DSTD_NT 512
+#endif
+constexpr int DSTD_NT = CISTGCN_DSTD_NT;
 
 int launch_dstd_10_22(const DstdArgs& a, void* stream);
 int launch_dstd_10_18(const DstdArgs& a, void* stream);
