@@ -283,7 +283,7 @@ def run_native(args, rank, world, local_rank):
                    "l2_policy": "inputs_larger_than_L2 (173 MB input + activations per step > 126 MB L2)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                 "ms_per_step": ms_e2e / args.steps, "api": "CISTGCN.forward on pinned host buffers", "checksum": checksum},
-        "gpu_launches": launches,
+        "gpu_launches": launches * world,     # every rank launches the same kernels on its own GPU
         "kernels": kshare,
         "roofline": roofline,
         "roofline_fp32_fma": roofline_fma,

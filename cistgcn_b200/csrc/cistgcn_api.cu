@@ -87,6 +87,7 @@ struct ProfScope { ProfScope(int, void*) {} };
 // ---------------------------------------------------------------------------------------------
 using cg::DSTD_NT;
 long long* g_phase_clocks = nullptr;   // debug hook, see cistgcn_debug_phase_clocks
+int g_stamp_iter = 0;
 
 int dstd_done(int e) {
   if (e) return fail(-4, "dstd_block_kernel launch: %s", cg::launch_error_string(e));
@@ -108,6 +109,7 @@ int launch_dstd(const int32_t* desc, const float* weights, const float* in, floa
   if (a.d[CB_IN_MODE] == 1 && Ci != 10) return fail(-2, "feature-building input mode needs Ci == 10");
   if (!a.d[CB_INTERP]) { a.tap_adj_s = nullptr; a.tap_adj_t = nullptr; }
   a.phase_clocks = g_phase_clocks;
+  a.stamp_iter = g_stamp_iter;
   if (!cg::dstd_plan(a, DSTD_NT, kMaxSmemBytes / 4) || (size_t)a.smem_floats * 4 > (size_t)kMaxSmemBytes)
     return fail(-2, "DSTD-GC block (%d->%d, T=%d, V=%d) needs %zu B of shared memory (> %d)", Ci, Co, T, V,
                 (size_t)a.smem_floats * 4, kMaxSmemBytes);
@@ -214,6 +216,11 @@ int cistgcn_abi_version(void) { return CISTGCN_ABI_VERSION; }
 
 int cistgcn_debug_phase_clocks(void* device_buffer) {
   g_phase_clocks = reinterpret_cast<long long*>(device_buffer);
+  return 0;
+}
+
+int cistgcn_debug_stamp_iteration(int iteration) {
+  g_stamp_iter = iteration < 0 ? 0 : iteration;
   return 0;
 }
 

@@ -27,7 +27,7 @@ namespace cg {
 #ifdef CISTGCN_EMU
 #define CG_STAMP(i)
 #else
-#define CG_STAMP(i) do { if (a.phase_clocks && blockIdx.x == 0 && threadIdx.x == 0 && b == (int)blockIdx.x) a.phase_clocks[i] = clock64(); } while (0)
+#define CG_STAMP(i) do { if (a.phase_clocks && blockIdx.x == 0 && threadIdx.x == 0 && b == (int)blockIdx.x + a.stamp_iter * (int)gridDim.x) a.phase_clocks[i] = clock64(); } while (0)
 #endif
 
 struct DstdArgs {
@@ -43,7 +43,9 @@ struct DstdArgs {
   float* tap_w2;
   int batch;
   int o_xn, o_ab, tile, o_adj, o_sm, o_ring, ring_floats, smem_floats;
+  int scratch_floats;    // capacity of the split-K partial scratch (the adjacency region)
   long long* phase_clocks;   // optional debug: first CTA / thread 0 stamps clock64() at phase boundaries
+  int stamp_iter;            // ... of its stamp_iter-th sample (0 = first: cold caches)
 };
 
 __host__ __device__ inline int pad4i(int n) { return (n + 3) & ~3; }
@@ -52,6 +54,7 @@ __host__ __device__ inline int imax(int a, int b) { return a > b ? a : b; }
 __host__ __device__ inline int imin(int a, int b) { return a < b ? a : b; }
 
 constexpr int RING_SLOTS = 4;   // cp.async streaming ring: slots in flight
+constexpr int KSPLIT_MAX = 8;   // split-K fan-out cap of the narrow GEMMs (also limited by the scratch capacity)
 
 // Host: sizes of every weight field, the shared-memory layout and the residency plan.
 // Returns false if even the mandatory small vectors do not fit.
@@ -90,8 +93,12 @@ inline bool dstd_plan(DstdArgs& a, int nt, int max_smem_floats) {
   a.o_ab = pad4i(Ci * TV);
   a.o_adj = a.o_ab + a.tile + imax(a.tile, pad4i(big));
   const int nw = nt / 32;
-  const int adj = imax(imax(pad4i(big), pad4i(T * T * (V | 1))), imax(pad4i(2 * Ci * T + 2 * Ci), nw * 8 * 32 * 2));   // also hosts split-K partials
+  // split-K partial sums of the narrow GEMMs (<= KSPLIT_MAX copies of an M x N output) and of the matvecs
+  // (nw/2 copies of 2 x Co) share the adjacency region with the row statistics
+  const int scratch = imax(4 * imax(2 * Cg * V, imax(Ch * V, Ch * T)), nw * Co);
+  const int adj = imax(imax(pad4i(big), pad4i(T * T * (V | 1))), imax(pad4i(2 * Ci * T + 2 * Ci), pad4i(scratch)));
   a.o_sm = a.o_adj + adj;
+  a.scratch_floats = adj;
   const int sm = pad4i(2 + 2 * T) + imax(pad4i(2 * Cg * V), pad4i(2 * Ch * V) + pad4i(2 * Ch * T)) + 3 * pad4i(2 * Co) +
                  2 * pad4i(2 * TV) + 2 * pad4i(Co) + pad4i(Hs);
   a.o_ring = a.o_sm + sm;
@@ -276,7 +283,7 @@ CG_DEV void store_vec(float* p, const float (&v)[TN]) {
 // ---------------------------------------------------------------------------------------------
 template <int TM, int N, bool STRIDED, int NT, class EPI>
 CG_DEV void gemm_narrow(const float* __restrict__ wg_, const float* ws, int Mp, int M, int K,
-                        const float* X, int R, int CS, float* partial, float* ring, int rb, EPI epi) {
+                        const float* X, int R, int CS, float* partial, int partial_cap, float* ring, int rb, EPI epi) {
   // X(k, n): contiguous mode  X[k*N + n]  (the (T,1) conv over a [c][t][v] tile, N = V);
   //          strided mode     X[(k / R)*CS + (k % R) + n*R]  (the (1,V) conv over the same layout: k = (c, v), n = t, R = V)
   static_assert(N <= 32, "gemm_narrow: row length must fit a warp");
@@ -288,7 +295,7 @@ CG_DEV void gemm_narrow(const float* __restrict__ wg_, const float* ws, int Mp, 
   const int msub = lane / NP, np = lane - msub * NP;
   const int mtiles = (M + TM - 1) / TM;
   const int mgroups = (mtiles + MS - 1) / MS;
-  const int ksplit = imax(1, NW / mgroups);
+  const int ksplit = imax(1, imin(imin(KSPLIT_MAX, NW / mgroups), partial_cap / (M * N)));
   for (int gbase = 0; gbase < mgroups; gbase += NW) {          // (one pass unless mgroups > NW)
     const int mg = gbase + warp % imin(mgroups, NW);
     const int ks = warp / imin(mgroups, NW);
@@ -367,10 +374,10 @@ CG_DEV void gemm_narrow(const float* __restrict__ wg_, const float* ws, int Mp, 
 
 template <int N, bool STRIDED, int NT, class EPI>
 CG_DEV void gemm_narrow_auto(const float* __restrict__ wg_, const float* ws, int Mp, int M, int K,
-                             const float* X, int R, int CS, float* partial, float* ring, int rb, EPI epi) {
-  if (M >= 16) gemm_narrow<8, N, STRIDED, NT>(wg_, ws, Mp, M, K, X, R, CS, partial, ring, rb, epi);
-  else if (M >= 8) gemm_narrow<4, N, STRIDED, NT>(wg_, ws, Mp, M, K, X, R, CS, partial, ring, rb, epi);
-  else gemm_narrow<2, N, STRIDED, NT>(wg_, ws, Mp, M, K, X, R, CS, partial, ring, rb, epi);
+                             const float* X, int R, int CS, float* partial, int partial_cap, float* ring, int rb, EPI epi) {
+  if (M >= 16) gemm_narrow<8, N, STRIDED, NT>(wg_, ws, Mp, M, K, X, R, CS, partial, partial_cap, ring, rb, epi);
+  else if (M >= 8) gemm_narrow<4, N, STRIDED, NT>(wg_, ws, Mp, M, K, X, R, CS, partial, partial_cap, ring, rb, epi);
+  else gemm_narrow<2, N, STRIDED, NT>(wg_, ws, Mp, M, K, X, R, CS, partial, partial_cap, ring, rb, epi);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -395,10 +402,22 @@ CG_DEV void gate_matvec(const float* wmat, int Mp, int M, int K1, const float* x
     const int mc = m < M ? m : M - 1;
     float acc = 0.f;
     const int e1 = imin(r1, K1);
-#pragma unroll 16
-    for (int k = r0; k < e1; ++k) acc = fmaf(wgt[(size_t)k * Mp + mc], xa[k], acc);
-#pragma unroll 16
-    for (int k = imax(r0, K1); k < r1; ++k) acc = fmaf(wgt[(size_t)k * Mp + mc], x2[k - K1], acc);
+    // fixed-trip batches of 16 independent loads (rows past the end are clamped and multiplied by 0): a
+    // rolled remainder loop would pay one L2 round trip per leftover row
+    for (int k0 = r0; k0 < e1; k0 += 16) {
+      float w[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) w[j] = wgt[(size_t)imin(k0 + j, e1 - 1) * Mp + mc];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc = fmaf(w[j], (k0 + j < e1) ? xa[k0 + j] : 0.f, acc);
+    }
+    for (int k0 = imax(r0, K1); k0 < r1; k0 += 8) {
+      float w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = wgt[(size_t)imin(k0 + j, r1 - 1) * Mp + mc];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(w[j], (k0 + j < r1) ? x2[k0 + j - K1] : 0.f, acc);
+    }
     if (m < M) partial[(ks * 2 + g) * M + m] = acc;
   }
   __syncthreads();
@@ -661,7 +680,7 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
     {
       const float* gb = P(CB_G0_B);
       const float* ga = P(CB_G0_A);
-      gemm_narrow_auto<V, false, NT>(G(CB_G0_WT), RS(CB_G0_WT), pad8i(2 * Cg), 2 * Cg, Ci * T, XN, T, TV, partial, ring, rb,
+      gemm_narrow_auto<V, false, NT>(G(CB_G0_WT), RS(CB_G0_WT), pad8i(2 * Cg), 2 * Cg, Ci * T, XN, T, TV, partial, a.scratch_floats, ring, rb,
                               [&](int m, int v, float acc) { h1[m * V + v] = prelu(acc + gb[m], ga[m / Cg]); });
     }
     CG_STAMP(3);
@@ -710,9 +729,9 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
         const float* jb = P(CB_JC3_B_S + L);
         float* dq = dseqp + L * Ch * V;
         float* dp = dspp + L * Ch * T;
-        gemm_narrow_auto<V, false, NT>(G(CB_TC3_WT_S + L), RS(CB_TC3_WT_S + L), pad8i(Ch), Ch, Ch * T, tl, T, TV, partial, ring, rb,
+        gemm_narrow_auto<V, false, NT>(G(CB_TC3_WT_S + L), RS(CB_TC3_WT_S + L), pad8i(Ch), Ch, Ch * T, tl, T, TV, partial, a.scratch_floats, ring, rb,
                                 [&](int m, int v, float acc) { dq[m * V + v] = acc + tb[m]; });
-        gemm_narrow_auto<T, true, NT>(G(CB_JC3_WT_S + L), RS(CB_JC3_WT_S + L), pad8i(Ch), Ch, Ch * V, tl + Ch * TV, V, TV, partial, ring, rb,
+        gemm_narrow_auto<T, true, NT>(G(CB_JC3_WT_S + L), RS(CB_JC3_WT_S + L), pad8i(Ch), Ch, Ch * V, tl + Ch * TV, V, TV, partial, a.scratch_floats, ring, rb,
                                 [&](int m, int t, float acc) { dp[m * T + t] = acc + jb[m]; });
       }
       CG_STAMP(6);

@@ -7,10 +7,11 @@
 // zero row), is updated in place layer after layer and never returns to HBM until x7 is written.
 //
 // Hot loop (56 % of the model's FLOPs): the three dilation branches run one after another with ALL
-// warps on the same branch, so the inner body (one input channel x one kernel row: 120 FFMAs) is a
+// warps on the same branch, so the inner body (one input channel x one kernel row: 180 FFMAs) is a
 // few KB of code shared by every warp and stays in the instruction cache.  A thread owns 5 output
-// channels x 8 (or 6) joints of one row; per body it loads the input window once (4 x LDS.128) and 15
-// folded weights (4 x LDG.128, warp-uniform per channel tile, L1-resident) for 120 FFMAs.  Each
+// channels x 12 (or 10) joints of one row; per body it loads the input window once (5 x LDS.128) and 15
+// folded weights (4 x LDG.128, warp-uniform per channel tile, L1-resident) for 180 FFMAs.  100 work items
+// per branch = 4 warps x 25 lanes: one warp per scheduler, equal work.  Each
 // branch's slice of the 1x1 `compress` convolution is accumulated right after the branch, so only one
 // branch output (25 x F x V) is ever staged.
 #pragma once
@@ -22,7 +23,7 @@ namespace cg {
 
 constexpr int FPN_XS = 36;        // padded row stride of the resident map (floats)
 constexpr int FPN_LPAD = 4;       // data starts at column 4 (keeps rows float4-aligned)
-constexpr int FPN_NT = 192;
+constexpr int FPN_NT = 128;       // 4 warps, one per scheduler; 2 CTAs per SM
 constexpr int FPN_MAX_LAYERS = CISTGCN_MAX_FPN;
 
 struct FpnArgs {
@@ -59,7 +60,12 @@ CG_DEV void fpn_branch(const float* __restrict__ Wd, const float* __restrict__ b
   static_assert((NWT - 1) * TN + WIN <= FPN_XS, "row padding too small for this joint count");
   const int notile = To / 5;
   const int items = notile * F * NWT;
-  for (int item = threadIdx.x; item < items; item += NT) {
+  // every warp gets the same number of items (100 items -> 4 x 25): equal work per scheduler
+  const int ipw = (items + NT / 32 - 1) / (NT / 32);
+  const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31;
+  for (int it0 = ln; it0 < ipw; it0 += 32) {
+    const int item = wid * ipw + it0;
+    if (item >= items) break;
     // channel tile fastest: neighbouring lanes read the same input window (broadcast), fewer LSU wavefronts
     const int ot = item % notile, wt = (item / notile) % NWT, h = item / (notile * NWT);
     const int w0 = wt * TN;
@@ -119,7 +125,7 @@ template <int V>
 __global__ void __launch_bounds__(FPN_NT, 2) fpn_chain_kernel(const FpnArgs a) {
   CG_DYN_SMEM(smem);
   constexpr int NT = FPN_NT;
-  constexpr int TN = (V % 8 == 0 || V % 8 >= 5) ? 8 : 6;       // 22 -> 8 (3 tiles), 18 -> 6 (3 tiles)
+  constexpr int TN = (V == 22) ? 12 : (V == 18 ? 10 : 8);       // 22 -> 12 + 10, 18 -> 10 + 8: two column tiles per row
   constexpr int FVC = 10 * V;                                    // F is fixed at 10 (in_ch, CISTGCN.py:512)
   const int tid = threadIdx.x, warp = tid >> 5;
   const float* __restrict__ W = a.w;

@@ -195,6 +195,8 @@ int cistgcn_profile_enable(int on);
 /* Debug: while non-NULL, thread 0 of the first CTA of every DSTD-GC launch stamps clock64() at its
  * phase boundaries into device_buffer (>= 16 x int64).  Pass NULL to switch off. */
 int cistgcn_debug_phase_clocks(void* device_buffer);
+/* Debug: stamp the CTA's `iteration`-th sample instead of its first (0 = cold caches, >= 1 = steady state). */
+int cistgcn_debug_stamp_iteration(int iteration);
 int cistgcn_profile_read(double* ms_by_kind, int64_t* launches_by_kind);
 
 #ifdef __cplusplus

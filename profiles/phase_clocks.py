@@ -12,6 +12,7 @@ from cistgcn_b200.pack import F  # noqa: E402
 E = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 V = int(sys.argv[2]) if len(sys.argv) > 2 else 22
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 148 * 4
+ITER = int(sys.argv[4]) if len(sys.argv) > 4 else 0       # which sample of CTA 0 to stamp (0 = cold, >=1 = warm)
 NAMES = ["load+norm", "stats", "gate conv(T,1)", "gate matvecs", "map2adj 1x1", "collapse convs", "dimseq/dsp+outer_s",
          "expansor_s", "gcn_space", "outer_t+expansor_t", "gcn_time", "tcn x2", "compressor", "SE", "store"]
 lib = _cabi.lib()
@@ -19,6 +20,7 @@ model = _make_model(E, V).cuda()
 pk = model.pack("cuda")
 clk = torch.zeros(16, dtype=torch.int64, device="cuda")
 lib.cistgcn_debug_phase_clocks(clk.data_ptr())
+lib.cistgcn_debug_stamp_iteration(ITER)
 for which, i in (("in", 0), ("in", 1), ("in", 4), ("out", 0)):
     d = pk.block_desc(which, i)
     ci, co, T, Vb = d[F["CB_CI"]], d[F["CB_CO"]], d[F["CB_T"]], d[F["CB_V"]]
