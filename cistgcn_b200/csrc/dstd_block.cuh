@@ -102,26 +102,38 @@ inline bool dstd_plan(DstdArgs& a, int nt, int max_smem_floats) {
   const int sm = pad4i(2 + 2 * T) + imax(pad4i(2 * Cg * V), pad4i(2 * Ch * V) + pad4i(2 * Ch * T)) + 3 * pad4i(2 * Co) +
                  2 * pad4i(2 * TV) + 2 * pad4i(Co) + pad4i(Hs);
   a.o_ring = a.o_sm + sm;
-  const int budget = max_smem_floats - a.o_ring;
   const int widest = imax(pad8i(4 * Ch), imax(Cop, pad8i(2 * Cg)));      // longest streamed row
-  a.ring_floats = imax(widest, budget >= 24576 ? 2048 : (budget >= 8192 ? 1024 : 512));  // per slot
-  int cur = a.o_ring + RING_SLOTS * a.ring_floats;
-  // residency: mandatory small operands first, then by benefit per byte
-  bool ok = true;
-  auto take = [&](int f, bool mandatory) {
-    if (a.wsz[f] == 0 || a.res[f] >= 0) return;
-    if (cur + a.wsz[f] <= max_smem_floats) { a.res[f] = cur; cur += a.wsz[f]; }
-    else if (mandatory) ok = false;
-  };
   const int vectors[] = {CB_GN_S, CB_GN_B, CB_G0_B, CB_G0_A, CB_G4_B, CB_G4_A, CB_M0_B, CB_M0_A, CB_A0_B, CB_A0_A,
                          CB_TC3_B_S, CB_TC3_B_T, CB_JC3_B_S, CB_JC3_B_T, CB_E0_B_S, CB_E0_B_T, CB_E0_A_S, CB_E0_A_T,
                          CB_TCN_B_S, CB_TCN_B_T, CB_TCN_A_S, CB_TCN_A_T, CB_P_S_S, CB_P_S_T, CB_P_B_S, CB_P_B_T,
                          CB_P_A_S, CB_P_A_T, CB_CP_B, CB_CP_A, CB_RS_B};
-  for (int f : vectors) take(f, true);
-  const int order[] = {CB_SE1_WT, CB_SE2_WT, CB_A0_WT, CB_TCN_WT_S, CB_TCN_WT_T, CB_CP_WT, CB_RS_WT, CB_E0_WT_S, CB_E0_WT_T,
-                       CB_E4_WT_S, CB_E4_WT_T, CB_TC6_WT_S, CB_TC6_WT_T, CB_JC6_WT_S, CB_JC6_WT_T, CB_G0_WT, CB_M0_WT, CB_M4_WT,
-                       CB_TC3_WT_S, CB_TC3_WT_T, CB_JC3_WT_S, CB_JC3_WT_T, CB_G4_WT};
-  for (int f : order) take(f, false);
+  // operands of GEMM-style loops (must sit in shared memory: resident, else streamed through the ring), by benefit
+  const int gemm_ops[] = {CB_SE1_WT, CB_SE2_WT, CB_A0_WT, CB_TCN_WT_S, CB_TCN_WT_T, CB_CP_WT, CB_RS_WT, CB_E0_WT_S, CB_E0_WT_T,
+                          CB_E4_WT_S, CB_E4_WT_T, CB_TC6_WT_S, CB_TC6_WT_T, CB_JC6_WT_S, CB_JC6_WT_T,
+                          CB_TC3_WT_S, CB_TC3_WT_T, CB_JC3_WT_S, CB_JC3_WT_T};
+  // operands read straight from L2 with deep load batches when not resident (gate conv, gate MLPs)
+  const int l2_ops[] = {CB_M4_WT, CB_M0_WT, CB_G0_WT, CB_G4_WT};
+  bool ok = true;
+  int cur = 0;
+  for (int with_ring = 0; with_ring < 2; ++with_ring) {          // first try: everything GEMM-side resident, no ring
+    for (int f = 0; f < CB_COUNT; ++f) a.res[f] = -1;
+    ok = true;
+    const int budget = max_smem_floats - a.o_ring;
+    a.ring_floats = with_ring ? imax(widest, budget >= 24576 ? 2048 : (budget >= 8192 ? 1024 : 512)) : 0;
+    cur = a.o_ring + RING_SLOTS * a.ring_floats;
+    auto take = [&](int f, bool mandatory) {
+      if (a.wsz[f] == 0 || a.res[f] >= 0) return true;
+      if (cur + a.wsz[f] <= max_smem_floats) { a.res[f] = cur; cur += a.wsz[f]; return true; }
+      if (mandatory) ok = false;
+      return false;
+    };
+    for (int f : vectors) take(f, true);
+    bool all_gemm = true;
+    for (int f : gemm_ops) all_gemm = take(f, false) && all_gemm;
+    if (!with_ring && !all_gemm) continue;                       // something must stream: plan again with a ring
+    for (int f : l2_ops) take(f, false);
+    break;
+  }
   a.smem_floats = cur;
   return ok && cur <= max_smem_floats;
 }
@@ -149,24 +161,24 @@ CG_DEV void cp_async_wait_pending(int n) {      // wait until at most n of this 
 #endif
 }
 
-template <int NT, class BODY>
+template <int NT, int SLOTS = RING_SLOTS, class BODY>
 CG_DEV void for_weight_chunks(const float* __restrict__ g, const float* s, int K, int Mp, float* ring, int rb, BODY body) {
   if (s != nullptr) { body(s, 0, K); return; }
-  // ring = RING_SLOTS slots of rb floats; up to RING_SLOTS-1 chunks are in flight ahead of the consumer
+  // ring = SLOTS slots of rb floats; up to SLOTS-1 chunks are in flight ahead of the consumer
   const int kc = rb / Mp;
   const int nch = (K + kc - 1) / kc;
   int issued = 0;
   auto issue = [&]() {
-    copy_async<NT>(ring + (issued % RING_SLOTS) * rb, g + (size_t)issued * kc * Mp, imin(kc, K - issued * kc) * Mp);
+    copy_async<NT>(ring + (issued % SLOTS) * rb, g + (size_t)issued * kc * Mp, imin(kc, K - issued * kc) * Mp);
     cp_async_commit();
     ++issued;
   };
-  for (int i = 0; i < imin(nch, RING_SLOTS - 1); ++i) issue();
+  for (int i = 0; i < imin(nch, SLOTS - 1); ++i) issue();
   for (int c = 0; c < nch; ++c) {
     cp_async_wait_pending(issued - c - 1);
     __syncthreads();                 // chunk c visible to all; everyone is done with chunk c-1, whose slot is reused now
     if (issued < nch) issue();
-    body(ring + (c % RING_SLOTS) * rb, c * kc, imin(kc, K - c * kc));
+    body(ring + (c % SLOTS) * rb, c * kc, imin(kc, K - c * kc));
   }
   __syncthreads();
 }
@@ -188,7 +200,7 @@ struct WideOp {
   const float* X2;   // next K2 rows (or nullptr)
 };
 
-template <int TM, int TN, int LD, int N, int NT, bool INPLACE, int NP, class EPI>
+template <int TM, int TN, int LD, int N, int NT, bool INPLACE, int NP, int SLOTS = RING_SLOTS, class EPI>
 CG_DEV void gemm_wide(const WideOp (&ops)[NP], int Mp, int M, int K1, int K2, float* ring, int rb, EPI epi) {
   static_assert(N % TN == 0 && LD % TN == 0, "gemm_wide: columns must tile by TN");
   constexpr int NW = NT / 32;
@@ -236,7 +248,7 @@ CG_DEV void gemm_wide(const WideOp (&ops)[NP], int Mp, int M, int K1, int K2, fl
       kb = imax(k0, K1); ke = k0 + kc;
       if (kb < ke) run(op.X2 + (kb - K1) * LD + n0, wc + (kb - k0) * Mp + m0, ke - kb);
     };
-    if constexpr (NP == 1) for_weight_chunks<NT>(ops[0].wg, ops[0].ws, K1 + K2, Mp, ring, rb, body);
+    if constexpr (NP == 1) for_weight_chunks<NT, SLOTS>(ops[0].wg, ops[0].ws, K1 + K2, Mp, ring, rb, body);
     else body(op.ws, 0, K1 + K2);                    // multi-problem phases need resident weights
     if (INPLACE) __syncthreads();
     if (active) {
@@ -378,6 +390,55 @@ CG_DEV void gemm_narrow_auto(const float* __restrict__ wg_, const float* ws, int
   if (M >= 16) gemm_narrow<8, N, STRIDED, NT>(wg_, ws, Mp, M, K, X, R, CS, partial, partial_cap, ring, rb, epi);
   else if (M >= 8) gemm_narrow<4, N, STRIDED, NT>(wg_, ws, Mp, M, K, X, R, CS, partial, partial_cap, ring, rb, epi);
   else gemm_narrow<2, N, STRIDED, NT>(wg_, ws, Mp, M, K, X, R, CS, partial, partial_cap, ring, rb, epi);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gate conv (T,1) with its weights read straight from L2 (used when the matrix is not resident):
+//   out(m, v) = sum_k W[k][m] * X[k*V + v].
+// Lanes own output rows (one coalesced 128-byte weight row per k), warps split K, every lane keeps V
+// accumulators; weight loads go out in fixed-trip batches of 8 independent requests (no rolled remainder),
+// activations are warp-uniform shared-memory broadcasts.  partial: >= ksplit*M*V floats.  Ends with a barrier.
+// ---------------------------------------------------------------------------------------------
+template <int V, int NT, class EPI>
+CG_DEV void gate_conv_l2(const float* __restrict__ Wg, int Mp, int M, int K, const float* X,
+                         float* partial, int partial_cap, EPI epi) {
+  constexpr int NW = NT / 32, BATCH = 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ksplit = imax(1, imin(NW, partial_cap / (M * V)));
+  const int r0 = (K * warp) / ksplit, r1 = warp < ksplit ? (K * (warp + 1)) / ksplit : r0;
+  for (int mb = 0; mb < M; mb += 32) {
+    const int m = mb + lane;
+    const int mc = m < M ? m : M - 1;
+    float acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = 0.f;
+    for (int k0 = r0; k0 < r1; k0 += BATCH) {
+      float w[BATCH];
+#pragma unroll
+      for (int j = 0; j < BATCH; ++j) w[j] = __ldg(Wg + (size_t)imin(k0 + j, r1 - 1) * Mp + mc);
+#pragma unroll
+      for (int j = 0; j < BATCH; ++j) {
+        if (k0 + j < r1) {
+          const float* xr = X + (k0 + j) * V;
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[v] = fmaf(w[j], xr[v], acc[v]);
+        }
+      }
+    }
+    if (m < M && warp < ksplit) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) partial[(warp * M + m) * V + v] = acc[v];
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < M * V; idx += NT) {
+    float s0 = 0.f, s1 = 0.f;
+    int q = 0;
+    for (; q + 2 <= ksplit; q += 2) { s0 += partial[q * M * V + idx]; s1 += partial[(q + 1) * M * V + idx]; }
+    if (q < ksplit) s0 += partial[q * M * V + idx];
+    epi(idx / V, idx % V, s0 + s1);
+  }
+  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -680,8 +741,11 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
     {
       const float* gb = P(CB_G0_B);
       const float* ga = P(CB_G0_A);
-      gemm_narrow_auto<V, false, NT>(G(CB_G0_WT), RS(CB_G0_WT), pad8i(2 * Cg), 2 * Cg, Ci * T, XN, T, TV, partial, a.scratch_floats, ring, rb,
-                              [&](int m, int v, float acc) { h1[m * V + v] = prelu(acc + gb[m], ga[m / Cg]); });
+      auto epi = [&](int m, int v, float acc) { h1[m * V + v] = prelu(acc + gb[m], ga[m / Cg]); };
+      if (RS(CB_G0_WT))
+        gemm_narrow_auto<V, false, NT>(G(CB_G0_WT), RS(CB_G0_WT), pad8i(2 * Cg), 2 * Cg, Ci * T, XN, T, TV, partial, a.scratch_floats, ring, rb, epi);
+      else          // not resident: deep-batched L2 reads; the (still unused) work tiles host the split-K partials
+        gate_conv_l2<V, NT>(G(CB_G0_WT), pad8i(2 * Cg), 2 * Cg, Ci * T, XN, A, a.o_adj - a.o_ab, epi);
     }
     CG_STAMP(3);
     // ---------------- P4: gate conv (1,V) -> h2 ; MLP -> w1, w2  (:327-352, 378-384)
