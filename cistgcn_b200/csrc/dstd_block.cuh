@@ -861,7 +861,8 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
     }
     CG_STAMP(8);
     // ---------------- P10: g1 = XN x_t Adj_s -> A
-    if (Ci >= 4) gcn_space<T, V, 4, NT>(XN, ADJ, A, Ci);
+    if (Ci >= 4 && ((Ci + 3) / 4) * V >= NT) gcn_space<T, V, 4, NT>(XN, ADJ, A, Ci);     // enough items for every thread
+    else if (Ci >= 2) gcn_space<T, V, 2, NT>(XN, ADJ, A, Ci);
     else gcn_space<T, V, 1, NT>(XN, ADJ, A, Ci);
     __syncthreads();
     CG_STAMP(9);
@@ -904,16 +905,21 @@ __global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
     __syncthreads();
     CG_STAMP(10);
     // ---------------- P12: g2 = XN x_v Adj_t -> B
-    if (Ci >= 4) gcn_time<T, V, 4, NT>(XN, ADJ, Bt, Ci);
+    if (Ci >= 4 && ((Ci + 3) / 4) * T * 2 >= NT) gcn_time<T, V, 4, NT>(XN, ADJ, Bt, Ci);
+    else if (Ci >= 2) gcn_time<T, V, 2, NT>(XN, ADJ, Bt, Ci);
     else gcn_time<T, V, 1, NT>(XN, ADJ, Bt, Ci);
     __syncthreads();
     CG_STAMP(11);
     // ---------------- P13: x_k = PReLU(BN(W g_k + b) + res); u_k = PReLU(BN(w_k * x_k))   (:266-268, 388)
     {
+      const float* tb0 = P(CB_TCN_B_S); const float* tb1 = P(CB_TCN_B_T);
+      const float* ps0 = P(CB_P_S_S);   const float* ps1 = P(CB_P_S_T);
+      const float* pb0 = P(CB_P_B_S);   const float* pb1 = P(CB_P_B_T);
+      const float ta0 = P(CB_TCN_A_S)[0], ta1 = P(CB_TCN_A_T)[0], pa0 = P(CB_P_A_S)[0], pa1 = P(CB_P_A_T)[0];
       auto tcn_epi = [&](int L, int m, int n0, float (&v)[TNW]) {
         float* Gt = L == 0 ? A : Bt;
-        const float tbm = P(CB_TCN_B_S + L)[m], ta = P(CB_TCN_A_S + L)[0];
-        const float sc = P(CB_P_S_S + L)[m] * wg[L * Co + m], pbm = P(CB_P_B_S + L)[m], pa = P(CB_P_A_S + L)[0];
+        const float tbm = (L ? tb1 : tb0)[m], ta = L ? ta1 : ta0;
+        const float sc = (L ? ps1 : ps0)[m] * wg[L * Co + m], pbm = (L ? pb1 : pb0)[m], pa = L ? pa1 : pa0;
         float r[TNW];
         if (!has_res) lds_vec<TNW>(XN + m * TV + n0, r);
 #pragma unroll
