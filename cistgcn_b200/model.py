@@ -264,6 +264,9 @@ class CISTGCN(nn.Module):
 
         self._packed: Optional[PackedModel] = None
         self._packed_key = None
+        self._tensor_cache = None
+        # load_state_dict(assign=True) swaps Parameter objects: drop the cached tensor list afterwards
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate_pack())
         self._workspace: Optional[torch.Tensor] = None
         self._taps_enabled = False
         self.last_taps: Dict[str, torch.Tensor] = {}
@@ -276,8 +279,23 @@ class CISTGCN(nn.Module):
                              n_fpn=self.n_txcnn_layers, hidden_dim=self.hidden_dim,
                              reduction=self.reduction, feat_ch=self.in_ch)
 
+    def _state_tensors(self):
+        # state_dict() rebuilds 1 178 prefixed keys per call (~1 ms); the tensor objects themselves only change
+        # when the module is moved (_apply replaces buffers), so cache the list and watch the version counters.
+        if self._tensor_cache is None:
+            self._tensor_cache = list(self.state_dict(keep_vars=True).values())
+        return self._tensor_cache
+
+    def _invalidate_pack(self):
+        self._tensor_cache = None
+        self._packed = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self._invalidate_pack()
+        return super()._apply(fn, *args, **kwargs)
+
     def _state_key(self, device):
-        return (str(device),) + tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+        return (str(device),) + tuple(t._version for t in self._state_tensors())
 
     def pack(self, device=None) -> PackedModel:
         """Fold eval-mode BatchNorm + biases and lay the weights out in one device blob
