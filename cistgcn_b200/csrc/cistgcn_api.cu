@@ -168,8 +168,10 @@ int launch_tail(const int32_t* tail_desc, const float* weights, const float* x, 
   cg::tail_plan(a);
   const size_t smem = (size_t)a.smem_floats * sizeof(float);
   auto kfn = cg::tail_kernel;
-  if (int rc = prepare(kfn, smem)) return rc;
-  const int grid = grid_for(batch, blocks_per_sm(kfn, cg::TAIL_NT, smem));
+  int perr = 0;
+  const int per_sm = cg::prepared_blocks_per_sm(kfn, cg::TAIL_NT, smem, &perr);
+  if (perr) return fail(-3, "cudaFuncSetAttribute(%zu B): %s", smem, cg::launch_error_string(perr));
+  const int grid = grid_for(batch, per_sm);
   ProfScope prof(KIND_TAIL, stream);
   CG_LAUNCH(kfn, grid, cg::TAIL_NT, smem, stream, a);
   return check_launch("tail_kernel");

@@ -20,8 +20,10 @@ template <int T, int V>
 inline int launch_dstd_impl(const DstdArgs& a, void* stream) {
   auto kfn = dstd_block_kernel<T, V, DSTD_NT>;
   const size_t smem = (size_t)a.smem_floats * sizeof(float);
-  if (int rc = prepare_kernel(kfn, smem)) return rc;
-  const int grid = grid_for(a.batch, blocks_per_sm(kfn, DSTD_NT, smem));
+  int err = 0;
+  const int per_sm = prepared_blocks_per_sm(kfn, DSTD_NT, smem, &err);
+  if (err) return err;
+  const int grid = grid_for(a.batch, per_sm);
   CG_LAUNCH(kfn, grid, DSTD_NT, smem, stream, a);
   return last_launch_error();
 }

@@ -12,8 +12,10 @@ template <int V>
 inline int launch_fpn_impl(const FpnArgs& a, void* stream) {
   auto kfn = fpn_chain_kernel<V>;
   const size_t smem = (size_t)a.smem_floats * sizeof(float);
-  if (int rc = prepare_kernel(kfn, smem)) return rc;
-  const int grid = grid_for(a.batch, blocks_per_sm(kfn, FPN_NT, smem));
+  int err = 0;
+  const int per_sm = prepared_blocks_per_sm(kfn, FPN_NT, smem, &err);
+  if (err) return err;
+  const int grid = grid_for(a.batch, per_sm);
   CG_LAUNCH(kfn, grid, FPN_NT, smem, stream, a);
   return last_launch_error();
 }
