@@ -36,13 +36,7 @@ constexpr int kMaxSmemBytes = 227 * 1024;
 
 using cg::sm_count;
 using cg::grid_for;
-using cg::blocks_per_sm;
 
-template <class K> int prepare(K kfn, size_t smem_bytes) {
-  if (int e = cg::prepare_kernel(kfn, smem_bytes))
-    return fail(-3, "cudaFuncSetAttribute(%zu B): %s", smem_bytes, cg::launch_error_string(e));
-  return 0;
-}
 int check_launch(const char* what) {
   if (int e = cg::last_launch_error()) return fail(-4, "%s launch: %s", what, cg::launch_error_string(e));
   return 0;

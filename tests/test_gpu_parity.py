@@ -156,3 +156,30 @@ def test_load_state_dict_repacks():
         ref = O.forward(sd2, cfg, x)
     assert not torch.allclose(a, b)
     assert (b.cpu() - ref).abs().max().item() <= G.tol(ref)
+
+
+def test_sharded_eval_single_rank_amass_shape():
+    """configs[2] shape (E=64, 18 joints) through the multi-GPU evaluation helper (world size 1 here): the
+    helper's global MPJPE figures equal losses.mpjpe on the whole batch."""
+    from cistgcn_b200.dist import sharded_eval_mpjpe
+    model, sd, cfg = M.build(64, 18, "W1")
+    x, tgt = O.synth_inputs(96, cfg)
+    model = model.to(DEV)
+    pred, (lo, hi), m_all, m_frames = sharded_eval_mpjpe(model.forward_mpjpe, x.to(DEV), tgt.to(DEV), rank=0, world=1)
+    assert (lo, hi) == (0, 96)
+    with torch.no_grad():
+        ref = O.forward(sd, cfg, x)
+    assert (pred.cpu() - ref).abs().max().item() <= G.tol(ref)
+    assert abs(m_all.item() - O.mpjpe(ref, tgt).item()) <= 1e-3 * _scale(ref)
+    assert torch.allclose(m_frames.float().cpu(), O.mpjpe(ref, tgt, (0, 2)), atol=1e-3 * _scale(ref))
+
+
+def test_choose_net_registry():
+    from cistgcn_b200 import choose_net
+    opt = M.make_opt(8, 22)
+    net = choose_net("CISTGCN_0", opt)
+    assert type(net).__name__ == "CISTGCN" and next(net.parameters()).is_cuda
+    out = net.eval()(torch.zeros(2, 10, 22, 3, device=DEV))
+    assert isinstance(out, tuple) and out[0].shape == (2, 25, 22, 3)
+    with pytest.raises(ValueError):
+        choose_net("resnet", opt)
