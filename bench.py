@@ -211,11 +211,33 @@ def run_native(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms / 1e3)
 
-    # ---- end-to-end arm: host buffers, H2D of the inputs and D2H of the predictions inside the timed region
+    # ---- end-to-end arm: host buffers; every step copies its inputs host->device and its predictions
+    # device->host inside the timed region.  The step is split into sub-batches so the copies (second stream)
+    # overlap the forward of the neighbouring sub-batch -- plain stream pipelining around the public forward().
+    n_sub = 4 if B % 4 == 0 and B >= 4096 else 1
+    sub = B // n_sub
+    copy_stream = torch.cuda.Stream(device=dev)
+    compute_stream = torch.cuda.current_stream(dev)
+    x_dev = [torch.empty(sub, 10, V, 3, device=dev) for _ in range(n_sub)]
+
     def e2e_step():
-        xd = x_pin.to(dev, non_blocking=True)
-        pr = model(xd)[0]
-        pred_pin.copy_(pr, non_blocking=True)
+        ev_in = [torch.cuda.Event() for _ in range(n_sub)]
+        ev_out = [torch.cuda.Event() for _ in range(n_sub)]
+        copy_stream.wait_stream(compute_stream)              # previous step's compute no longer reads x_dev
+        with torch.cuda.stream(copy_stream):
+            for i in range(n_sub):
+                x_dev[i].copy_(x_pin[i * sub:(i + 1) * sub], non_blocking=True)
+                ev_in[i].record(copy_stream)
+        for i in range(n_sub):
+            compute_stream.wait_event(ev_in[i])
+            pr = model(x_dev[i])[0]
+            ev_out[i].record(compute_stream)
+            pr.record_stream(copy_stream)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_out[i])
+                pred_pin[i * sub:(i + 1) * sub].copy_(pr, non_blocking=True)
+        compute_stream.wait_stream(copy_stream)              # the step ends when its last D2H has landed
+
     for _ in range(2):
         e2e_step()
     barrier()
@@ -282,7 +304,8 @@ def run_native(args, rank, world, local_rank):
                    "parallelism": f"batch-sharded x{world}, no data-path collective",
                    "l2_policy": "inputs_larger_than_L2 (173 MB input + activations per step > 126 MB L2)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
-                "ms_per_step": ms_e2e / args.steps, "api": "CISTGCN.forward on pinned host buffers", "checksum": checksum},
+                "ms_per_step": ms_e2e / args.steps, "api": f"CISTGCN.forward on pinned host buffers, {n_sub} sub-batches, copies overlapped on a second stream",
+                "checksum": checksum},
         "gpu_launches": launches * world,     # every rank launches the same kernels on its own GPU
         "kernels": kshare,
         "roofline": roofline,
