@@ -6,10 +6,11 @@
 // BatchNorm + PReLU + residual, gating, compressor, squeeze-excitation, block residual) reads and
 // writes shared memory only.  HBM sees the tile once in and once out.
 //
-// Weights: the CTA processes hundreds of samples with the same weights, so as many weight matrices
-// as fit are copied into shared memory ONCE per launch (host-side greedy plan, dstd_plan()); the
-// rest stream through a double-buffered cp.async ring (GEMM operands) or are read straight from L2
-// with wide split-K loads (single-use matvec operands).  No inner loop waits on an L2 round trip.
+// Weights: the CTA processes hundreds of samples with the same weights, so every operand of a
+// GEMM-style loop that fits is copied into shared memory ONCE per launch (host-side plan, dstd_plan());
+// what does not fit streams through a RING_SLOTS-deep cp.async ring; single-use operands (gate conv,
+// gate MLPs) are read straight from L2 in fixed-trip batches of 8-16 independent loads per lane.
+// No inner loop waits on one L2 round trip per iteration.
 //
 // Shared-memory map (floats):
 //   XN  [Ci][TV]          resident input tile (after global_norm)
@@ -17,7 +18,8 @@
 //                         expansor's hidden map
 //   ADJ [TV*max(T,V)]     row statistics / split-K partials, then o / Adj_s ([t][q][v]), then o / Adj_t
 //   SM                    small vectors (stats, gate activations, dseq/dsp, SE)
-//   RES                   resident weights;  RING  2 x ring_floats streaming slots
+//   RING                  RING_SLOTS x ring_floats streaming slots (absent when nothing streams)
+//   RES                   resident weights
 #pragma once
 #include "../../include/cistgcn_b200.h"
 #include "simt.h"
