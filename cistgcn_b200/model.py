@@ -372,7 +372,33 @@ class CISTGCN(nn.Module):
         _cabi.check(rc, "cistgcn_forward_f32")
         if self._taps_enabled:
             self.last_taps = holders
+            self._publish_taps(holders)
         return pred, sums
+
+    def _publish_taps(self, taps: Dict[str, torch.Tensor]):
+        """Expose the interpretability outputs as attributes on the same dotted paths the reference sets
+        in its forward (CISTGCN.py:262, 381-382, 469-473), so `getattr`-walking callers such as
+        environment/test.py:146-157 (predict.yaml:162-195) keep working."""
+        taps = dict(taps)
+        if "context_layer.joints" in taps and "context_layer.displacements" in taps:      # CISTGCN.py:471
+            taps["context_layer.seq_joints"] = taps["context_layer.displacements"].unsqueeze(2) * \
+                taps["context_layer.joints"].unsqueeze(1)
+        for key, value in taps.items():
+            node = self
+            parts = key.split(".")
+            try:
+                for k in parts[:-1]:
+                    node = getattr(node, k)
+            except AttributeError:
+                continue
+            object.__setattr__(node, parts[-1], value)
+            if parts[-1] == "Adj":                           # the reference also aliases it as gcn.A (CISTGCN.py:264)
+                gcn = node._modules.get("gcn")
+                if gcn is None:
+                    gcn = _Node()
+                    object.__setattr__(node, "gcn", gcn)     # plain attribute: keeps state_dict / module tree unchanged
+                if "A" not in gcn._parameters:
+                    object.__setattr__(gcn, "A", value)
 
 
 def choose_net(architecture: str, opt):

@@ -183,3 +183,27 @@ def test_choose_net_registry():
     assert isinstance(out, tuple) and out[0].shape == (2, 25, 22, 3)
     with pytest.raises(ValueError):
         choose_net("resnet", opt)
+
+
+def test_interpretation_attributes_like_reference():
+    """environment/test.py:146-157 walks dotted attribute paths on the live module after a forward."""
+    g = G.load("e8_v22_stress")
+    opt = M.make_opt(g["embed"], g["cfg"].joints, True)
+    model = CISTGCN(opt.architecture_config, opt.learning_config).eval()
+    model.load_state_dict(g["sd"])
+    keys_before = list(model.state_dict().keys())
+    model = model.to(DEV).enable_taps()
+    model(g["x"].to(DEV))
+    for key in ("context_layer.joints", "context_layer.displacements", "context_layer.seq_joints_n",
+                "context_layer.seq_joints_dims", "st_gcnns.1.dsgn.Adj", "st_gcnns.3.tsgn.Adj", "st_gcnns.2.w1",
+                "st_gcnns_o.0.dsgn.Adj", "st_gcnns_o.0.w2", "st_gcnns.0.dsgn.gcn.A", "context_layer.seq_joints"):
+        node = model
+        for k in key.split("."):
+            node = getattr(node, k)
+        ref = g["taps"].get(key)
+        if key.endswith("gcn.A"):
+            ref = g["taps"][key.replace("gcn.A", "Adj")]
+        if key == "context_layer.seq_joints":
+            ref = g["taps"]["context_layer.displacements"].unsqueeze(2) * g["taps"]["context_layer.joints"].unsqueeze(1)
+        assert (node.cpu().reshape(ref.shape) - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item()), key
+    assert list(model.state_dict().keys()) == keys_before          # publishing taps must not touch the state_dict
