@@ -79,7 +79,6 @@ struct ProfScope { ProfScope(int, void*) {} };
 #endif
 
 // ---------------------------------------------------------------------------------------------
-using cg::DSTD_NT;
 long long* g_phase_clocks = nullptr;   // debug hook, see cistgcn_debug_phase_clocks
 int g_stamp_iter = 0;
 
@@ -99,19 +98,28 @@ int launch_dstd(const int32_t* desc, const float* weights, const float* in, floa
   a.tap_w2 = taps ? taps->w2 : nullptr;
   const int T = a.d[CB_T], V = a.d[CB_V], Ci = a.d[CB_CI], Co = a.d[CB_CO];
   if (Ci < 2 || Co < 1) return fail(-2, "DSTD-GC block needs Ci >= 2 (got %d -> %d)", Ci, Co);
-  if ((Co + 7) / 8 > DSTD_NT / 32 || Ci > 64) return fail(-2, "DSTD-GC block: %d -> %d channels exceed the 64 supported", Ci, Co);
+  if (Co > 64 || Ci > 64) return fail(-2, "DSTD-GC block: %d -> %d channels exceed the 64 supported", Ci, Co);
   if (a.d[CB_IN_MODE] == 1 && Ci != 10) return fail(-2, "feature-building input mode needs Ci == 10");
   if (!a.d[CB_INTERP]) { a.tap_adj_s = nullptr; a.tap_adj_t = nullptr; }
   a.phase_clocks = g_phase_clocks;
   a.stamp_iter = g_stamp_iter;
-  if (!cg::dstd_plan(a, DSTD_NT, kMaxSmemBytes / 4) || (size_t)a.smem_floats * 4 > (size_t)kMaxSmemBytes)
-    return fail(-2, "DSTD-GC block (%d->%d, T=%d, V=%d) needs %zu B of shared memory (> %d)", Ci, Co, T, V,
-                (size_t)a.smem_floats * 4, kMaxSmemBytes);
+  // narrow blocks: 256 threads, two CTAs per SM (if the whole plan fits half an SM's shared memory);
+  // wide blocks: 512 threads, one CTA per SM
+  int nt = cg::DSTD_NT_NARROW;
+  if (!cg::dstd_plan(a, nt, cg::DSTD_SMEM_NARROW_BYTES / 4) || !cg::dstd_all_gemm_resident(a)) {
+    nt = cg::DSTD_NT_WIDE;
+    if (!cg::dstd_plan(a, nt, kMaxSmemBytes / 4) || (size_t)a.smem_floats * 4 > (size_t)kMaxSmemBytes)
+      return fail(-2, "DSTD-GC block (%d->%d, T=%d, V=%d) needs %zu B of shared memory (> %d)", Ci, Co, T, V,
+                  (size_t)a.smem_floats * 4, kMaxSmemBytes);
+  }
   ProfScope prof(KIND_DSTD, stream);
-  if (T == 10 && V == 22) return dstd_done(cg::launch_dstd_10_22(a, stream));
-  if (T == 10 && V == 18) return dstd_done(cg::launch_dstd_10_18(a, stream));
-  if (T == 22 && V == 25) return dstd_done(cg::launch_dstd_22_25(a, stream));
-  if (T == 18 && V == 25) return dstd_done(cg::launch_dstd_18_25(a, stream));
+#define CG_TRY_DSTD(TT, VV) \
+  if (T == TT && V == VV) return dstd_done(nt == 256 ? cg::launch_dstd_##TT##_##VV##_256(a, stream) : cg::launch_dstd_##TT##_##VV##_512(a, stream));
+  CG_TRY_DSTD(10, 22)
+  CG_TRY_DSTD(10, 18)
+  CG_TRY_DSTD(22, 25)
+  CG_TRY_DSTD(18, 25)
+#undef CG_TRY_DSTD
   return fail(-2, "DSTD-GC block: (T, V) = (%d, %d) has no compiled kernel "
                   "(built: (10,22), (10,18), (22,25), (18,25))", T, V);
 }

@@ -140,6 +140,9 @@ inline bool dstd_plan(DstdArgs& a, int nt, int max_smem_floats) {
   return ok && cur <= max_smem_floats;
 }
 
+// True when the plan keeps every GEMM-style operand resident (no ring needed).
+inline bool dstd_all_gemm_resident(const DstdArgs& a) { return a.ring_floats == 0; }
+
 // ---------------------------------------------------------------------------------------------
 // Weight delivery: body(wc, k0, kc) is called by every thread for consecutive row chunks
 // [k0, k0+kc) of a k-major matrix (row length Mp) with the rows available in shared memory at wc.
@@ -567,7 +570,7 @@ CG_DEV void gcn_time(const float* XN, const float* adj, float* G, int C) {
 
 // ---------------------------------------------------------------------------------------------
 template <int T, int V, int NT>
-__global__ void __launch_bounds__(NT, 1) dstd_block_kernel(const DstdArgs a) {
+__global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_block_kernel(const DstdArgs a) {
   CG_DYN_SMEM(smem);
   constexpr int TV = T * V, TT = T * T, VV = V * V, VP = V | 1;   // VP: odd row stride of the transposed Adj_s
   constexpr int NW = NT / 32;

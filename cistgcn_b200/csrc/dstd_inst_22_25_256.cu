@@ -1,0 +1,5 @@
+// Explicit instantiation of the fused DSTD-GC kernel for (T, V) = (22, 25), 256 threads per CTA.
+#include "dstd_launch.h"
+namespace cg {
+int launch_dstd_22_25_256(const DstdArgs& a, void* stream) { return launch_dstd_impl<22, 25, 256>(a, stream); }
+}  // namespace cg

@@ -1,30 +1,37 @@
-// Launchers of the fused DSTD-GC kernel, one translation unit per (T, V) instantiation so that nvcc
-// can compile them in parallel (dstd_inst_*.cu).  Return 0 or a CUDA error code.
+// Launchers of the fused DSTD-GC kernel, one translation unit per (T, V, threads) instantiation so that
+// nvcc can compile them in parallel (dstd_inst_*.cu).  Return 0 or a CUDA error code.
+//
+// Two CTA shapes: 512 threads x 1 CTA per SM (wide blocks: the fp32 working set of E >= 32 fills the SM's
+// shared memory) and 256 threads x 2 CTAs per SM (narrow blocks: two samples in flight per SM hide each
+// other's barrier and latency stalls).  cistgcn_api.cu picks by what the shared-memory plan allows.
 #pragma once
 #include "dstd_block.cuh"
 #include "host_util.h"
 
 namespace cg {
 
-#ifndef CISTGCN_DSTD_NT
-#define CISTGCN_DSTD_NT 512
-#endif
-constexpr int DSTD_NT = CISTGCN_DSTD_NT;
+constexpr int DSTD_NT_WIDE = 512;      // 1 CTA / SM, up to 227 KB of shared memory
+constexpr int DSTD_NT_NARROW = 256;    // 2 CTAs / SM, up to 113 KB each
+constexpr int DSTD_SMEM_NARROW_BYTES = (233472 - 2 * 1024) / 2;
 
-int launch_dstd_10_22(const DstdArgs& a, void* stream);
-int launch_dstd_10_18(const DstdArgs& a, void* stream);
-int launch_dstd_22_25(const DstdArgs& a, void* stream);
-int launch_dstd_18_25(const DstdArgs& a, void* stream);
+#define CG_DECL_DSTD(T, V) \
+  int launch_dstd_##T##_##V##_256(const DstdArgs& a, void* stream); \
+  int launch_dstd_##T##_##V##_512(const DstdArgs& a, void* stream);
+CG_DECL_DSTD(10, 22)
+CG_DECL_DSTD(10, 18)
+CG_DECL_DSTD(22, 25)
+CG_DECL_DSTD(18, 25)
+#undef CG_DECL_DSTD
 
-template <int T, int V>
+template <int T, int V, int NT>
 inline int launch_dstd_impl(const DstdArgs& a, void* stream) {
-  auto kfn = dstd_block_kernel<T, V, DSTD_NT>;
+  auto kfn = dstd_block_kernel<T, V, NT>;
   const size_t smem = (size_t)a.smem_floats * sizeof(float);
   int err = 0;
-  const int per_sm = prepared_blocks_per_sm(kfn, DSTD_NT, smem, &err);
+  const int per_sm = prepared_blocks_per_sm(kfn, NT, smem, &err);
   if (err) return err;
   const int grid = grid_for(a.batch, per_sm);
-  CG_LAUNCH(kfn, grid, DSTD_NT, smem, stream, a);
+  CG_LAUNCH(kfn, grid, NT, smem, stream, a);
   return last_launch_error();
 }
 

@@ -10,7 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(HERE, "_build", "libcistgcn_emu.so")
 CSRC = os.path.join(ROOT, "cistgcn_b200", "csrc")
-UNITS = ["cistgcn_api.cu", "dstd_inst_10_22.cu", "dstd_inst_10_18.cu", "dstd_inst_22_25.cu", "dstd_inst_18_25.cu",
+UNITS = ["cistgcn_api.cu", "dstd_inst_10_22_256.cu", "dstd_inst_10_22_512.cu", "dstd_inst_10_18_256.cu", "dstd_inst_10_18_512.cu",
+           "dstd_inst_22_25_256.cu", "dstd_inst_22_25_512.cu", "dstd_inst_18_25_256.cu", "dstd_inst_18_25_512.cu",
          "fpn_inst_22.cu", "fpn_inst_18.cu"]
 SRCS = [os.path.join(CSRC, f) for f in UNITS + ["dstd_block.cuh", "fpn_chain.cuh", "tail.cuh", "simt.h", "host_util.h",
                                                  "dstd_launch.h", "fpn_launch.h"]] + \
