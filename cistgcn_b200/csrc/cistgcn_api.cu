@@ -106,7 +106,7 @@ int launch_dstd(const int32_t* desc, const float* weights, const float* in, floa
   // narrow blocks: 256 threads, two CTAs per SM (if the whole plan fits half an SM's shared memory);
   // wide blocks: 512 threads, one CTA per SM
   int nt = cg::DSTD_NT_NARROW;
-  if (!cg::dstd_plan(a, nt, cg::DSTD_SMEM_NARROW_BYTES / 4) || !cg::dstd_all_gemm_resident(a)) {
+  if (!cg::dstd_plan(a, nt, cg::DSTD_SMEM_NARROW_BYTES / 4)) {
     nt = cg::DSTD_NT_WIDE;
     if (!cg::dstd_plan(a, nt, kMaxSmemBytes / 4) || (size_t)a.smem_floats * 4 > (size_t)kMaxSmemBytes)
       return fail(-2, "DSTD-GC block (%d->%d, T=%d, V=%d) needs %zu B of shared memory (> %d)", Ci, Co, T, V,
