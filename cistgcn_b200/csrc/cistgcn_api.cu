@@ -10,6 +10,7 @@
 #include "../../include/cistgcn_b200.h"
 #include "dstd_launch.h"
 #include "fpn_launch.h"
+#include "fpn_tc_launch.h"
 #include "host_util.h"
 #include "simt.h"
 #include "tail.cuh"
@@ -124,9 +125,44 @@ int launch_dstd(const int32_t* desc, const float* weights, const float* in, floa
                   "(built: (10,22), (10,18), (22,25), (18,25))", T, V);
 }
 
+int g_fpn_path = 0;   // 0: tensor-core kernel whenever the shape fits, 1: FP32-FMA kernel (cistgcn_set_fpn_path)
+
+#ifndef CISTGCN_EMU
+// tcgen05 kernel (fpn_tc.cuh): 32-wide channel tiles, two 128-position tiles, weights packed with CF_TC_*
+bool fpn_tc_supported(const int32_t* fpn_descs, int n_fpn, const int32_t* tail_desc) {
+  const int To = tail_desc[CT_TOUT], V = tail_desc[CT_V], Tin = tail_desc[CT_TIN];
+  if (To > 25 || Tin > 16 || tail_desc[CT_F] != cg::FTC_F || (V != 22 && V != 18)) return false;
+  for (int l = 0; l < n_fpn; ++l) {
+    const int32_t* f = fpn_descs + l * CF_COUNT;
+    if (f[CF_TC_KC] != (l == 0 ? 2 : 4) || f[CF_TC_W] <= 0 || f[CF_TC_PRM] <= 0) return false;
+  }
+  return true;
+}
+
+int launch_fpn_tc(const int32_t* fpn_descs, int n_fpn, const int32_t* tail_desc, const float* weights,
+                  const float* in, float* x7, long long batch, void* stream) {
+  cg::FpnTcArgs a;
+  memcpy(a.f, fpn_descs, sizeof(int32_t) * CF_COUNT * n_fpn);
+  memcpy(a.t, tail_desc, sizeof(a.t));
+  a.n_layers = n_fpn; a.w = weights; a.in = in; a.x7 = x7; a.batch = (int)batch;
+  a.dbg = g_phase_clocks;
+  int e;
+  {
+    ProfScope prof(KIND_FPN, stream);
+    e = a.t[CT_V] == 22 ? cg::launch_fpn_tc_22(a, stream) : cg::launch_fpn_tc_18(a, stream);
+  }
+  if (e) return fail(-4, "fpn_tc_kernel launch: %s", cg::launch_error_string(e));
+  return 0;
+}
+#endif
+
 int launch_fpn(const int32_t* fpn_descs, int n_fpn, const int32_t* tail_desc, const float* weights,
                const float* in, float* x7, long long batch, void* stream) {
   if (n_fpn < 1 || n_fpn > cg::FPN_MAX_LAYERS) return fail(-2, "FPN chain: %d layers unsupported", n_fpn);
+#ifndef CISTGCN_EMU
+  if (g_fpn_path == 0 && fpn_tc_supported(fpn_descs, n_fpn, tail_desc))
+    return launch_fpn_tc(fpn_descs, n_fpn, tail_desc, weights, in, x7, batch, stream);
+#endif
   cg::FpnArgs a;
   memcpy(a.f, fpn_descs, sizeof(int32_t) * CF_COUNT * n_fpn);
   memcpy(a.t, tail_desc, sizeof(a.t));
@@ -225,6 +261,12 @@ int cistgcn_debug_phase_clocks(void* device_buffer) {
 
 int cistgcn_debug_stamp_iteration(int iteration) {
   g_stamp_iter = iteration < 0 ? 0 : iteration;
+  return 0;
+}
+
+int cistgcn_set_fpn_path(int path) {
+  if (path != 0 && path != 1) return fail(-1, "fpn path %d unknown (0 tensor-core when supported, 1 FP32-FMA)", path);
+  g_fpn_path = path;
   return 0;
 }
 

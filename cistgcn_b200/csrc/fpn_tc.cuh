@@ -1,0 +1,510 @@
+// Time-extrapolator stack on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
+//
+// Same contract as fpn_chain.cuh (4 x FPN, CISTGCN.py:38-79, with the caller's PReLU / residual :584-586,
+// then dim_conversor :541-545 and the cumulative sum :588-589), but the three dilated 3x3 convolutions and
+// the 1x1 `compress` run as implicit GEMMs issued with tcgen05.mma, accumulators in tensor memory.
+//
+// fp32 accuracy on a bf16 pipe: every operand is split into three bf16 terms (x = x1 + x2 + x3, 24 bits).
+// The weight image of a tap holds the three terms of W side by side as N = 96 rows, so one k-step is three
+// MMAs: x1 * [W1|W2|W3] (N = 96), x2 * [W1|W2] (N = 64), x3 * [W1] (N = 32), i.e. the six products that
+// carry more than 2^-24; the epilogue adds the three 32-column blocks.  Accumulation is fp32 in TMEM.
+//
+// Implicit GEMM without im2col: the sample's map lives in shared memory as [term][k-chunk of 8 channels]
+// [position][8 bf16] with positions at a 16-byte pitch (row pitch W + 3: the three pad columns serve as
+// the right padding of one row and the left padding of the next).  That is the K-major, no-swizzle
+// canonical layout with SBO = 128 B, whose operand may start at ANY position: a 3x3 tap with dilation d is
+// the same matrix started (kh-1)*d rows and (kw-1)*d columns away (profiles/micro/umma_probe.cu pins this).
+// M = 128 positions per MMA, two tiles cover the 10 x (V+3) map.
+//
+// Roles (one CTA of 384 threads per SM, persistent over samples):
+//   warp 0   weight producer: cp.async.bulk (1-D TMA) of per-tap slices from L2 into a 10-slot ring,
+//            mbarrier complete_tx; the ring is refilled behind the second tile's pass over a branch
+//   warp 1   MMA issuer (one thread): conv(d, tile) -> acc[tile] in TMEM; compress(d, tile) accumulates into
+//            cacc[tile]; schedule conv(d,0) cmp(d-1,1) conv(d,1) cmp(d,0) keeps the pipe busy while the
+//            epilogue of the other tile runs
+//   warps 2-3  input loader: next sample's (Tin, F, V) map -> bf16 terms, global-average branch of layer 0
+//   warps 4-11 epilogue, one warpgroup per tile (TMEM lane = position): branch bias + PReLU -> bf16 terms into
+//            the staging operand of `compress`; compress bias + average branch + PReLU (+ residual) -> next
+//            layer's map in place; last layer -> dim_conversor, cumsum, x7
+#pragma once
+#ifndef CISTGCN_EMU
+#include <cuda_bf16.h>
+
+#include "../../include/cistgcn_b200.h"
+#include "fpn_chain.cuh"
+#include "simt.h"
+
+namespace cg {
+
+constexpr int FTC_NT = 384;
+constexpr int FTC_F = 10;                              // feature rows (in_ch, CISTGCN.py:512)
+constexpr int FTC_SLOTS = 10;                          // 9 taps + the branch's compress slice
+constexpr int FTC_BROWS = 96;                          // B rows: 3 bf16 terms x 32 output channels
+constexpr int FTC_BCHUNK = FTC_BROWS * 16;             // bytes of one k-chunk of a weight slice
+constexpr int FTC_SLOT_BYTES = 4 * FTC_BCHUNK;         // 6144
+constexpr int FTC_STAGE_CHUNK = 256 * 16;              // staging operand: [term][chunk][256 positions][8 bf16]
+constexpr int FTC_TMEM_COLS = 512;
+constexpr int FTC_PRM_BIAS = 0, FTC_PRM_SLOPE = 96, FTC_PRM_OUT_A = 99, FTC_PRM_CPB = 100, FTC_PRM_WAVG = 132;
+
+enum { FB_FULL = 0, FB_EMPTY = 10, FB_ACC_FULL = 20, FB_ACC_EMPTY = 22, FB_STG_FULL = 24, FB_STG_EMPTY = 26,
+       FB_CACC_FULL = 28, FB_A_READY = 30, FB_IN_READY = 31, FB_A_FREE = 32, FB_A_RELEASE = 33, FB_COUNT = 34 };
+
+struct FpnTcArgs {
+  int f[FPN_MAX_LAYERS][CF_COUNT];
+  int t[CT_COUNT];
+  int n_layers;
+  const float* w;
+  const float* in;     // (B, Tin, F, V)
+  float* x7;           // (B, Tout, V, 3)
+  int batch;
+  long long* dbg;      // optional (cistgcn_debug_phase_clocks): CTA 0 writes its wait / total cycle counters, 16 x int64
+};
+
+template <int V>
+struct FtcGeom {
+  static constexpr int WP = V + 3;                     // row pitch in positions
+  static constexpr int Q0 = 3 * WP + 3;                // array row of map position (0, 0)
+  static constexpr int NPOS = 6 * WP + 262;            // rows reachable by tile + tap shifts
+  static constexpr int SA = NPOS * 16;                 // bytes of one [term][chunk] array
+  static constexpr int O_A = 0;
+  static constexpr int O_RING = (12 * SA + 127) / 128 * 128;
+  static constexpr int O_STAGE = O_RING + FTC_SLOTS * FTC_SLOT_BYTES;
+  static constexpr int O_SCR = O_STAGE + 12 * FTC_STAGE_CHUNK;       // final map, fp32 [position][To]
+  static constexpr int O_Y6 = O_SCR + 256 * 25 * 4;                  // 256 positions x (To <= 25) channels
+  static constexpr int O_MISC = O_Y6 + (25 * V * 3 * 4 + 15) / 16 * 16;
+  static constexpr int O_BAR = O_MISC + 8 * 32 * 4;                  // chsum[2][32] cst[2][32] chsum_in[2][32] cst_in[32] spare
+  static constexpr int SMEM_BYTES = O_BAR + FB_COUNT * 8 + 16;
+  static_assert(10 * WP <= 256, "map does not fit two 128-position tiles");
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------
+CG_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+CG_DEV uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {   // K-major, no swizzle, version 1
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+CG_DEV constexpr uint32_t umma_idesc_bf16(int n) {      // fp32 accumulate, bf16 x bf16, K-major both, M = 128
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+CG_DEV void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+CG_DEV void mbar_wait(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    if ((spin & 0xFFF) == 0xFFF && clock64() - t0 > 8000000000LL) __trap();   // a lost arrival must not hang the GPU
+  }
+}
+CG_DEV void mbar_wait_timed(uint32_t bar, uint32_t parity, long long& acc) {
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
+CG_DEV void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+CG_DEV void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+CG_DEV void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+CG_DEV void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+CG_DEV void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+CG_DEV void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+CG_DEV void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+CG_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+CG_DEV void named_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+CG_DEV void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(addr));
+}
+CG_DEV void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 16 accumulator columns of this thread's position: the three 32-column term blocks added, small terms first
+CG_DEV void ftc_load_sum(uint32_t addr, float (&o)[16]) {
+  uint32_t b0[16], b1[16], b2[16];
+  tmem_ld16(addr, b0);
+  tmem_ld16(addr + 32, b1);
+  tmem_ld16(addr + 64, b2);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o[i] = (__uint_as_float(b1[i]) + __uint_as_float(b2[i])) + __uint_as_float(b0[i]);
+}
+
+// 8 channels of one position -> three bf16 terms, one 16-byte chunk row each
+CG_DEV void ftc_split_store8(const float* x, unsigned char* dst, int term_stride) {
+  uint32_t t1[4], t2[4], t3[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float x0 = x[2 * e], x1 = x[2 * e + 1];
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    float r0 = x0 - __low2float(h), r1 = x1 - __high2float(h);
+    const __nv_bfloat162 m = __floats2bfloat162_rn(r0, r1);
+    r0 -= __low2float(m);
+    r1 -= __high2float(m);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
+    t1[e] = *reinterpret_cast<const uint32_t*>(&h);
+    t2[e] = *reinterpret_cast<const uint32_t*>(&m);
+    t3[e] = *reinterpret_cast<const uint32_t*>(&l);
+  }
+  *reinterpret_cast<uint4*>(dst) = make_uint4(t1[0], t1[1], t1[2], t1[3]);
+  *reinterpret_cast<uint4*>(dst + term_stride) = make_uint4(t2[0], t2[1], t2[2], t2[3]);
+  *reinterpret_cast<uint4*>(dst + 2 * term_stride) = make_uint4(t3[0], t3[1], t3[2], t3[3]);
+}
+
+CG_DEV void ftc_add_terms8(const unsigned char* src, int term_stride, float* x) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const uint4 q = *reinterpret_cast<const uint4*>(src + j * term_stride);
+    const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      x[2 * e] += __uint_as_float(wv[e] << 16);
+      x[2 * e + 1] += __uint_as_float(wv[e] & 0xFFFF0000u);
+    }
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
+  using G = FtcGeom<V>;
+  extern __shared__ __align__(128) unsigned char ftc_smem[];
+  constexpr int WP = G::WP, Q0 = G::Q0, SA = G::SA, F = FTC_F, FV = F * V;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int L = a.n_layers, Tin = a.t[CT_TIN], To = a.t[CT_TOUT];
+  const uint32_t sbase = smem_u32(ftc_smem);
+  unsigned char* sA = ftc_smem + G::O_A;
+  unsigned char* sStage = ftc_smem + G::O_STAGE;
+  float* scr = reinterpret_cast<float*>(ftc_smem + G::O_SCR);
+  float* y6 = reinterpret_cast<float*>(ftc_smem + G::O_Y6);
+  float* misc = reinterpret_cast<float*>(ftc_smem + G::O_MISC);
+  float* chsum = misc;              // [2][32] channel sums of the next layer's input
+  float* cstv = misc + 64;          // [2][32] compress bias + average branch, per layer parity
+  float* chsum_in = misc + 128;     // [2][32] same for layer 0, per sample parity
+  float* cst_in = misc + 192;       // [32]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ftc_smem + G::O_BAR + FB_COUNT * 8);
+  auto bar = [&](int i) { return sbase + G::O_BAR + 8 * i; };
+
+  if (tid == 0) {
+    for (int s = 0; s < FTC_SLOTS; ++s) { mbar_init(bar(FB_FULL + s), 1); mbar_init(bar(FB_EMPTY + s), 1); }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(bar(FB_ACC_FULL + t), 1);
+      mbar_init(bar(FB_ACC_EMPTY + t), 128);
+      mbar_init(bar(FB_STG_FULL + t), 128);
+      mbar_init(bar(FB_STG_EMPTY + t), 1);
+      mbar_init(bar(FB_CACC_FULL + t), 1);
+    }
+    mbar_init(bar(FB_A_READY), 256);
+    mbar_init(bar(FB_IN_READY), 64);
+    mbar_init(bar(FB_A_FREE), 1);
+    mbar_init(bar(FB_A_RELEASE), 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // zero the map (padding rows / columns / channels stay zero for the kernel's lifetime) and the small state
+  for (int i = tid; i < 12 * SA / 16; i += FTC_NT) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 8 * 32; i += FTC_NT) misc[i] = 0.f;
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)FTC_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const float inv_fv = 1.f / (float)FV;
+
+  if (warp == 0) {
+    // ===== weight producer =====
+    if (lane == 0) {
+      uint32_t u = 0;
+      for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
+        for (int l = 0; l < L; ++l) {
+          const uint32_t tap_bytes = (uint32_t)a.f[l][CF_TC_KC] * FTC_BCHUNK;
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(a.w + a.f[l][CF_TC_W]);
+          for (int d = 0; d < 3; ++d, ++u) {
+            for (int s = 0; s < FTC_SLOTS; ++s) {
+              mbar_wait(bar(FB_EMPTY + s), (u & 1) ^ 1);
+              const uint32_t bytes = s < 9 ? tap_bytes : (uint32_t)FTC_SLOT_BYTES;
+              mbar_expect_tx(bar(FB_FULL + s), bytes);
+              bulk_g2s(sbase + G::O_RING + s * FTC_SLOT_BYTES, src, bytes, bar(FB_FULL + s));
+              src += bytes;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t I96 = umma_idesc_bf16(96), I64 = umma_idesc_bf16(64), I32 = umma_idesc_bf16(32);
+      const uint64_t dA0 = umma_desc(sbase + G::O_A, SA, 128);
+      const uint64_t dB0 = umma_desc(sbase + G::O_RING, FTC_BCHUNK, 128);
+      const uint64_t dS0 = umma_desc(sbase + G::O_STAGE, FTC_STAGE_CHUNK, 128);
+      const uint32_t acc[2] = {tmem, tmem + 96}, cacc[2] = {tmem + 192, tmem + 288};
+      uint32_t u0 = 0, ar = 0, it = 0;
+      long long w_in = 0, w_ar = 0, w_acc = 0, w_full = 0, w_stg = 0;
+      const long long t_begin = clock64();
+      for (int b = blockIdx.x; b < a.batch; b += gridDim.x, ++it) {
+        mbar_wait_timed(bar(FB_IN_READY), it & 1, w_in);
+        tc_fence_after();
+        for (int l = 0; l < L; ++l, u0 += 3) {
+          const int nks = a.f[l][CF_TC_KC] / 2;
+          if (l > 0) { mbar_wait_timed(bar(FB_A_READY), ar & 1, w_ar); ++ar; tc_fence_after(); }
+          auto conv = [&](int d, int t) {
+            const uint32_t ud = u0 + d;
+            mbar_wait_timed(bar(FB_ACC_EMPTY + t), (ud & 1) ^ 1, w_acc);
+            tc_fence_after();
+            for (int tap = 0; tap < 9; ++tap) {
+              if (t == 0) { mbar_wait_timed(bar(FB_FULL + tap), ud & 1, w_full); tc_fence_after(); }
+              const int kh = tap / 3, kw = tap - kh * 3;
+              const int row = Q0 + t * 128 + (kh - 1) * (d + 1) * WP + (kw - 1) * (d + 1);
+              for (int ks = 0; ks < nks; ++ks) {
+                const uint64_t da = dA0 + (uint64_t)((2 * ks * SA + row * 16) >> 4);
+                const uint64_t db = dB0 + (uint64_t)((tap * FTC_SLOT_BYTES + 2 * ks * FTC_BCHUNK) >> 4);
+                umma_bf16(acc[t], da, db, I96, (tap | ks) != 0);
+                umma_bf16(acc[t], da + (uint64_t)((4 * SA) >> 4), db, I64, 1);
+                umma_bf16(acc[t], da + (uint64_t)((8 * SA) >> 4), db, I32, 1);
+              }
+              if (t == 1) umma_commit(bar(FB_EMPTY + tap));      // both tiles have read this tap: refill it
+            }
+            umma_commit(bar(FB_ACC_FULL + t));
+            if (l == L - 1 && d == 2 && t == 1) umma_commit(bar(FB_A_FREE));   // the map may take the next sample
+          };
+          auto cmp = [&](int d, int t) {
+            const uint32_t ud = u0 + d;
+            if (t == 0) mbar_wait_timed(bar(FB_FULL + 9), ud & 1, w_full);
+            mbar_wait_timed(bar(FB_STG_FULL + t), ud & 1, w_stg);
+            tc_fence_after();
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t da = dS0 + (uint64_t)((2 * ks * FTC_STAGE_CHUNK + t * 128 * 16) >> 4);
+              const uint64_t db = dB0 + (uint64_t)((9 * FTC_SLOT_BYTES + 2 * ks * FTC_BCHUNK) >> 4);
+              umma_bf16(cacc[t], da, db, I96, (d | ks) != 0);
+              umma_bf16(cacc[t], da + (uint64_t)((4 * FTC_STAGE_CHUNK) >> 4), db, I64, 1);
+              umma_bf16(cacc[t], da + (uint64_t)((8 * FTC_STAGE_CHUNK) >> 4), db, I32, 1);
+            }
+            umma_commit(bar(FB_STG_EMPTY + t));
+            if (t == 1) umma_commit(bar(FB_EMPTY + 9));
+            if (d == 2) umma_commit(bar(FB_CACC_FULL + t));
+          };
+          for (int d = 0; d < 3; ++d) {
+            conv(d, 0);
+            if (d > 0) cmp(d - 1, 1);
+            conv(d, 1);
+            cmp(d, 0);
+          }
+          cmp(2, 1);
+        }
+      }
+      if (a.dbg && blockIdx.x == 0) {
+        a.dbg[0] = clock64() - t_begin; a.dbg[1] = w_in; a.dbg[2] = w_ar; a.dbg[3] = w_acc; a.dbg[4] = w_full; a.dbg[5] = w_stg;
+        a.dbg[6] = it;
+      }
+    }
+  } else if (warp < 4) {
+    // ===== input loader (64 threads) =====
+    const int lt = tid - 64;
+    uint32_t it = 0;
+    const float* prm0 = a.w + a.f[0][CF_TC_PRM];
+    const int kc0 = a.f[0][CF_TC_KC];
+    for (int b = blockIdx.x; b < a.batch; b += gridDim.x, ++it) {
+      const float* src = a.in + (size_t)b * Tin * FV;
+      float xin[4][16];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int idx = lt + 64 * k;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) xin[k][c] = (idx < FV && c < Tin) ? __ldg(src + c * FV + idx) : 0.f;
+      }
+      if (it > 0) {                                         // previous sample: last convolutions and residual reads done
+        mbar_wait(bar(FB_A_FREE), (it - 1) & 1);
+        mbar_wait(bar(FB_A_RELEASE), (it - 1) & 1);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int idx = lt + 64 * k;
+        if (idx < FV) {
+          const int h = idx / V, w = idx - h * V;
+          unsigned char* dst = sA + (size_t)(Q0 + h * WP + w) * 16;
+          ftc_split_store8(&xin[k][0], dst, 4 * SA);
+          ftc_split_store8(&xin[k][8], dst + SA, 4 * SA);
+          if (kc0 > 2) {                                    // Tin > 16 would need the upper chunks; zero them
+            const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            ftc_split_store8(z, dst + 2 * SA, 4 * SA);
+            ftc_split_store8(z, dst + 3 * SA, 4 * SA);
+          }
+        }
+      }
+      float* cs = chsum_in + (it & 1) * 32;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        float s = (xin[0][c] + xin[1][c]) + (xin[2][c] + xin[3][c]);
+        s = warp_sum(s);
+        if (lane == 0 && c < Tin) atomicAdd(cs + c, s);
+      }
+      named_bar(3, 64);
+      if (warp == 2) {
+        float acc = __ldg(prm0 + FTC_PRM_CPB + lane);
+        for (int c = 0; c < Tin; ++c) acc = fmaf(__ldg(prm0 + FTC_PRM_WAVG + c * 32 + lane), cs[c] * inv_fv, acc);
+        cst_in[lane] = acc;
+        __syncwarp();
+        cs[lane] = 0.f;
+      }
+      fence_proxy_async();
+      mbar_arrive(bar(FB_IN_READY));
+    }
+  } else {
+    // ===== epilogue: warpgroup t owns tile t, thread = position =====
+    const int t = (warp - 4) >> 2, q = warp & 3;
+    const int m = q * 32 + lane;
+    const int p = t * 128 + m;
+    const int ph = p / WP, pw = p - ph * WP;
+    const bool valid = ph < F && pw < V;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const uint32_t acc = tmem + t * 96 + lane_addr, cacc = tmem + 192 + t * 96 + lane_addr;
+    unsigned char* stage_row = sStage + (size_t)p * 16;
+    unsigned char* a_row = sA + (size_t)(Q0 + p) * 16;
+    const int et = tid - 128;
+    uint32_t u = 0, lv = 0, it = 0;
+    long long w_in = 0, w_accf = 0, w_stge = 0, w_cacc = 0, w_nb = 0;
+    const long long t_begin = clock64();
+    for (int b = blockIdx.x; b < a.batch; b += gridDim.x, ++it) {
+      mbar_wait_timed(bar(FB_IN_READY), it & 1, w_in);      // cst_in of this sample is visible
+      for (int l = 0; l < L; ++l) {
+        const float* prm = a.w + a.f[l][CF_TC_PRM];
+        for (int d = 0; d < 3; ++d, ++u) {
+          const float slope = __ldg(prm + FTC_PRM_SLOPE + d);
+          mbar_wait_timed(bar(FB_ACC_FULL + t), u & 1, w_accf);
+          tc_fence_after();
+          mbar_wait_timed(bar(FB_STG_EMPTY + t), (u & 1) ^ 1, w_stge);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float o[16];
+            ftc_load_sum(acc + half * 16, o);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = prelu(o[i] + __ldg(prm + FTC_PRM_BIAS + d * 32 + half * 16 + i), slope);
+            ftc_split_store8(&o[0], stage_row + (2 * half) * FTC_STAGE_CHUNK, 4 * FTC_STAGE_CHUNK);
+            ftc_split_store8(&o[8], stage_row + (2 * half + 1) * FTC_STAGE_CHUNK, 4 * FTC_STAGE_CHUNK);
+          }
+          tc_fence_before();
+          mbar_arrive(bar(FB_ACC_EMPTY + t));
+          fence_proxy_async();
+          mbar_arrive(bar(FB_STG_FULL + t));
+        }
+        // ---- compress epilogue: bias + average branch, caller's PReLU (+ residual) ----
+        const bool last = l == L - 1;
+        const bool resid = a.f[l][CF_RESID] != 0;
+        const float oa = __ldg(prm + FTC_PRM_OUT_A);
+        float xo[32];                                       // residual: this layer's input at this position
+#pragma unroll
+        for (int i = 0; i < 32; ++i) xo[i] = 0.f;
+        if (resid) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) ftc_add_terms8(a_row + c * SA, 4 * SA, &xo[8 * c]);
+        }
+        if (last) mbar_arrive(bar(FB_A_RELEASE));           // the loader may overwrite the map once a_free fires too
+        mbar_wait_timed(bar(FB_CACC_FULL + t), lv & 1, w_cacc);
+        ++lv;
+        tc_fence_after();
+        { const long long tb = clock64(); named_bar(1, 256); w_nb += clock64() - tb; }   // this layer's cst is in place
+        const float* cst = l == 0 ? cst_in : cstv + (l & 1) * 32;
+        float* csn = chsum + ((l + 1) & 1) * 32;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float o[16];
+          ftc_load_sum(cacc + half * 16, o);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float val = prelu(o[i] + cst[half * 16 + i], oa) + xo[half * 16 + i];
+            o[i] = valid ? val : 0.f;
+          }
+          if (last) {
+            if (valid) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (half * 16 + i < To) scr[p * To + half * 16 + i] = o[i];
+            }
+          } else {
+            ftc_split_store8(&o[0], a_row + (2 * half) * SA, 4 * SA);
+            ftc_split_store8(&o[8], a_row + (2 * half + 1) * SA, 4 * SA);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float s = warp_sum(o[i]);
+              if (lane == 0 && half * 16 + i < To) atomicAdd(csn + half * 16 + i, s);
+            }
+          }
+        }
+        tc_fence_before();
+        if (!last) {
+          fence_proxy_async();
+          mbar_arrive(bar(FB_A_READY));
+        }
+        named_bar(1, 256);                                  // channel sums complete / final map complete
+        if (!last) {
+          if (warp == 4) {
+            const float* prn = a.w + a.f[l + 1][CF_TC_PRM];
+            float accv = __ldg(prn + FTC_PRM_CPB + lane);
+            for (int c = 0; c < To; ++c) accv = fmaf(__ldg(prn + FTC_PRM_WAVG + c * 32 + lane), csn[c] * inv_fv, accv);
+            cstv[((l + 1) & 1) * 32 + lane] = accv;
+            __syncwarp();
+            csn[lane] = 0.f;
+          }
+        } else {
+          // dim_conversor on (F channels, To, V): conv1x1 F->3, BN, PReLU, conv1x1 3->3, PReLU(3)  (:541-545)
+          const float* W = a.w;
+          const float* w0 = W + a.t[CT_DC0_WT];
+          const float* b0 = W + a.t[CT_DC0_B];
+          const float a0 = __ldg(W + a.t[CT_DC0_A]);
+          const float* w3 = W + a.t[CT_DC3_WT];
+          const float* a3 = W + a.t[CT_DC3_A];
+          for (int i = et; i < To * V; i += 256) {
+            const int fr = i / V, v = i - fr * V;
+            float y[3] = {__ldg(b0), __ldg(b0 + 1), __ldg(b0 + 2)};
+            for (int c = 0; c < F; ++c) {
+              const float xv = scr[(c * WP + v) * To + fr];
+#pragma unroll
+              for (int k = 0; k < 3; ++k) y[k] = fmaf(__ldg(w0 + c * 8 + k), xv, y[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) y[k] = prelu(y[k], a0);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              float z = 0.f;
+#pragma unroll
+              for (int j = 0; j < 3; ++j) z = fmaf(__ldg(w3 + j * 8 + k), y[j], z);
+              y6[i * 3 + k] = prelu(z, __ldg(a3 + k));
+            }
+          }
+          named_bar(1, 256);
+          float* dst = a.x7 + (size_t)b * To * V * 3;           // x7 = cumsum over frames (:589)
+          for (int i = et; i < V * 3; i += 256) {
+            float s = 0.f;
+            for (int fr = 0; fr < To; ++fr) { s += y6[fr * V * 3 + i]; dst[fr * V * 3 + i] = s; }
+          }
+        }
+      }
+    }
+    if (a.dbg && blockIdx.x == 0 && (tid == 128 || tid == 256)) {
+      long long* o = a.dbg + (tid == 128 ? 8 : 16);
+      o[0] = clock64() - t_begin; o[1] = w_in; o[2] = w_accf; o[3] = w_stge; o[4] = w_cacc; o[5] = w_nb;
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)FTC_TMEM_COLS));
+  }
+}
+
+}  // namespace cg
+#endif  // CISTGCN_EMU

@@ -103,6 +103,16 @@ class _Blob:
         self.size = 0
         self.offsets: Dict[str, int] = {}
 
+    def add_raw(self, name: str, words: torch.Tensor) -> int:
+        """Appends raw 32-bit words (bf16 pairs of the tensor-core images); bit patterns are preserved."""
+        words = words.detach().reshape(-1).cpu()
+        assert words.dtype == torch.int32 and words.numel() % 4 == 0
+        off = self.size
+        self.chunks.append(words)
+        self.size += words.numel()
+        self.offsets[name] = off
+        return off
+
     def add(self, name: str, t: torch.Tensor) -> int:
         t = t.detach().to(torch.float64).reshape(-1).cpu()
         off = self.size
@@ -116,7 +126,8 @@ class _Blob:
         return off
 
     def finish(self, device) -> torch.Tensor:
-        return torch.cat(self.chunks).to(torch.float32).to(device).contiguous()
+        words = [c if c.dtype == torch.int32 else c.to(torch.float32).view(torch.int32) for c in self.chunks]
+        return torch.cat(words).view(torch.float32).to(device).contiguous()
 
 
 def _fold(sd, p):
@@ -247,6 +258,58 @@ def _pack_block(blob: _Blob, sd, p: str, ci: int, co: int, T: int, V: int, inter
     return d
 
 
+def bf16_split3(w: torch.Tensor):
+    """w (any float dtype) -> three bf16 tensors with fp32(w) == b1 + b2 + b3 up to 2^-24 relative."""
+    w32 = w.to(torch.float32)
+    b1 = w32.to(torch.bfloat16)
+    r = w32 - b1.float()
+    b2 = r.to(torch.bfloat16)
+    b3 = (r - b2.float()).to(torch.bfloat16)
+    return b1, b2, b3
+
+
+def tc_slice(Wm: torch.Tensor, kc: int) -> torch.Tensor:
+    """(cout <= 32, cin <= 8*kc) matrix -> int32 words of the K-major tcgen05 operand image
+    [kc k-chunks][96 rows = 32*term + cout][8 bf16] (csrc/fpn_tc.cuh)."""
+    co, ci = Wm.shape
+    assert co <= 32 and ci <= 8 * kc
+    full = torch.zeros(32, kc * 8, dtype=torch.float64)
+    full[:co, :ci] = Wm
+    img = torch.zeros(kc, 96, 8, dtype=torch.bfloat16)
+    for j, part in enumerate(bf16_split3(full)):
+        img[:, 32 * j: 32 * j + 32, :] = part.reshape(32, kc, 8).permute(1, 0, 2)
+    return img.contiguous().view(torch.int32).reshape(-1)
+
+
+TC_PRM_BIAS, TC_PRM_SLOPE, TC_PRM_OUT_A, TC_PRM_CPB, TC_PRM_WAVG, TC_PRM_FLOATS = 0, 96, 99, 100, 132, 132 + 32 * 32
+
+
+def _pack_fpn_tc(blob: _Blob, sd, p: str, prelu_key: str, cin: int, cout: int, d: List[int]) -> None:
+    """Tensor-core image of one FPN layer (only when it fits the kernel's 32-wide tiles)."""
+    if cout > 32 or cin > 32:
+        return
+    kc = pad_up(cin, 16) // 8
+    words, prm = [], torch.zeros(TC_PRM_FLOATS, dtype=torch.float64)
+    Wc = _w(sd, f"{p}.compress.weight").reshape(cout, 3 * cout + cin)
+    for i in (1, 2, 3):
+        s, b = _fold(sd, f"{p}.block{i}.1")
+        W = s[:, None, None, None] * _w(sd, f"{p}.block{i}.0.weight")                   # (cout, cin, 3, 3)
+        for kh in range(3):
+            for kw in range(3):
+                words.append(tc_slice(W[:, :, kh, kw], kc))
+        words.append(tc_slice(Wc[:, (i - 1) * cout: i * cout], 4))
+        prm[TC_PRM_BIAS + 32 * (i - 1): TC_PRM_BIAS + 32 * (i - 1) + cout] = s * _w(sd, f"{p}.block{i}.0.bias") + b
+        prm[TC_PRM_SLOPE + i - 1] = _w(sd, f"{p}.block{i}.3.weight").reshape(-1)[0]
+    prm[TC_PRM_OUT_A] = _w(sd, prelu_key + ".weight").reshape(-1)[0]
+    prm[TC_PRM_CPB: TC_PRM_CPB + cout] = _w(sd, f"{p}.compress.bias")
+    wavg = torch.zeros(32, 32, dtype=torch.float64)
+    wavg[:cin, :cout] = Wc[:, 3 * cout:].t()
+    prm[TC_PRM_WAVG:] = wavg.reshape(-1)
+    d[F["CF_TC_KC"]] = kc
+    d[F["CF_TC_W"]] = blob.add_raw(f"{p}:tc_w", torch.cat(words))
+    d[F["CF_TC_PRM"]] = blob.add(f"{p}:tc_prm", prm)
+
+
 def _pack_fpn(blob: _Blob, sd, p: str, prelu_key: str, cin: int, cout: int, resid: bool) -> List[int]:
     if cout % 5 != 0:
         raise ValueError("cistgcn_b200 FPN kernel needs output_n to be a multiple of 5")
@@ -267,6 +330,7 @@ def _pack_fpn(blob: _Blob, sd, p: str, prelu_key: str, cin: int, cout: int, resi
     d[F["CF_CP_AVG_WT"]] = blob.add(f"{p}:cp_avg_wt", _kmajor(Wc[:, 3 * cout:]))
     d[F["CF_CP_B"]] = blob.add(f"{p}:cp_b", _w(sd, f"{p}.compress.bias"))
     d[F["CF_OUT_A"]] = blob.add(f"{p}:out_a", _w(sd, prelu_key + ".weight"))
+    _pack_fpn_tc(blob, sd, p, prelu_key, cin, cout, d)
     return d
 
 

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CISTGCN_ABI_VERSION 3
+#define CISTGCN_ABI_VERSION 4
 #define CISTGCN_MPAD 8          /* output-dimension padding of every k-major matrix */
 #define CISTGCN_MAX_BLOCKS 8    /* input + output DSTD-GC blocks in one plan */
 #define CISTGCN_MAX_FPN 8
@@ -94,6 +94,11 @@ enum cistgcn_fpn_field {
   CF_CP_AVG_WT,   /* compress weights for the Cin global-average channels: [Cin][pad(Cout)] */
   CF_CP_B,        /* compress bias [Cout] */
   CF_OUT_A,       /* prelus.{i} slope */
+  /* tensor-core (tcgen05) image of the same layer, see csrc/fpn_tc.cuh.  Weights are split into three bf16
+   * terms (w = w1 + w2 + w3 to 24 bits) so that fp32 accuracy survives the bf16 tensor pipe. */
+  CF_TC_KC,       /* 16-byte k-chunks (8 input channels each) per kernel tap: pad16(Cin) / 8 */
+  CF_TC_W,        /* 3 branches x { 9 tap slices [KC][96][8 bf16], 1 compress slice [4][96][8 bf16] }; row = 32*term + cout */
+  CF_TC_PRM,      /* fp32: bias[3][32], slope[3], out slope, compress bias[32], avg-branch weights [32 cin][32 cout] */
   CF_COUNT
 };
 
@@ -186,6 +191,10 @@ int cistgcn_tail_f32(const int32_t* tail_desc, const float* weights, const float
 /* mpjpe: err (optional): (B, T, V) per-joint L2 error; frame_sums (optional): double[T] accumulated. */
 int cistgcn_mpjpe_f32(const float* pred, const float* target, int64_t batch, int32_t T, int32_t V,
                       float* err, double* frame_sums, void* stream);
+
+/* FPN stack kernel choice (process-wide): 0 (default) = tcgen05 tensor-core kernel whenever the shape fits
+ * (csrc/fpn_tc.cuh), 1 = FP32-FMA kernel (csrc/fpn_chain.cuh).  Both implement CISTGCN.py:38-79, 582-589. */
+int cistgcn_set_fpn_path(int path);
 
 /* Optional per-kernel timing for benchmarks (no reference counterpart).  While enabled every launch
  * is bracketed by CUDA events on its stream; cistgcn_profile_read synchronises the device, sums the
