@@ -135,6 +135,7 @@ bool fpn_tc_supported(const int32_t* fpn_descs, int n_fpn, const int32_t* tail_d
   for (int l = 0; l < n_fpn; ++l) {
     const int32_t* f = fpn_descs + l * CF_COUNT;
     if (f[CF_TC_KC] != (l == 0 ? 2 : 4) || f[CF_TC_W] <= 0 || f[CF_TC_PRM] <= 0) return false;
+    if ((f[CF_RESID] != 0) != (l > 0)) return false;       // layer 0 reads the separate input buffer, no residual there
   }
   return true;
 }

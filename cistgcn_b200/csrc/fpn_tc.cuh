@@ -4,13 +4,17 @@
 // then dim_conversor :541-545 and the cumulative sum :588-589), but the three dilated 3x3 convolutions and
 // the 1x1 `compress` run as implicit GEMMs issued with tcgen05.mma, accumulators in tensor memory.
 //
-// fp32 accuracy on a bf16 pipe: every operand is split into three bf16 terms (x = x1 + x2 + x3, 24 bits).
-// The weight image of a tap holds the three terms of W side by side as N = 96 rows, so one k-step is three
-// MMAs: x1 * [W1|W2|W3] (N = 96), x2 * [W1|W2] (N = 64), x3 * [W1] (N = 32), i.e. the six products that
-// carry more than 2^-24; the epilogue adds the three 32-column blocks.  Accumulation is fp32 in TMEM.
+// fp32 accuracy on the 16-bit tensor pipe: an activation is carried as x = x1 + x2 with x1 = bf16(x) (fp32 range)
+// and x2 = fp16(x - x1) (|x - x1| <= 2^-9 |x|, so fp16's narrow range is safe and the pair holds ~20 bits); a
+// weight as w = w1 + w2 + w3 (three bf16 terms, 24 bits) plus wh = fp16(w).  The weight image of a tap puts
+// [w1 | w2 | w3 | wh] side by side as 128 rows, so one k-step is two MMAs: x1 * [w1|w2|w3] (kind::f16 with bf16
+// operands, N = 96) and x2 * wh (fp16 operands, N = 32, accumulated into the first 32 columns); the epilogue adds
+// the three 32-column blocks.  Accumulation is fp32 in TMEM.  What is dropped is below 2^-20 |x||w|.
+// (The tensor pipe here is bound by shared-memory operand reads, ~70 B/clk: 12 KB per k-step this way against
+// 18 KB for three bf16 terms on both sides, which was the first version.)
 //
 // Implicit GEMM without im2col: the sample's map lives in shared memory as [term][k-chunk of 8 channels]
-// [position][8 bf16] with positions at a 16-byte pitch (row pitch W + 3: the three pad columns serve as
+// [position][8 x 16 bit] with positions at a 16-byte pitch (row pitch W + 3: the three pad columns serve as
 // the right padding of one row and the left padding of the next).  That is the K-major, no-swizzle
 // canonical layout with SBO = 128 B, whose operand may start at ANY position: a 3x3 tap with dilation d is
 // the same matrix started (kh-1)*d rows and (kw-1)*d columns away (profiles/micro/umma_probe.cu pins this).
@@ -22,13 +26,15 @@
 //   warp 1   MMA issuer (one thread): conv(d, tile) -> acc[tile] in TMEM; compress(d, tile) accumulates into
 //            cacc[tile]; schedule conv(d,0) cmp(d-1,1) conv(d,1) cmp(d,0) keeps the pipe busy while the
 //            epilogue of the other tile runs
-//   warps 2-3  input loader: next sample's (Tin, F, V) map -> bf16 terms, global-average branch of layer 0
+//   warps 2-3  input loader: next sample's (Tin, F, V) map -> the two terms in a separate input buffer (layer 0
+//            reads it, so the next sample's first layer overlaps this sample's last epilogue), average branch of layer 0
 //   warps 4-11 epilogue, one warpgroup per tile (TMEM lane = position): branch bias + PReLU -> bf16 terms into
 //            the staging operand of `compress`; compress bias + average branch + PReLU (+ residual) -> next
 //            layer's map in place; last layer -> dim_conversor, cumsum, x7
 #pragma once
 #ifndef CISTGCN_EMU
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "../../include/cistgcn_b200.h"
 #include "fpn_chain.cuh"
@@ -39,15 +45,15 @@ namespace cg {
 constexpr int FTC_NT = 384;
 constexpr int FTC_F = 10;                              // feature rows (in_ch, CISTGCN.py:512)
 constexpr int FTC_SLOTS = 10;                          // 9 taps + the branch's compress slice
-constexpr int FTC_BROWS = 96;                          // B rows: 3 bf16 terms x 32 output channels
+constexpr int FTC_BROWS = 128;                         // B rows: 3 bf16 terms + 1 fp16 copy, 32 output channels each
 constexpr int FTC_BCHUNK = FTC_BROWS * 16;             // bytes of one k-chunk of a weight slice
-constexpr int FTC_SLOT_BYTES = 4 * FTC_BCHUNK;         // 6144
-constexpr int FTC_STAGE_CHUNK = 256 * 16;              // staging operand: [term][chunk][256 positions][8 bf16]
+constexpr int FTC_SLOT_BYTES = 4 * FTC_BCHUNK;         // 8192
+constexpr int FTC_STAGE_CHUNK = 256 * 16;              // staging operand: [term][chunk][256 positions][8 x 16 bit]
 constexpr int FTC_TMEM_COLS = 512;
 constexpr int FTC_PRM_BIAS = 0, FTC_PRM_SLOPE = 96, FTC_PRM_OUT_A = 99, FTC_PRM_CPB = 100, FTC_PRM_WAVG = 132;
 
 enum { FB_FULL = 0, FB_EMPTY = 10, FB_ACC_FULL = 20, FB_ACC_EMPTY = 22, FB_STG_FULL = 24, FB_STG_EMPTY = 26,
-       FB_CACC_FULL = 28, FB_A_READY = 30, FB_IN_READY = 31, FB_A_FREE = 32, FB_A_RELEASE = 33, FB_COUNT = 34 };
+       FB_CACC_FULL = 28, FB_A_READY = 30, FB_IN_READY = 31, FB_IN_FREE = 32, FB_COUNT = 33 };
 
 struct FpnTcArgs {
   int f[FPN_MAX_LAYERS][CF_COUNT];
@@ -66,14 +72,16 @@ struct FtcGeom {
   static constexpr int Q0 = 3 * WP + 3;                // array row of map position (0, 0)
   static constexpr int NPOS = 6 * WP + 262;            // rows reachable by tile + tap shifts
   static constexpr int SA = NPOS * 16;                 // bytes of one [term][chunk] array
-  static constexpr int O_A = 0;
+  static constexpr int O_A = 0;                                      // map: [2 terms][4 chunks][NPOS][16 B]
+  static constexpr int O_IN = 8 * SA;                                // next sample's input: [2 terms][2 chunks][NPOS][16 B]
   static constexpr int O_RING = (12 * SA + 127) / 128 * 128;
   static constexpr int O_STAGE = O_RING + FTC_SLOTS * FTC_SLOT_BYTES;
-  static constexpr int O_SCR = O_STAGE + 12 * FTC_STAGE_CHUNK;       // final map, fp32 [position][To]
+  static constexpr int O_SCR = O_STAGE + 8 * FTC_STAGE_CHUNK;        // final map, fp32 [position][To]
   static constexpr int O_Y6 = O_SCR + 256 * 25 * 4;                  // 256 positions x (To <= 25) channels
   static constexpr int O_MISC = O_Y6 + (25 * V * 3 * 4 + 15) / 16 * 16;
-  static constexpr int O_BAR = O_MISC + 8 * 32 * 4;                  // chsum[2][32] cst[2][32] chsum_in[2][32] cst_in[32] spare
+  static constexpr int O_BAR = O_MISC + 768 * 4;                     // channel-sum partials and average-branch constants
   static constexpr int SMEM_BYTES = O_BAR + FB_COUNT * 8 + 16;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared-memory plan exceeds the 227 KB opt-in limit");
   static_assert(10 * WP <= 256, "map does not fit two 128-position tiles");
 };
 
@@ -84,6 +92,9 @@ CG_DEV uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {   // K-ma
 }
 CG_DEV constexpr uint32_t umma_idesc_bf16(int n) {      // fp32 accumulate, bf16 x bf16, K-major both, M = 128
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+CG_DEV constexpr uint32_t umma_idesc_f16(int n) {       // fp32 accumulate, fp16 x fp16, K-major both, M = 128
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 CG_DEV void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
 CG_DEV void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -116,6 +127,11 @@ CG_DEV void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
 CG_DEV void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+CG_DEV bool elect_one() {            // one lane of a converged warp; keeps the surrounding control flow warp-uniform
+  uint32_t pred = 0;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
 CG_DEV void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 CG_DEV void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 CG_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -139,37 +155,32 @@ CG_DEV void ftc_load_sum(uint32_t addr, float (&o)[16]) {
   for (int i = 0; i < 16; ++i) o[i] = (__uint_as_float(b1[i]) + __uint_as_float(b2[i])) + __uint_as_float(b0[i]);
 }
 
-// 8 channels of one position -> three bf16 terms, one 16-byte chunk row each
+// 8 channels of one position -> the bf16 term and the fp16 remainder, one 16-byte chunk row each
 CG_DEV void ftc_split_store8(const float* x, unsigned char* dst, int term_stride) {
-  uint32_t t1[4], t2[4], t3[4];
+  uint32_t t1[4], t2[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const float x0 = x[2 * e], x1 = x[2 * e + 1];
     const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-    float r0 = x0 - __low2float(h), r1 = x1 - __high2float(h);
-    const __nv_bfloat162 m = __floats2bfloat162_rn(r0, r1);
-    r0 -= __low2float(m);
-    r1 -= __high2float(m);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
+    const float r0 = fminf(fmaxf(x0 - __low2float(h), -65504.f), 65504.f);
+    const float r1 = fminf(fmaxf(x1 - __high2float(h), -65504.f), 65504.f);
+    const __half2 m = __floats2half2_rn(r0, r1);
     t1[e] = *reinterpret_cast<const uint32_t*>(&h);
     t2[e] = *reinterpret_cast<const uint32_t*>(&m);
-    t3[e] = *reinterpret_cast<const uint32_t*>(&l);
   }
   *reinterpret_cast<uint4*>(dst) = make_uint4(t1[0], t1[1], t1[2], t1[3]);
   *reinterpret_cast<uint4*>(dst + term_stride) = make_uint4(t2[0], t2[1], t2[2], t2[3]);
-  *reinterpret_cast<uint4*>(dst + 2 * term_stride) = make_uint4(t3[0], t3[1], t3[2], t3[3]);
 }
 
 CG_DEV void ftc_add_terms8(const unsigned char* src, int term_stride, float* x) {
+  const uint4 q = *reinterpret_cast<const uint4*>(src);
+  const uint4 r = *reinterpret_cast<const uint4*>(src + term_stride);
+  const uint32_t wq[4] = {q.x, q.y, q.z, q.w}, wr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    const uint4 q = *reinterpret_cast<const uint4*>(src + j * term_stride);
-    const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      x[2 * e] += __uint_as_float(wv[e] << 16);
-      x[2 * e + 1] += __uint_as_float(wv[e] & 0xFFFF0000u);
-    }
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wr[e]));
+    x[2 * e] += __uint_as_float(wq[e] << 16) + f.x;
+    x[2 * e + 1] += __uint_as_float(wq[e] & 0xFFFF0000u) + f.y;
   }
 }
 
@@ -186,10 +197,11 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
   float* scr = reinterpret_cast<float*>(ftc_smem + G::O_SCR);
   float* y6 = reinterpret_cast<float*>(ftc_smem + G::O_Y6);
   float* misc = reinterpret_cast<float*>(ftc_smem + G::O_MISC);
-  float* chsum = misc;              // [2][32] channel sums of the next layer's input
-  float* cstv = misc + 64;          // [2][32] compress bias + average branch, per layer parity
-  float* chsum_in = misc + 128;     // [2][32] same for layer 0, per sample parity
-  float* cst_in = misc + 192;       // [32]
+  float* chsum = misc;              // [2][8 warps][32] per-warp channel sums of the next layer's input (fixed-order
+                                    // reduction: results are bit-reproducible, no atomics)
+  float* cstv = misc + 512;         // [2][32] compress bias + average branch, per layer parity
+  float* cst_in = misc + 576;       // [2][32] same for layer 0, per sample parity (the loader runs a sample ahead)
+  float* chsum_in = misc + 640;     // [2][2 warps][32] loader partials, per sample parity
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ftc_smem + G::O_BAR + FB_COUNT * 8);
   auto bar = [&](int i) { return sbase + G::O_BAR + 8 * i; };
 
@@ -204,13 +216,12 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
     }
     mbar_init(bar(FB_A_READY), 256);
     mbar_init(bar(FB_IN_READY), 64);
-    mbar_init(bar(FB_A_FREE), 1);
-    mbar_init(bar(FB_A_RELEASE), 256);
+    mbar_init(bar(FB_IN_FREE), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // zero the map (padding rows / columns / channels stay zero for the kernel's lifetime) and the small state
   for (int i = tid; i < 12 * SA / 16; i += FTC_NT) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < 8 * 32; i += FTC_NT) misc[i] = 0.f;
+  for (int i = tid; i < 768; i += FTC_NT) misc[i] = 0.f;
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)FTC_TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -243,13 +254,16 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t I96 = umma_idesc_bf16(96), I64 = umma_idesc_bf16(64), I32 = umma_idesc_bf16(32);
+    // ===== MMA issuer: the whole warp walks the schedule (warp-uniform control flow keeps descriptors in
+    // uniform registers), one elected lane issues =====
+    {
+      constexpr uint32_t I96 = umma_idesc_bf16(96), I32H = umma_idesc_f16(32);
+      constexpr uint64_t BH = (uint64_t)((96 * 16) >> 4);              // the fp16 rows of a weight slice
       const uint64_t dA0 = umma_desc(sbase + G::O_A, SA, 128);
+      const uint64_t dI0 = umma_desc(sbase + G::O_IN, SA, 128);
       const uint64_t dB0 = umma_desc(sbase + G::O_RING, FTC_BCHUNK, 128);
       const uint64_t dS0 = umma_desc(sbase + G::O_STAGE, FTC_STAGE_CHUNK, 128);
-      const uint32_t acc[2] = {tmem, tmem + 96}, cacc[2] = {tmem + 192, tmem + 288};
+      const uint32_t acc0 = tmem, cacc0 = tmem + 192;
       uint32_t u0 = 0, ar = 0, it = 0;
       long long w_in = 0, w_ar = 0, w_acc = 0, w_full = 0, w_stg = 0;
       const long long t_begin = clock64();
@@ -263,37 +277,49 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
             const uint32_t ud = u0 + d;
             mbar_wait_timed(bar(FB_ACC_EMPTY + t), (ud & 1) ^ 1, w_acc);
             tc_fence_after();
+            const uint32_t acc = acc0 + t * 96;
             for (int tap = 0; tap < 9; ++tap) {
               if (t == 0) { mbar_wait_timed(bar(FB_FULL + tap), ud & 1, w_full); tc_fence_after(); }
               const int kh = tap / 3, kw = tap - kh * 3;
               const int row = Q0 + t * 128 + (kh - 1) * (d + 1) * WP + (kw - 1) * (d + 1);
-              for (int ks = 0; ks < nks; ++ks) {
-                const uint64_t da = dA0 + (uint64_t)((2 * ks * SA + row * 16) >> 4);
-                const uint64_t db = dB0 + (uint64_t)((tap * FTC_SLOT_BYTES + 2 * ks * FTC_BCHUNK) >> 4);
-                umma_bf16(acc[t], da, db, I96, (tap | ks) != 0);
-                umma_bf16(acc[t], da + (uint64_t)((4 * SA) >> 4), db, I64, 1);
-                umma_bf16(acc[t], da + (uint64_t)((8 * SA) >> 4), db, I32, 1);
+              const uint64_t da_tap = (l == 0 ? dI0 : dA0) + (uint64_t)(row);          // 16 bytes per position
+              const uint64_t db_tap = dB0 + (uint64_t)((tap * FTC_SLOT_BYTES) >> 4);
+              if (elect_one()) {
+                for (int ks = 0; ks < nks; ++ks) {
+                  const uint64_t da = da_tap + (uint64_t)((2 * ks * SA) >> 4);
+                  const uint64_t db = db_tap + (uint64_t)((2 * ks * FTC_BCHUNK) >> 4);
+                  umma_bf16(acc, da, db, I96, (tap | ks) != 0);
+                  umma_bf16(acc, da + (uint64_t)(((l == 0 ? 2 : 4) * SA) >> 4), db + BH, I32H, 1);
+                }
+                if (t == 1) umma_commit(bar(FB_EMPTY + tap));      // both tiles have read this tap: refill it
               }
-              if (t == 1) umma_commit(bar(FB_EMPTY + tap));      // both tiles have read this tap: refill it
+              __syncwarp();
             }
-            umma_commit(bar(FB_ACC_FULL + t));
-            if (l == L - 1 && d == 2 && t == 1) umma_commit(bar(FB_A_FREE));   // the map may take the next sample
+            if (elect_one()) {
+              umma_commit(bar(FB_ACC_FULL + t));
+              if (l == 0 && d == 2 && t == 1) umma_commit(bar(FB_IN_FREE));      // the input buffer may take the next sample
+            }
+            __syncwarp();
           };
           auto cmp = [&](int d, int t) {
             const uint32_t ud = u0 + d;
             if (t == 0) mbar_wait_timed(bar(FB_FULL + 9), ud & 1, w_full);
             mbar_wait_timed(bar(FB_STG_FULL + t), ud & 1, w_stg);
             tc_fence_after();
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t da = dS0 + (uint64_t)((2 * ks * FTC_STAGE_CHUNK + t * 128 * 16) >> 4);
-              const uint64_t db = dB0 + (uint64_t)((9 * FTC_SLOT_BYTES + 2 * ks * FTC_BCHUNK) >> 4);
-              umma_bf16(cacc[t], da, db, I96, (d | ks) != 0);
-              umma_bf16(cacc[t], da + (uint64_t)((4 * FTC_STAGE_CHUNK) >> 4), db, I64, 1);
-              umma_bf16(cacc[t], da + (uint64_t)((8 * FTC_STAGE_CHUNK) >> 4), db, I32, 1);
+            const uint32_t cacc = cacc0 + t * 96;
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t da = dS0 + (uint64_t)((2 * ks * FTC_STAGE_CHUNK + t * 128 * 16) >> 4);
+                const uint64_t db = dB0 + (uint64_t)((9 * FTC_SLOT_BYTES + 2 * ks * FTC_BCHUNK) >> 4);
+                umma_bf16(cacc, da, db, I96, (d | ks) != 0);
+                umma_bf16(cacc, da + (uint64_t)((4 * FTC_STAGE_CHUNK) >> 4), db + BH, I32H, 1);
+              }
+              umma_commit(bar(FB_STG_EMPTY + t));
+              if (t == 1) umma_commit(bar(FB_EMPTY + 9));
+              if (d == 2) umma_commit(bar(FB_CACC_FULL + t));
             }
-            umma_commit(bar(FB_STG_EMPTY + t));
-            if (t == 1) umma_commit(bar(FB_EMPTY + 9));
-            if (d == 2) umma_commit(bar(FB_CACC_FULL + t));
+            __syncwarp();
           };
           for (int d = 0; d < 3; ++d) {
             conv(d, 0);
@@ -304,7 +330,7 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
           cmp(2, 1);
         }
       }
-      if (a.dbg && blockIdx.x == 0) {
+      if (a.dbg && blockIdx.x == 0 && lane == 0) {
         a.dbg[0] = clock64() - t_begin; a.dbg[1] = w_in; a.dbg[2] = w_ar; a.dbg[3] = w_acc; a.dbg[4] = w_full; a.dbg[5] = w_stg;
         a.dbg[6] = it;
       }
@@ -314,7 +340,6 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
     const int lt = tid - 64;
     uint32_t it = 0;
     const float* prm0 = a.w + a.f[0][CF_TC_PRM];
-    const int kc0 = a.f[0][CF_TC_KC];
     for (int b = blockIdx.x; b < a.batch; b += gridDim.x, ++it) {
       const float* src = a.in + (size_t)b * Tin * FV;
       float xin[4][16];
@@ -324,39 +349,31 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
 #pragma unroll
         for (int c = 0; c < 16; ++c) xin[k][c] = (idx < FV && c < Tin) ? __ldg(src + c * FV + idx) : 0.f;
       }
-      if (it > 0) {                                         // previous sample: last convolutions and residual reads done
-        mbar_wait(bar(FB_A_FREE), (it - 1) & 1);
-        mbar_wait(bar(FB_A_RELEASE), (it - 1) & 1);
-      }
+      if (it > 0) mbar_wait(bar(FB_IN_FREE), (it - 1) & 1); // the previous sample's first layer has read the buffer
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int idx = lt + 64 * k;
         if (idx < FV) {
           const int h = idx / V, w = idx - h * V;
-          unsigned char* dst = sA + (size_t)(Q0 + h * WP + w) * 16;
-          ftc_split_store8(&xin[k][0], dst, 4 * SA);
-          ftc_split_store8(&xin[k][8], dst + SA, 4 * SA);
-          if (kc0 > 2) {                                    // Tin > 16 would need the upper chunks; zero them
-            const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            ftc_split_store8(z, dst + 2 * SA, 4 * SA);
-            ftc_split_store8(z, dst + 3 * SA, 4 * SA);
-          }
+          unsigned char* dst = ftc_smem + G::O_IN + (size_t)(Q0 + h * WP + w) * 16;
+          ftc_split_store8(&xin[k][0], dst, 2 * SA);
+          ftc_split_store8(&xin[k][8], dst + SA, 2 * SA);
         }
       }
-      float* cs = chsum_in + (it & 1) * 32;
+      float* cs = chsum_in + (it & 1) * 64;
+      float mine = 0.f;
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
-        float s = (xin[0][c] + xin[1][c]) + (xin[2][c] + xin[3][c]);
-        s = warp_sum(s);
-        if (lane == 0 && c < Tin) atomicAdd(cs + c, s);
+        const float s = warp_sum((xin[0][c] + xin[1][c]) + (xin[2][c] + xin[3][c]));
+        if (lane == c) mine = s;
       }
+      cs[(warp - 2) * 32 + lane] = mine;
       named_bar(3, 64);
       if (warp == 2) {
+        const float tot = (cs[lane] + cs[32 + lane]) * inv_fv;       // lane c holds the mean of input channel c
         float acc = __ldg(prm0 + FTC_PRM_CPB + lane);
-        for (int c = 0; c < Tin; ++c) acc = fmaf(__ldg(prm0 + FTC_PRM_WAVG + c * 32 + lane), cs[c] * inv_fv, acc);
-        cst_in[lane] = acc;
-        __syncwarp();
-        cs[lane] = 0.f;
+        for (int c = 0; c < Tin; ++c) acc = fmaf(__ldg(prm0 + FTC_PRM_WAVG + c * 32 + lane), __shfl_sync(0xffffffffu, tot, c), acc);
+        cst_in[(it & 1) * 32 + lane] = acc;
       }
       fence_proxy_async();
       mbar_arrive(bar(FB_IN_READY));
@@ -374,7 +391,7 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
     unsigned char* a_row = sA + (size_t)(Q0 + p) * 16;
     const int et = tid - 128;
     uint32_t u = 0, lv = 0, it = 0;
-    long long w_in = 0, w_accf = 0, w_stge = 0, w_cacc = 0, w_nb = 0;
+    long long w_in = 0, w_accf = 0, w_stge = 0, w_cacc = 0, w_nb = 0, c_ld = 0, c_e1 = 0, c_e2 = 0;
     const long long t_begin = clock64();
     for (int b = blockIdx.x; b < a.batch; b += gridDim.x, ++it) {
       mbar_wait_timed(bar(FB_IN_READY), it & 1, w_in);      // cst_in of this sample is visible
@@ -385,10 +402,11 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
           mbar_wait_timed(bar(FB_ACC_FULL + t), u & 1, w_accf);
           tc_fence_after();
           mbar_wait_timed(bar(FB_STG_EMPTY + t), (u & 1) ^ 1, w_stge);
+          const long long te1 = clock64();
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             float o[16];
-            ftc_load_sum(acc + half * 16, o);
+            { const long long tl = clock64(); ftc_load_sum(acc + half * 16, o); c_ld += clock64() - tl; }
 #pragma unroll
             for (int i = 0; i < 16; ++i) o[i] = prelu(o[i] + __ldg(prm + FTC_PRM_BIAS + d * 32 + half * 16 + i), slope);
             ftc_split_store8(&o[0], stage_row + (2 * half) * FTC_STAGE_CHUNK, 4 * FTC_STAGE_CHUNK);
@@ -398,6 +416,7 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
           mbar_arrive(bar(FB_ACC_EMPTY + t));
           fence_proxy_async();
           mbar_arrive(bar(FB_STG_FULL + t));
+          c_e1 += clock64() - te1;
         }
         // ---- compress epilogue: bias + average branch, caller's PReLU (+ residual) ----
         const bool last = l == L - 1;
@@ -410,13 +429,13 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) ftc_add_terms8(a_row + c * SA, 4 * SA, &xo[8 * c]);
         }
-        if (last) mbar_arrive(bar(FB_A_RELEASE));           // the loader may overwrite the map once a_free fires too
         mbar_wait_timed(bar(FB_CACC_FULL + t), lv & 1, w_cacc);
         ++lv;
         tc_fence_after();
         { const long long tb = clock64(); named_bar(1, 256); w_nb += clock64() - tb; }   // this layer's cst is in place
-        const float* cst = l == 0 ? cst_in : cstv + (l & 1) * 32;
-        float* csn = chsum + ((l + 1) & 1) * 32;
+        const float* cst = l == 0 ? cst_in + (it & 1) * 32 : cstv + (l & 1) * 32;
+        float* csn = chsum + ((l + 1) & 1) * 256;
+        const long long te2 = clock64();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           float o[16];
@@ -424,38 +443,41 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float val = prelu(o[i] + cst[half * 16 + i], oa) + xo[half * 16 + i];
-            o[i] = valid ? val : 0.f;
+            xo[half * 16 + i] = valid ? val : 0.f;          // xo now holds the layer's output at this position
           }
-          if (last) {
-            if (valid) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (half * 16 + i < To) scr[p * To + half * 16 + i] = o[i];
-            }
-          } else {
-            ftc_split_store8(&o[0], a_row + (2 * half) * SA, 4 * SA);
-            ftc_split_store8(&o[8], a_row + (2 * half + 1) * SA, 4 * SA);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float s = warp_sum(o[i]);
-              if (lane == 0 && half * 16 + i < To) atomicAdd(csn + half * 16 + i, s);
-            }
+          if (!last) {
+            ftc_split_store8(&xo[half * 16], a_row + (2 * half) * SA, 4 * SA);
+            ftc_split_store8(&xo[half * 16 + 8], a_row + (2 * half + 1) * SA, 4 * SA);
           }
         }
         tc_fence_before();
         if (!last) {
           fence_proxy_async();
-          mbar_arrive(bar(FB_A_READY));
+          mbar_arrive(bar(FB_A_READY));                     // the next layer's convolutions may start
+          c_e2 += clock64() - te2;
+          float mine = 0.f;                                 // channel sums for its average branch, off the critical path
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float sm = warp_sum(xo[i]);
+            if (lane == i) mine = sm;
+          }
+          csn[(warp - 4) * 32 + lane] = mine;
+        } else if (valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < To) scr[p * To + i] = xo[i];
         }
         named_bar(1, 256);                                  // channel sums complete / final map complete
         if (!last) {
           if (warp == 4) {
             const float* prn = a.w + a.f[l + 1][CF_TC_PRM];
+            float tot = 0.f;
+#pragma unroll
+            for (int wq = 0; wq < 8; ++wq) tot += csn[wq * 32 + lane];
+            tot *= inv_fv;                                  // lane c holds the mean of channel c
             float accv = __ldg(prn + FTC_PRM_CPB + lane);
-            for (int c = 0; c < To; ++c) accv = fmaf(__ldg(prn + FTC_PRM_WAVG + c * 32 + lane), csn[c] * inv_fv, accv);
+            for (int c = 0; c < To; ++c) accv = fmaf(__ldg(prn + FTC_PRM_WAVG + c * 32 + lane), __shfl_sync(0xffffffffu, tot, c), accv);
             cstv[((l + 1) & 1) * 32 + lane] = accv;
-            __syncwarp();
-            csn[lane] = 0.f;
           }
         } else {
           // dim_conversor on (F channels, To, V): conv1x1 F->3, BN, PReLU, conv1x1 3->3, PReLU(3)  (:541-545)
@@ -495,6 +517,7 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
     if (a.dbg && blockIdx.x == 0 && (tid == 128 || tid == 256)) {
       long long* o = a.dbg + (tid == 128 ? 8 : 16);
       o[0] = clock64() - t_begin; o[1] = w_in; o[2] = w_accf; o[3] = w_stge; o[4] = w_cacc; o[5] = w_nb;
+      if (tid == 128) { a.dbg[24] = c_ld; a.dbg[25] = c_e1; a.dbg[26] = c_e2; }
     }
   }
   __syncwarp();

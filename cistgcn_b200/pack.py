@@ -268,16 +268,22 @@ def bf16_split3(w: torch.Tensor):
     return b1, b2, b3
 
 
+TC_FP16_MAX = 6.0e4
+
+
 def tc_slice(Wm: torch.Tensor, kc: int) -> torch.Tensor:
     """(cout <= 32, cin <= 8*kc) matrix -> int32 words of the K-major tcgen05 operand image
-    [kc k-chunks][96 rows = 32*term + cout][8 bf16] (csrc/fpn_tc.cuh)."""
+    [kc k-chunks][128 rows][8 x 16 bit] (csrc/fpn_tc.cuh): rows 32*term + cout hold the three bf16 terms of
+    the weights (term = 0, 1, 2), rows 96 + cout their fp16 rounding (the partner of the activations' fp16
+    remainder)."""
     co, ci = Wm.shape
     assert co <= 32 and ci <= 8 * kc
     full = torch.zeros(32, kc * 8, dtype=torch.float64)
     full[:co, :ci] = Wm
-    img = torch.zeros(kc, 96, 8, dtype=torch.bfloat16)
+    img = torch.zeros(kc, 128, 8, dtype=torch.int16)
     for j, part in enumerate(bf16_split3(full)):
-        img[:, 32 * j: 32 * j + 32, :] = part.reshape(32, kc, 8).permute(1, 0, 2)
+        img[:, 32 * j: 32 * j + 32, :] = part.view(torch.int16).reshape(32, kc, 8).permute(1, 0, 2)
+    img[:, 96:, :] = full.to(torch.float32).to(torch.float16).view(torch.int16).reshape(32, kc, 8).permute(1, 0, 2)
     return img.contiguous().view(torch.int32).reshape(-1)
 
 
@@ -288,6 +294,9 @@ def _pack_fpn_tc(blob: _Blob, sd, p: str, prelu_key: str, cin: int, cout: int, d
     """Tensor-core image of one FPN layer (only when it fits the kernel's 32-wide tiles)."""
     if cout > 32 or cin > 32:
         return
+    folded = [_fold(sd, f"{p}.block{i}.1")[0][:, None, None, None] * _w(sd, f"{p}.block{i}.0.weight") for i in (1, 2, 3)]
+    if max(float(t.abs().max()) for t in folded + [_w(sd, f"{p}.compress.weight")]) >= TC_FP16_MAX:
+        return      # the fp16 copy of the weights would overflow: this layer stays on the FP32-FMA kernel
     kc = pad_up(cin, 16) // 8
     words, prm = [], torch.zeros(TC_PRM_FLOATS, dtype=torch.float64)
     Wc = _w(sd, f"{p}.compress.weight").reshape(cout, 3 * cout + cin)

@@ -255,6 +255,25 @@ def build_features(x: torch.Tensor) -> torch.Tensor:
     return torch.cat((x, acc, vel, speed), dim=-1).permute(0, 3, 1, 2)
 
 
+def fpn_stack(c: _Ctx, x5: torch.Tensor, cfg: OracleConfig) -> torch.Tensor:
+    """CISTGCN.py:584-589: the FPN layers with the caller's PReLU / residual, dim_conversor, cumsum.
+    x5 (B, input_n, 10, V) -> x7 (B, output_n, V, 3)."""
+    x6 = _prelu(c, fpn(c, x5, "txcnns.0", cfg.txc_kernel_size), "prelus.0")                 # :584
+    for i in range(1, cfg.n_txcnn_layers):                                                  # :585-586
+        x6 = _prelu(c, fpn(c, x6, f"txcnns.{i}", cfg.txc_kernel_size), f"prelus.{i}") + x6
+    c.tap("x6", x6)
+    d = x6.permute(0, 2, 1, 3)                                                              # :588, 541-545
+    d = _prelu(c, _bn(c, _conv(c, d, "dim_conversor.0"), "dim_conversor.1"), "dim_conversor.2")
+    d = _prelu(c, _conv(c, d, "dim_conversor.3"), "dim_conversor.4")
+    return d.permute(0, 2, 3, 1).cumsum(1)                                                  # :588-589
+
+
+def fpn_stack_eval(sd: Dict[str, torch.Tensor], cfg: OracleConfig, x5: torch.Tensor) -> torch.Tensor:
+    """Eval-mode fpn_stack on a raw state_dict (entry point for the FPN-only parity tests)."""
+    with torch.no_grad():
+        return fpn_stack(_Ctx(sd, False, None, None), x5, cfg)
+
+
 def forward(sd: Dict[str, torch.Tensor], cfg: OracleConfig, x: torch.Tensor, *, train: bool = False,
             taps: Optional[dict] = None, bn_updates: Optional[dict] = None,
             interpretable_in: Optional[List[bool]] = None,
@@ -269,14 +288,7 @@ def forward(sd: Dict[str, torch.Tensor], cfg: OracleConfig, x: torch.Tensor, *, 
         h = dstd_gc(c, h, f"st_gcnns.{i}", itp)
         c.tap(f"st_gcnns.{i}.out", h)
     x5 = h.permute(0, 2, 1, 3)                                                              # :582
-    x6 = _prelu(c, fpn(c, x5, "txcnns.0", cfg.txc_kernel_size), "prelus.0")                 # :584
-    for i in range(1, cfg.n_txcnn_layers):                                                  # :585-586
-        x6 = _prelu(c, fpn(c, x6, f"txcnns.{i}", cfg.txc_kernel_size), f"prelus.{i}") + x6
-    c.tap("x6", x6)
-    d = x6.permute(0, 2, 1, 3)                                                              # :588, 541-545
-    d = _prelu(c, _bn(c, _conv(c, d, "dim_conversor.0"), "dim_conversor.1"), "dim_conversor.2")
-    d = _prelu(c, _conv(c, d, "dim_conversor.3"), "dim_conversor.4")
-    x7 = d.permute(0, 2, 3, 1).cumsum(1)                                                    # :588-589
+    x7 = fpn_stack(c, x5, cfg)                                                              # :584-589
     c.tap("x7", x7)
     act = context_layer(c, x7.reshape(b, 1, cfg.output_n, joints * 3), "context_layer",
                         cfg.output_n, joints)                                               # :591

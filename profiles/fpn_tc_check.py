@@ -66,3 +66,4 @@ print(f"MMA issuer, {n} samples: total {c[0] / n:.0f} cyc/sample; waits: input {
 for name, o in (("epilogue tile 0", 8), ("epilogue tile 1", 16)):
     print(f"{name}: total {c[o] / n:.0f} cyc/sample; waits: input {c[o + 1] / n:.0f}, conv accumulator {c[o + 2] / n:.0f}, "
           f"staging free {c[o + 3] / n:.0f}, compress accumulator {c[o + 4] / n:.0f}, group barrier {c[o + 5] / n:.0f}")
+print(f"epilogue thread 128: branch epilogues {c[25] / n / 12:.0f} cyc each (TMEM loads {c[24] / n / 12:.0f}), compress epilogue to map-ready {c[26] / n / 3:.0f} cyc each")
