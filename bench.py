@@ -44,6 +44,25 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_tensor_peak():
+    """Dense bf16 TFLOP/s, sustained figure (the FPN kernel is timed inside a long step)."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        for k in ("bf16_tflops_sustained", "bf16_tflops"):
+            if k in d:
+                return float(d[k]), f"measured {k} (MEASURED_PEAKS.json)"
+    return 1400.0, "fallback sustained (B200_PROFILING.md)"
+
+
+def fpn_tc_issued_flops_per_seq():
+    """Tensor FLOPs the tcgen05 FPN kernel ISSUES per sequence (csrc/fpn_tc.cuh): per k-step and 128-position tile one
+    M128 N96 K16 bf16 MMA + one M128 N32 K16 fp16 MMA; 2 tiles; layer 0 has 1 k-step per tap, layers 1-3 have 2;
+    27 taps + 3 compress slices (2 k-steps) per layer."""
+    ksteps_tiles = 2 * ((27 * 1 + 3 * 2) + 3 * (27 * 2 + 3 * 2))
+    return ksteps_tiles * 2.0 * 128 * (96 + 32) * 16
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons through `nvidia-smi -lms 200` while the timed region runs."""
 
@@ -167,6 +186,7 @@ def run_native(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _cabi.lib()                                   # fails loudly if the extension is missing
+    _cabi.check(lib.cistgcn_set_fpn_path(int(os.environ.get("CISTGCN_BENCH_FPN_PATH", "0"))), "cistgcn_set_fpn_path", lib)
     model = _make_model(E, V).to(dev)
     cfg = O.OracleConfig(joints=V, input_gcn=[E] * 4)
     # every rank owns its own shard of the global batch (different seed per rank); no data-path collective
@@ -257,7 +277,8 @@ def run_native(args, rank, world, local_rank):
 
     hbm_peak, peak_src = measured_peaks()
     launches = sum(int(v) for v in kln)                     # launches of OUR kernels inside the timed region
-    names = ["dstd_block_kernel", "fpn_chain_kernel", "tail_kernel", "mpjpe_kernel"]
+    fpn_tc = V in (22, 18) and os.environ.get("CISTGCN_BENCH_FPN_PATH", "0") == "0"
+    names = ["dstd_block_kernel", "fpn_tc_kernel" if fpn_tc else "fpn_chain_kernel", "tail_kernel", "mpjpe_kernel"]
     kshare = {names[i]: {"ms_per_step": kms[i] / args.steps, "launches_per_step": int(kln[i]) / args.steps}
               for i in range(4) if kln[i]}
     dom = max(range(4), key=lambda i: kms[i])
@@ -294,6 +315,19 @@ def run_native(args, rank, world, local_rank):
                     "whole_forward": {"achieved": fl_total * (value / world) / 1e12,
                                       "frac": fl_total * (value / world) / 1e12 / FP32_FMA_PEAK_TFLOPS,
                                       "hbm_frac_survey_bytes": bytes_per_seq(V, E) * (value / world) / 1e9 / hbm_peak}}
+    roofline_tensor = None
+    if fpn_tc and kln[1]:
+        tpeak, tsrc = measured_tensor_peak()
+        fpn_s = kms[1] / 1e3
+        alg = FPN_FLOPS_PER_SEQ[V] * seqs / fpn_s / 1e12
+        issued = fpn_tc_issued_flops_per_seq() * seqs / fpn_s / 1e12
+        roofline_tensor = {"bound": "tensor", "kernel": "fpn_tc_kernel", "achieved": alg, "issued": issued, "peak": tpeak,
+                           "unit": "TFLOP/s", "frac": alg / tpeak, "frac_issued": issued / tpeak, "peak_source": tsrc,
+                           "share_of_step": kms[1] / total_kms if total_kms else None,
+                           "launch_ms": kms[1] / max(int(kln[1]), 1),
+                           "note": "achieved = the reference's algorithmic FPN FLOPs (SURVEY.md 8d) / kernel time; issued = tcgen05 "
+                                   "FLOPs incl. channel padding to 32 and the split-operand products that buy fp32 accuracy "
+                                   "(x1*[w1|w2|w3] + x2*wh); the pipe is fed from shared memory at N <= 96, see DESIGN.md"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -310,6 +344,7 @@ def run_native(args, rank, world, local_rank):
         "kernels": kshare,
         "roofline": roofline,
         "roofline_fp32_fma": roofline_fma,
+        "roofline_tensor": roofline_tensor,
         "clocks": clocks,
     }
     if world == 1:
