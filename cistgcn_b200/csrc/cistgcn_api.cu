@@ -131,7 +131,7 @@ int g_fpn_path = 0;   // 0: tensor-core kernel whenever the shape fits, 1: FP32-
 // tcgen05 kernel (fpn_tc.cuh): 32-wide channel tiles, two 128-position tiles, weights packed with CF_TC_*
 bool fpn_tc_supported(const int32_t* fpn_descs, int n_fpn, const int32_t* tail_desc) {
   const int To = tail_desc[CT_TOUT], V = tail_desc[CT_V], Tin = tail_desc[CT_TIN];
-  if (To > 25 || Tin > 16 || tail_desc[CT_F] != cg::FTC_F || (V != 22 && V != 18)) return false;
+  if (To > 25 || Tin > 16 || tail_desc[CT_F] != cg::FTC_F || (V != 22 && V != 18) || n_fpn > 4) return false;
   for (int l = 0; l < n_fpn; ++l) {
     const int32_t* f = fpn_descs + l * CF_COUNT;
     if (f[CF_TC_KC] != (l == 0 ? 2 : 4) || f[CF_TC_W] <= 0 || f[CF_TC_PRM] <= 0) return false;

@@ -80,7 +80,8 @@ struct FtcGeom {
   static constexpr int O_Y6 = O_SCR + 256 * 25 * 4;                  // 256 positions x (To <= 25) channels
   static constexpr int O_MISC = O_Y6 + (25 * V * 3 * 4 + 15) / 16 * 16;
   static constexpr int O_BAR = O_MISC + 768 * 4;                     // channel-sum partials and average-branch constants
-  static constexpr int SMEM_BYTES = O_BAR + FB_COUNT * 8 + 16;
+  static constexpr int O_PRM = O_BAR + FB_COUNT * 8 + 16;            // per-layer epilogue constants + dim_conversor weights
+  static constexpr int SMEM_BYTES = O_PRM + (4 * 136 + 120) * 4;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared-memory plan exceeds the 227 KB opt-in limit");
   static_assert(10 * WP <= 256, "map does not fit two 128-position tiles");
 };
@@ -203,6 +204,9 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
   float* cst_in = misc + 576;       // [2][32] same for layer 0, per sample parity (the loader runs a sample ahead)
   float* chsum_in = misc + 640;     // [2][2 warps][32] loader partials, per sample parity
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ftc_smem + G::O_BAR + FB_COUNT * 8);
+  // epilogue constants in shared memory: with 224 KB of it carved out the L1 is tiny and an __ldg is an L2 round trip
+  float* sprm = reinterpret_cast<float*>(ftc_smem + G::O_PRM);   // [layer][136]: bias[3][32], slope[3], out slope, compress bias[32]
+  float* sdc = sprm + 4 * 136;                                   // dim_conversor: w0[F][8] @0, b0[3] @80, a0 @84, w3[3][8] @88, a3[3] @112
   auto bar = [&](int i) { return sbase + G::O_BAR + 8 * i; };
 
   if (tid == 0) {
@@ -222,6 +226,19 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
   // zero the map (padding rows / columns / channels stay zero for the kernel's lifetime) and the small state
   for (int i = tid; i < 12 * SA / 16; i += FTC_NT) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < 768; i += FTC_NT) misc[i] = 0.f;
+  for (int i = tid; i < L * 136; i += FTC_NT) {
+    const int l = i / 136, j = i - l * 136;
+    sprm[i] = j < FTC_PRM_WAVG ? __ldg(a.w + a.f[l][CF_TC_PRM] + j) : 0.f;
+  }
+  for (int i = tid; i < 120; i += FTC_NT) {
+    float v = 0.f;
+    if (i < F * 8) v = __ldg(a.w + a.t[CT_DC0_WT] + i);
+    else if (i >= 80 && i < 83) v = __ldg(a.w + a.t[CT_DC0_B] + i - 80);
+    else if (i == 84) v = __ldg(a.w + a.t[CT_DC0_A]);
+    else if (i >= 88 && i < 112) v = __ldg(a.w + a.t[CT_DC3_WT] + i - 88);
+    else if (i >= 112 && i < 115) v = __ldg(a.w + a.t[CT_DC3_A] + i - 112);
+    sdc[i] = v;
+  }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)FTC_TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -396,9 +413,9 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
     for (int b = blockIdx.x; b < a.batch; b += gridDim.x, ++it) {
       mbar_wait_timed(bar(FB_IN_READY), it & 1, w_in);      // cst_in of this sample is visible
       for (int l = 0; l < L; ++l) {
-        const float* prm = a.w + a.f[l][CF_TC_PRM];
+        const float* prm = sprm + l * 136;
         for (int d = 0; d < 3; ++d, ++u) {
-          const float slope = __ldg(prm + FTC_PRM_SLOPE + d);
+          const float slope = prm[FTC_PRM_SLOPE + d];
           mbar_wait_timed(bar(FB_ACC_FULL + t), u & 1, w_accf);
           tc_fence_after();
           mbar_wait_timed(bar(FB_STG_EMPTY + t), (u & 1) ^ 1, w_stge);
@@ -408,7 +425,7 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
             float o[16];
             { const long long tl = clock64(); ftc_load_sum(acc + half * 16, o); c_ld += clock64() - tl; }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = prelu(o[i] + __ldg(prm + FTC_PRM_BIAS + d * 32 + half * 16 + i), slope);
+            for (int i = 0; i < 16; ++i) o[i] = prelu(o[i] + prm[FTC_PRM_BIAS + d * 32 + half * 16 + i], slope);
             ftc_split_store8(&o[0], stage_row + (2 * half) * FTC_STAGE_CHUNK, 4 * FTC_STAGE_CHUNK);
             ftc_split_store8(&o[8], stage_row + (2 * half + 1) * FTC_STAGE_CHUNK, 4 * FTC_STAGE_CHUNK);
           }
@@ -421,7 +438,7 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
         // ---- compress epilogue: bias + average branch, caller's PReLU (+ residual) ----
         const bool last = l == L - 1;
         const bool resid = a.f[l][CF_RESID] != 0;
-        const float oa = __ldg(prm + FTC_PRM_OUT_A);
+        const float oa = prm[FTC_PRM_OUT_A];
         float xo[32];                                       // residual: this layer's input at this position
 #pragma unroll
         for (int i = 0; i < 32; ++i) xo[i] = 0.f;
@@ -481,19 +498,16 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
           }
         } else {
           // dim_conversor on (F channels, To, V): conv1x1 F->3, BN, PReLU, conv1x1 3->3, PReLU(3)  (:541-545)
-          const float* W = a.w;
-          const float* w0 = W + a.t[CT_DC0_WT];
-          const float* b0 = W + a.t[CT_DC0_B];
-          const float a0 = __ldg(W + a.t[CT_DC0_A]);
-          const float* w3 = W + a.t[CT_DC3_WT];
-          const float* a3 = W + a.t[CT_DC3_A];
+          const float* w0 = sdc;
+          const float a0 = sdc[84];
+          const float* w3 = sdc + 88;
           for (int i = et; i < To * V; i += 256) {
             const int fr = i / V, v = i - fr * V;
-            float y[3] = {__ldg(b0), __ldg(b0 + 1), __ldg(b0 + 2)};
+            float y[3] = {sdc[80], sdc[81], sdc[82]};
             for (int c = 0; c < F; ++c) {
               const float xv = scr[(c * WP + v) * To + fr];
 #pragma unroll
-              for (int k = 0; k < 3; ++k) y[k] = fmaf(__ldg(w0 + c * 8 + k), xv, y[k]);
+              for (int k = 0; k < 3; ++k) y[k] = fmaf(w0[c * 8 + k], xv, y[k]);
             }
 #pragma unroll
             for (int k = 0; k < 3; ++k) y[k] = prelu(y[k], a0);
@@ -501,8 +515,8 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
             for (int k = 0; k < 3; ++k) {
               float z = 0.f;
 #pragma unroll
-              for (int j = 0; j < 3; ++j) z = fmaf(__ldg(w3 + j * 8 + k), y[j], z);
-              y6[i * 3 + k] = prelu(z, __ldg(a3 + k));
+              for (int j = 0; j < 3; ++j) z = fmaf(w3[j * 8 + k], y[j], z);
+              y6[i * 3 + k] = prelu(z, sdc[112 + k]);
             }
           }
           named_bar(1, 256);
