@@ -181,6 +181,10 @@ def run_native(args, rank, world, local_rank):
     from oracle import cistgcn_oracle as O
 
     E, V, B = args.embed, args.joints, args.batch
+    # library chatter on stdout (e.g. the "NCCL version" banner) goes to stderr: stdout carries the ONE JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
@@ -349,6 +353,8 @@ def run_native(args, rank, world, local_rank):
     }
     if world == 1:
         line["cpu_baseline"] = cpu_baseline(E, V, args.cpu_budget)
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
 
 
