@@ -36,7 +36,7 @@ class Taps(ctypes.Structure):
 EXPORTS = ("cistgcn_last_error", "cistgcn_abi_version", "cistgcn_workspace_bytes", "cistgcn_forward_f32",
            "cistgcn_dstd_block_f32", "cistgcn_fpn_chain_f32", "cistgcn_tail_f32", "cistgcn_mpjpe_f32",
            "cistgcn_profile_enable", "cistgcn_profile_read", "cistgcn_debug_phase_clocks", "cistgcn_debug_stamp_iteration",
-           "cistgcn_set_fpn_path")
+           "cistgcn_set_fpn_path", "cistgcn_set_dstd_path")
 
 
 def bind(path: str) -> ctypes.CDLL:
@@ -68,6 +68,8 @@ def bind(path: str) -> ctypes.CDLL:
     L.cistgcn_debug_stamp_iteration.argtypes = [ctypes.c_int]
     L.cistgcn_set_fpn_path.restype = ctypes.c_int
     L.cistgcn_set_fpn_path.argtypes = [ctypes.c_int]
+    L.cistgcn_set_dstd_path.restype = ctypes.c_int
+    L.cistgcn_set_dstd_path.argtypes = [ctypes.c_int]
     if L.cistgcn_abi_version() != ABI_VERSION:
         raise RuntimeError(f"cistgcn_b200: {path} has ABI {L.cistgcn_abi_version()}, header says {ABI_VERSION}; "
                            "rebuild with `python -c 'import __graft_entry__ as g; g.build()'`")

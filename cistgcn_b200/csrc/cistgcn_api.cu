@@ -83,6 +83,8 @@ struct ProfScope { ProfScope(int, void*) {} };
 long long* g_phase_clocks = nullptr;   // debug hook, see cistgcn_debug_phase_clocks
 int g_stamp_iter = 0;
 
+int g_dstd_path = 0;  // 0: FP32-FMA channel mixes (default, faster at K <= 64), 1: tcgen05 channel mixes where the plan fits
+
 int dstd_done(int e) {
   if (e) return fail(-4, "dstd_block_kernel launch: %s", cg::launch_error_string(e));
   return 0;
@@ -109,11 +111,13 @@ int launch_dstd(const int32_t* desc, const float* weights, const float* in, floa
   int nt = cg::DSTD_NT_NARROW;
   if (!cg::dstd_plan(a, nt, cg::DSTD_SMEM_NARROW_BYTES / 4)) {
     nt = cg::DSTD_NT_WIDE;
-    if (!cg::dstd_plan(a, nt, kMaxSmemBytes / 4) || (size_t)a.smem_floats * 4 > (size_t)kMaxSmemBytes)
+    const bool tc_ok = g_dstd_path == 1 && T == 10 && (V == 22 || V == 18);     // shapes with a tensor-core instantiation
+    if (!cg::dstd_plan(a, nt, kMaxSmemBytes / 4, tc_ok) || (size_t)a.smem_floats * 4 > (size_t)kMaxSmemBytes)
       return fail(-2, "DSTD-GC block (%d->%d, T=%d, V=%d) needs %zu B of shared memory (> %d)", Ci, Co, T, V,
                   (size_t)a.smem_floats * 4, kMaxSmemBytes);
   }
   ProfScope prof(KIND_DSTD, stream);
+  if (nt == 512 && a.tc) return dstd_done(V == 22 ? cg::launch_dstd_10_22_512_tc(a, stream) : cg::launch_dstd_10_18_512_tc(a, stream));
 #define CG_TRY_DSTD(TT, VV) \
   if (T == TT && V == VV) return dstd_done(nt == 256 ? cg::launch_dstd_##TT##_##VV##_256(a, stream) : cg::launch_dstd_##TT##_##VV##_512(a, stream));
   CG_TRY_DSTD(10, 22)
@@ -268,6 +272,12 @@ int cistgcn_debug_stamp_iteration(int iteration) {
 int cistgcn_set_fpn_path(int path) {
   if (path != 0 && path != 1) return fail(-1, "fpn path %d unknown (0 tensor-core when supported, 1 FP32-FMA)", path);
   g_fpn_path = path;
+  return 0;
+}
+
+int cistgcn_set_dstd_path(int path) {
+  if (path != 0 && path != 1) return fail(-1, "dstd path %d unknown (0 FP32-FMA channel mixes, 1 tensor-core channel mixes when the plan fits)", path);
+  g_dstd_path = path;
   return 0;
 }
 

@@ -23,6 +23,7 @@
 #pragma once
 #include "../../include/cistgcn_b200.h"
 #include "simt.h"
+#include "umma.cuh"
 
 namespace cg {
 
@@ -46,6 +47,8 @@ struct DstdArgs {
   int batch;
   int o_xn, o_ab, tile, o_adj, o_sm, o_ring, ring_floats, smem_floats;
   int scratch_floats;    // capacity of the split-K partial scratch (the adjacency region)
+  // tensor-core channel mixes (tc_gemm): staging operand [2 terms][tc_kc chunks][256 positions][16 B] + mbarrier / TMEM slot
+  int tc, o_stage, tc_kc, o_tcmisc, o_img;     // o_img: one weight-image buffer, refilled by cp.async.bulk between uses
   long long* phase_clocks;   // optional debug: first CTA / thread 0 stamps clock64() at phase boundaries
   int stamp_iter;            // ... of its stamp_iter-th sample (0 = first: cold caches)
 };
@@ -60,7 +63,7 @@ constexpr int KSPLIT_MAX = 8;   // split-K fan-out cap of the narrow GEMMs (also
 
 // Host: sizes of every weight field, the shared-memory layout and the residency plan.
 // Returns false if even the mandatory small vectors do not fit.
-inline bool dstd_plan(DstdArgs& a, int nt, int max_smem_floats) {
+inline bool dstd_plan(DstdArgs& a, int nt, int max_smem_floats, bool tc_allowed = true) {
   const int* d = a.d;
   const int Ci = d[CB_CI], Co = d[CB_CO], T = d[CB_T], V = d[CB_V], Ch = d[CB_CH], Cg = d[CB_CG], Hs = d[CB_HS];
   const bool has_res = d[CB_HAS_RES] != 0, interp = d[CB_INTERP] != 0;
@@ -98,7 +101,8 @@ inline bool dstd_plan(DstdArgs& a, int nt, int max_smem_floats) {
   // split-K partial sums of the narrow GEMMs (<= KSPLIT_MAX copies of an M x N output) and of the matvecs
   // (nw/2 copies of 2 x Co) share the adjacency region with the row statistics
   const int scratch = imax(4 * imax(2 * Cg * V, imax(Ch * V, Ch * T)), nw * Co);
-  const int adj = imax(imax(pad4i(big), pad4i(T * T * (V | 1))), imax(pad4i(2 * Ci * T + 2 * Ci), pad4i(scratch)));
+  const int adj0 = imax(imax(pad4i(big), pad4i(T * T * (V | 1))), imax(pad4i(2 * Ci * T + 2 * Ci), pad4i(scratch)));
+  int adj = adj0;
   a.o_sm = a.o_adj + adj;
   a.scratch_floats = adj;
   const int sm = pad4i(2 + 2 * T) + imax(pad4i(2 * Cg * V), pad4i(2 * Ch * V) + pad4i(2 * Ch * T)) + 3 * pad4i(2 * Co) +
@@ -115,16 +119,53 @@ inline bool dstd_plan(DstdArgs& a, int nt, int max_smem_floats) {
                           CB_TC3_WT_S, CB_TC3_WT_T, CB_JC3_WT_S, CB_JC3_WT_T};
   // operands read straight from L2 with deep load batches when not resident (gate conv, gate MLPs)
   const int l2_ops[] = {CB_M4_WT, CB_M0_WT, CB_G0_WT, CB_G4_WT};
+  // tensor-core images of the channel mixes (512-thread CTAs only: one CTA per SM owns the SM's tensor memory)
+  const int tc_fields[] = {CB_TC_A0, CB_TC_TCN_S, CB_TC_TCN_T, CB_TC_CP, CB_TC_RS};
+  const int kc_a0 = ((Ci + 15) / 16) * 2;                        // k-chunks of one row block of Ci / Co channels
+  const int kc_co = ((Co + 15) / 16) * 2;
+  const int kc_tcn = has_res ? 2 * kc_a0 : kc_a0;
+  const int kc_cp = 2 * kc_co;
+  const int np_a0 = (4 * Ch + 15) / 16 * 16, np_co = (Co + 15) / 16 * 16;
+  bool want_tc = false;
+#ifndef CISTGCN_EMU
+  want_tc = nt == 512 && tc_allowed && d[CB_TC_CP] > 0 && d[CB_TC_TCN_S] > 0 && d[CB_TC_TCN_T] > 0 && TV <= 256 &&
+            (!interp || d[CB_TC_A0] > 0) && (!has_res || d[CB_TC_RS] > 0) && np_a0 <= 64 && np_co <= 64;
+#endif
   bool ok = true;
   int cur = 0;
+  for (int try_tc = want_tc ? 1 : 0; try_tc >= 0; --try_tc) {
+    for (int f : tc_fields) z[f] = 0;
+    a.tc = try_tc;
+    a.tc_kc = 0;
+    if (try_tc) {
+      if (interp) z[CB_TC_A0] = kc_a0 * 4 * np_a0 * 4;
+      z[CB_TC_TCN_S] = z[CB_TC_TCN_T] = kc_tcn * 4 * np_co * 4;
+      z[CB_TC_CP] = kc_cp * 4 * np_co * 4;
+      if (has_res) z[CB_TC_RS] = kc_a0 * 4 * np_co * 4;
+      a.tc_kc = imax(kc_a0, kc_co);                                // the staging operand holds one row block at a time
+    }
+    // the staging operand aliases the adjacency region (dead during every channel mix), which grows to hold it
+    adj = try_tc ? imax(adj0, 2 * a.tc_kc * 256 * 4) : adj0;
+    a.o_stage = a.o_adj;
+    a.o_sm = a.o_adj + adj;
+    a.scratch_floats = adj;
+    a.o_ring = a.o_sm + sm;
   for (int with_ring = 0; with_ring < 2; ++with_ring) {          // first try: everything GEMM-side resident, no ring
     for (int f = 0; f < CB_COUNT; ++f) a.res[f] = -1;
     ok = true;
     const int budget = max_smem_floats - a.o_ring;
     a.ring_floats = with_ring ? imax(widest, budget >= 24576 ? 2048 : (budget >= 8192 ? 1024 : 512)) : 0;
     cur = a.o_ring + RING_SLOTS * a.ring_floats;
+    if (try_tc) {
+      a.o_tcmisc = cur; cur += 8;
+      cur = (cur + 31) & ~31;
+      int img = 0;
+      for (int f : tc_fields) img = imax(img, a.wsz[f]);
+      a.o_img = cur; cur += img;                                   // images stream from L2 into this one buffer
+    }
     auto take = [&](int f, bool mandatory) {
       if (a.wsz[f] == 0 || a.res[f] >= 0) return true;
+      if (try_tc && (f == CB_A0_WT || f == CB_TCN_WT_S || f == CB_TCN_WT_T || f == CB_CP_WT || f == CB_RS_WT)) return true;
       if (cur + a.wsz[f] <= max_smem_floats) { a.res[f] = cur; cur += a.wsz[f]; return true; }
       if (mandatory) ok = false;
       return false;
@@ -136,6 +177,9 @@ inline bool dstd_plan(DstdArgs& a, int nt, int max_smem_floats) {
     for (int f : l2_ops) take(f, false);
     break;
   }
+    if (ok && cur <= max_smem_floats) break;                     // else: plan again without the tensor-core path
+  }
+  if (a.tc && cur < 30 * 1024) cur = 30 * 1024;                  // > half an SM: the CTA must own all 512 TMEM columns
   a.smem_floats = cur;
   return ok && cur <= max_smem_floats;
 }
@@ -569,7 +613,146 @@ CG_DEV void gcn_time(const float* XN, const float* adj, float* G, int C) {
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int T, int V, int NT>
+#ifndef CISTGCN_EMU
+// ---------------------------------------------------------------------------------------------
+// Tensor-core channel mix (512-thread CTAs): out(m, p) = sum_k W[m][k] * X[k][p] over the TV positions of the
+// sample, as tcgen05 MMAs with M = 128 positions (two tiles), N = channels, accumulators in tensor memory.
+//   1. every thread converts its share of the fp32 activation rows (X1: K1 rows, X2: K2 rows, row stride TV) into
+//      the staging operand [term][k-chunk][position][8 x 16 bit]: term 0 = bf16(x), term 1 = fp16(x - bf16(x));
+//   2. one elected lane of warp 0 issues, per tile and k-step, x_bf16 * [w1|w2|w3] (N = 3*Np) and x_fp16 * w_fp16
+//      (N = Np, accumulated into the first Np columns) against the resident weight image (pack.py tc_image);
+//   3. after the commit's mbarrier fires, the 16 warps read their TMEM lane quadrant (thread = position, 16 channels
+//      per tcgen05.ld) and hand (first channel, position, 16 values) to the epilogue.
+// Same split scheme and accuracy as the FPN kernel (fpn_tc.cuh): ~1e-6 relative.
+// ---------------------------------------------------------------------------------------------
+struct TcState {
+  uint32_t tmem;          // TMEM base (512 columns)
+  uint32_t bar;           // mbarrier: MMA completion (shared address)
+  uint32_t parity;        // phase parity of the next wait on it
+  uint32_t img_bar;       // mbarrier: weight image landed (cp.async.bulk complete_tx)
+  uint32_t img_parity;
+  unsigned char* stage;   // staging operand (aliases the adjacency region)
+  const float* img;       // the one weight-image buffer
+  int kc_cap;             // chunks per term the staging buffer holds (term stride = kc_cap * 4096 B)
+  long long* dbg;         // optional cycle counters of thread 0 (cistgcn_debug_phase_clocks): conversion, MMA wait, epilogue, calls
+};
+
+// Thread 0: start the bulk copy of the next weight image (the previous user's MMAs have completed).
+CG_DEV void tc_prefetch(const TcState& tc, const float* gsrc, int floats) {
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(tc.img_bar, (uint32_t)floats * 4u);
+    bulk_g2s(smem_u32(tc.img), gsrc, (uint32_t)floats * 4u, tc.img_bar);
+  }
+}
+
+// Operand conversion and MMA issue are shared, non-inlined routines and the epilogue walks its channels four at a
+// time in a rolled loop: the fused kernel is far larger than the instruction cache, so straight-line code that runs
+// once per phase costs more in instruction fetch than it saves in issue slots.
+template <int TV, int NT>
+__device__ __noinline__ void tc_convert(unsigned char* stage, int term_stride, const float* X, int K) {
+  const int kc = ((K + 15) / 16) * 2;
+  for (int item = threadIdx.x; item < kc * TV; item += NT) {       // position fastest: conflict-free loads, 16-byte stores
+    const int c = item / TV, p = item - c * TV;
+    float x[8];
+    const int k0 = c * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = (k0 + e < K) ? X[(k0 + e) * TV + p] : 0.f;
+    split_store8(x, stage + (size_t)c * 4096 + p * 16, term_stride);
+  }
+  fence_proxy_async();
+}
+
+// One elected lane of warp 0: per tile and k-step the three bf16 weight terms and the fp16 pair accumulate into the
+// same Np tensor-memory columns (tensor-memory reads of the epilogue are the scarcer resource here, unlike in fpn_tc.cuh).
+static __device__ __noinline__ void tc_issue(uint32_t tmem, uint32_t stage_addr, int term_stride, uint32_t img_addr, int img_chunk,
+                                      int kc, int Np, int first, uint32_t bar) {
+  if (elect_one()) {
+    const uint32_t i1 = umma_idesc_bf16(Np), i2 = umma_idesc_f16(Np);
+    const uint32_t bch = (uint32_t)(4 * Np * 16);                  // bytes of one k-chunk of the image
+    const uint64_t da0 = umma_desc(stage_addr, 4096, 128);
+    const uint64_t db0 = umma_desc(img_addr, bch, 128) + (uint64_t)((img_chunk * bch) >> 4);
+    const uint64_t brow = (uint64_t)((Np * 16) >> 4);              // Np rows of the image
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t) {
+      const uint32_t acc = tmem + (uint32_t)(t * Np);
+#pragma unroll 1
+      for (int ks = 0; ks < kc / 2; ++ks) {
+        const uint64_t da = da0 + (uint64_t)((2 * ks * 4096 + t * 2048) >> 4);
+        const uint64_t db = db0 + (uint64_t)((2 * ks * bch) >> 4);
+        umma_bf16(acc, da, db, i1, (first == 0) || ks != 0);
+        umma_bf16(acc, da, db + brow, i1, 1);
+        umma_bf16(acc, da, db + 2 * brow, i1, 1);
+        umma_bf16(acc, da + (uint64_t)(term_stride >> 4), db + 3 * brow, i2, 1);
+      }
+    }
+    umma_commit(bar);
+  }
+  __syncwarp();
+}
+
+template <int TV, int NT, class EPI>
+CG_DEV void tc_gemm(TcState& tc, const float* X1, int K1, const float* X2, int K2, int M,
+                    const float* next_img, int next_floats, EPI epi) {
+  static_assert(NT == 512, "tc_gemm: written for 16 warps");
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Np = (M + 15) & ~15;
+  const int term_stride = tc.kc_cap * 4096;
+  const int npass = K2 > 0 ? 2 : 1;
+  int img_chunk = 0;
+#pragma unroll 1
+  for (int pass = 0; pass < npass; ++pass) {
+    const float* X = pass ? X2 : X1;
+    const int K = pass ? K2 : K1;
+    const int kc = ((K + 15) / 16) * 2;
+    if (pass) {                                        // the first row block's MMAs must have read the staging operand
+      mbar_wait(tc.bar, tc.parity);
+      tc.parity ^= 1;
+    }
+    const long long tq0 = clock64();
+    tc_convert<TV, NT>(tc.stage, term_stride, X, K);
+    __syncthreads();
+    if (tc.dbg && tid == 0) tc.dbg[0] += clock64() - tq0;
+    if (warp == 0) {
+      if (pass == 0) mbar_wait(tc.img_bar, tc.img_parity);
+      tc_fence_after();
+      tc_issue(tc.tmem, smem_u32(tc.stage), term_stride, smem_u32(tc.img), img_chunk, kc, Np, pass == 0, tc.bar);
+    }
+    img_chunk += kc;
+  }
+  tc.img_parity ^= 1;
+  const long long tq1 = clock64();
+  mbar_wait(tc.bar, tc.parity);
+  tc.parity ^= 1;
+  tc_fence_after();
+  if (next_img) tc_prefetch(tc, next_img, next_floats);     // the image buffer is free: fetch the next user's weights
+  const long long tq2 = clock64();
+  {
+    const int q = warp & 3, g = warp >> 2;
+    const int t = g & 1;
+    const int p = t * 128 + q * 32 + lane;
+    const uint32_t base = tc.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * Np);
+    // warps g>>1 = 0 / 1 split the channels in halves; four channels per tcgen05.ld, rolled loop
+    const int half = Np / 2, c_begin = (g >> 1) * half;
+#pragma unroll 1
+    for (int c = c_begin; c < c_begin + half; c += 4) {
+      uint32_t v[4];
+      tmem_ld4(base + c, v);
+      tmem_ld_wait();
+      if (p < TV && c < M) {
+        float f[4] = {__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])};
+        epi(c, p, f);                          // channels c .. c+3 of position p (the callee masks m >= M)
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tc.dbg && tid == 0) { tc.dbg[1] += tq2 - tq1; tc.dbg[2] += clock64() - tq2; tc.dbg[3] += 1; }
+}
+#endif  // CISTGCN_EMU
+
+// TC = true: the instantiation that carries the tensor-core channel mixes (kept apart: their code costs the FP32-FMA
+// variant registers and instruction-cache space even when it never runs).
+template <int T, int V, int NT, bool TC = false>
 __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_block_kernel(const DstdArgs a) {
   CG_DYN_SMEM(smem);
   constexpr int TV = T * V, TT = T * T, VV = V * V, VP = V | 1;   // VP: odd row stride of the transposed Adj_s
@@ -619,6 +802,38 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_block_kernel(const
     if (a.res[f] >= 0) copy_async<NT>(smem + a.res[f], W + d[f], a.wsz[f]);
   cp_async_commit();
   cp_async_wait_all();
+#ifndef CISTGCN_EMU
+  TcState tc = {0, 0, 0, 0, 0, nullptr, nullptr, 0, nullptr};
+  const float* tc_first = nullptr;       // first image a sample needs, and its size
+  int tc_first_floats = 0;
+  bool use_tc = false;
+  if constexpr (TC) {
+    use_tc = a.tc != 0;
+    if (use_tc) {
+      uint32_t* slot = reinterpret_cast<uint32_t*>(smem + a.o_tcmisc) + 2;      // [mbarrier 8 B][slot 4 B][pad][mbarrier 8 B]
+      tc.bar = smem_u32(smem + a.o_tcmisc);
+      tc.img_bar = tc.bar + 16;
+      tc.stage = reinterpret_cast<unsigned char*>(smem + a.o_stage);
+      tc.img = smem + a.o_img;
+      tc.kc_cap = a.tc_kc;
+      tc_first = W + (interp ? d[CB_TC_A0] : d[CB_TC_TCN_S]);
+      tc_first_floats = interp ? a.wsz[CB_TC_A0] : a.wsz[CB_TC_TCN_S];
+      tc.dbg = (a.phase_clocks && blockIdx.x == 0) ? a.phase_clocks + 16 : nullptr;
+      if (tid == 0) { mbar_init(tc.bar, 1); mbar_init(tc.img_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+      if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+      }
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      tc.tmem = *slot;
+      tc_prefetch(tc, tc_first, tc_first_floats);
+    }
+  }
+#else
+  constexpr bool use_tc = false;
+#endif
   __syncthreads();
 
   for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
@@ -777,8 +992,31 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_block_kernel(const
       {
         const float* ab = P(CB_A0_B);
         const float* aa = P(CB_A0_A);
+#ifndef CISTGCN_EMU
+        if constexpr (TC) {
+          if (use_tc)
+            tc_gemm<TV, NT>(tc, XN, Ci, nullptr, 0, 4 * Ch, W + d[CB_TC_TCN_S], a.wsz[CB_TC_TCN_S], [&](int m0, int pp, float (&v)[4]) {
+              const float* sab = smem + a.res[CB_A0_B];       // vectors are always resident
+              const float* saa = smem + a.res[CB_A0_A];
+              // all loads first, then all stores: the compiler cannot prove the tiles and the vectors disjoint
+              const int br0 = m0 / Ch, r0 = m0 - br0 * Ch;
+              int br = br0, r = r0;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                v[i] = prelu(v[i] + sab[imin(m0 + i, 4 * Ch - 1)], saa[imin(br, 3)]);
+                if (++r == Ch) { r = 0; ++br; }
+              }
+              br = br0; r = r0;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (m0 + i < 4 * Ch) (A + (br >> 1) * a.tile)[((br & 1) * Ch + r) * TV + pp] = v[i];
+                if (++r == Ch) { r = 0; ++br; }
+              }
+            });
+        }
+#endif
         const WideOp ops[1] = {{G(CB_A0_WT), RS(CB_A0_WT), XN, nullptr}};
-        gemm_wide_auto<TNW, TV, TV, NT, false, 1>(ops, pad8i(4 * Ch), 4 * Ch, Ci, 0, ring, rb,
+        if (!use_tc) gemm_wide_auto<TNW, TV, TV, NT, false, 1>(ops, pad8i(4 * Ch), 4 * Ch, Ci, 0, ring, rb,
           [&](int, int m, int n0, float (&v)[TNW]) {
             const int br = m / Ch, r = m - br * Ch;
             const float bias = ab[m], sl = aa[br];
@@ -937,7 +1175,36 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_block_kernel(const
         store_vec<TNW>(Gt + m * TV + n0, v);
       };
       const int K2 = has_res ? Ci : 0;
-      if (RS(CB_TCN_WT_S) && RS(CB_TCN_WT_T)) {            // both resident: one phase for both domains
+#ifndef CISTGCN_EMU
+      if constexpr (TC) {
+        if (use_tc) {
+#pragma unroll 1
+          for (int L = 0; L < 2; ++L) {
+            float* Gt = L == 0 ? A : Bt;
+            const float ta = L ? ta1 : ta0, pa = L ? pa1 : pa0;
+            const int nf = L == 0 ? CB_TC_TCN_T : CB_TC_CP;
+            const float* stb = smem + a.res[CB_TCN_B_S + L];
+            const float* sps = smem + a.res[CB_P_S_S + L];
+            const float* spb = smem + a.res[CB_P_B_S + L];
+            tc_gemm<TV, NT>(tc, Gt, Ci, XN, K2, Co, W + d[nf], a.wsz[nf], [&](int m0, int pp, float (&v)[4]) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {                 // all loads first, then all stores
+                const int m = imin(m0 + i, Co - 1);
+                float x = v[i] + stb[m];
+                if (!has_res) x += XN[m * TV + pp];
+                x = prelu(x, ta);
+                v[i] = prelu(fmaf(sps[m] * wg[L * Co + m], x, spb[m]), pa);
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (m0 + i < Co) Gt[(m0 + i) * TV + pp] = v[i];
+            });
+          }
+        }
+      }
+#endif
+      if (use_tc) {
+      } else if (RS(CB_TCN_WT_S) && RS(CB_TCN_WT_T)) {            // both resident: one phase for both domains
         const WideOp ops[2] = {{G(CB_TCN_WT_S), RS(CB_TCN_WT_S), A, XN}, {G(CB_TCN_WT_T), RS(CB_TCN_WT_T), Bt, XN}};
         gemm_wide_auto<TNW, TV, TV, NT, true, 2>(ops, Cop, Co, Ci, K2, ring, rb, tcn_epi);
       } else {
@@ -954,8 +1221,22 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_block_kernel(const
     {
       const float* cb = P(CB_CP_B);
       const float ca = P(CB_CP_A)[0];
+#ifndef CISTGCN_EMU
+      if constexpr (TC) {
+        if (use_tc)
+          tc_gemm<TV, NT>(tc, A, Co, Bt, Co, Co, has_res ? W + d[CB_TC_RS] : tc_first, has_res ? a.wsz[CB_TC_RS] : tc_first_floats,
+                          [&](int m0, int pp, float (&v)[4]) {
+            const float* scb = smem + a.res[CB_CP_B];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = prelu(v[i] + scb[imin(m0 + i, Co - 1)], ca);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (m0 + i < Co) A[(m0 + i) * TV + pp] = v[i];
+          });
+      }
+#endif
       const WideOp ops[1] = {{G(CB_CP_WT), RS(CB_CP_WT), A, Bt}};
-      gemm_wide_auto<TNW, TV, TV, NT, true, 1>(ops, Cop, Co, Co, Co, ring, rb,
+      if (!use_tc) gemm_wide_auto<TNW, TV, TV, NT, true, 1>(ops, Cop, Co, Co, Co, ring, rb,
         [&](int, int m, int n0, float (&v)[TNW]) {
           const float bias = cb[m];
 #pragma unroll
@@ -995,8 +1276,26 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_block_kernel(const
       const bool contiguous = sv == 1 && st == V && sc == TV && (TV % 4) == 0;
       if (has_res) {
         const float* rbias = P(CB_RS_B);
+#ifndef CISTGCN_EMU
+        if constexpr (TC) {
+          if (use_tc)
+            tc_gemm<TV, NT>(tc, XN, Ci, nullptr, 0, Co, tc_first, tc_first_floats, [&](int m0, int pp, float (&v)[4]) {
+              const float* srb = smem + a.res[CB_RS_B];
+              const int t = pp / V, vv = pp - t * V;
+              float* dp = dst + t * st + vv * sv;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int m = imin(m0 + i, Co - 1);
+                v[i] = fmaf(A[m * TV + pp], gate[m], v[i] + srb[m]);
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (m0 + i < Co) dp[(m0 + i) * sc] = v[i];
+            });
+        }
+#endif
         const WideOp ops[1] = {{G(CB_RS_WT), RS(CB_RS_WT), XN, nullptr}};
-        gemm_wide_auto<TNW, TV, TV, NT, false, 1>(ops, Cop, Co, Ci, 0, ring, rb,
+        if (!use_tc) gemm_wide_auto<TNW, TV, TV, NT, false, 1>(ops, Cop, Co, Ci, 0, ring, rb,
           [&](int, int m, int n0, float (&v)[TNW]) {
             const float gm = gate[m], bias = rbias[m];
             float c[TNW];
@@ -1031,6 +1330,18 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_block_kernel(const
     __syncthreads();
     CG_STAMP(15);
   }
+#ifndef CISTGCN_EMU
+  if constexpr (TC) {
+    if (use_tc) {
+      tc_fence_before();
+      __syncthreads();
+      if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tc.tmem), "r"(512u));
+      }
+    }
+  }
+#endif
 }
 
 }  // namespace cg

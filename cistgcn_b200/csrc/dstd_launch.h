@@ -22,10 +22,12 @@ CG_DECL_DSTD(10, 18)
 CG_DECL_DSTD(22, 25)
 CG_DECL_DSTD(18, 25)
 #undef CG_DECL_DSTD
+int launch_dstd_10_22_512_tc(const DstdArgs& a, void* stream);     // tensor-core channel mixes (DstdArgs::tc)
+int launch_dstd_10_18_512_tc(const DstdArgs& a, void* stream);
 
-template <int T, int V, int NT>
+template <int T, int V, int NT, bool TC = false>
 inline int launch_dstd_impl(const DstdArgs& a, void* stream) {
-  auto kfn = dstd_block_kernel<T, V, NT>;
+  auto kfn = dstd_block_kernel<T, V, NT, TC>;
   const size_t smem = (size_t)a.smem_floats * sizeof(float);
   int err = 0;
   const int per_sm = prepared_blocks_per_sm(kfn, NT, smem, &err);

@@ -166,6 +166,7 @@ def _pack_block(blob: _Blob, sd, p: str, ci: int, co: int, T: int, V: int, inter
     def put(field, name, t):
         d[F[field]] = blob.add(f"{p}:{name}", t)
 
+    tc_mats = {}          # field -> (matrix (outputs, inputs), input row blocks) of the tensor-core channel mixes
     s, b = _fold(sd, p + ".global_norm")
     put("CB_GN_S", "gn_s", s)
     put("CB_GN_B", "gn_b", b)
@@ -221,6 +222,7 @@ def _pack_block(blob: _Blob, sd, p: str, ci: int, co: int, T: int, V: int, inter
             put("CB_E0_A" + sfx, Lname + ".e0_a", _w(sd, f"{q}.expansor.3.weight"))
             put("CB_E4_WT" + sfx, Lname + ".e4_wt", _kmajor(_w(sd, f"{q}.expansor.4.weight").reshape(n, n)))
         put("CB_A0_WT", "a0_wt", _kmajor(torch.cat(aw, 0)))
+        tc_mats["CB_TC_A0"] = (torch.cat(aw, 0), [ci])
         put("CB_A0_B", "a0_b", torch.cat(ab))
         put("CB_A0_A", "a0_a", torch.cat(aa))
     else:
@@ -238,6 +240,7 @@ def _pack_block(blob: _Blob, sd, p: str, ci: int, co: int, T: int, V: int, inter
             W = torch.cat([W, sr[:, None] * _w(sd, f"{q}.residual.0.weight").reshape(co, ci)], 1)
             bias = bias + sr * _w(sd, f"{q}.residual.0.bias") + br
         put("CB_TCN_WT" + sfx, Lname + ".tcn_wt", _kmajor(W))
+        tc_mats["CB_TC_TCN" + sfx] = (W, [ci, ci] if has_res else [ci])
         put("CB_TCN_B" + sfx, Lname + ".tcn_b", bias)
         put("CB_TCN_A" + sfx, Lname + ".tcn_a", _w(sd, f"{q}.prelu.weight"))
         s, b = _fold(sd, f"{p}.{pk}.0")
@@ -247,6 +250,7 @@ def _pack_block(blob: _Blob, sd, p: str, ci: int, co: int, T: int, V: int, inter
     # ---- compressor + SE (CISTGCN.py:305-309, SE.py:24-41)
     s, b = _fold(sd, f"{p}.compressor.1")
     put("CB_CP_WT", "cp_wt", _kmajor(s[:, None] * _w(sd, f"{p}.compressor.0.weight").reshape(co, 2 * co)))
+    tc_mats["CB_TC_CP"] = (s[:, None] * _w(sd, f"{p}.compressor.0.weight").reshape(co, 2 * co), [co, co])
     put("CB_CP_B", "cp_b", b)
     put("CB_CP_A", "cp_a", _w(sd, f"{p}.compressor.2.weight"))
     put("CB_SE1_WT", "se1_wt", _kmajor(_w(sd, f"{p}.compressor.3.excitation.0.weight")))
@@ -255,6 +259,11 @@ def _pack_block(blob: _Blob, sd, p: str, ci: int, co: int, T: int, V: int, inter
         s, b = _fold(sd, f"{p}.residual.1")
         put("CB_RS_WT", "rs_wt", _kmajor(s[:, None] * _w(sd, f"{p}.residual.0.weight").reshape(co, ci)))
         put("CB_RS_B", "rs_b", s * _w(sd, f"{p}.residual.0.bias") + b)
+        tc_mats["CB_TC_RS"] = (s[:, None] * _w(sd, f"{p}.residual.0.weight").reshape(co, ci), [ci])
+    # tensor-core images: only where K is worth a k-step and the fp16 copies cannot overflow
+    if ci >= 16 and max(4 * ch, co) <= 64 and all(float(m.abs().max()) < TC_FP16_MAX for m, _ in tc_mats.values()):
+        for field, (mat, segs) in tc_mats.items():
+            d[F[field]] = blob.add_raw(f"{p}:{field.lower()}", tc_image(mat, segs))
     return d
 
 
@@ -284,6 +293,29 @@ def tc_slice(Wm: torch.Tensor, kc: int) -> torch.Tensor:
     for j, part in enumerate(bf16_split3(full)):
         img[:, 32 * j: 32 * j + 32, :] = part.view(torch.int16).reshape(32, kc, 8).permute(1, 0, 2)
     img[:, 96:, :] = full.to(torch.float32).to(torch.float16).view(torch.int16).reshape(32, kc, 8).permute(1, 0, 2)
+    return img.contiguous().view(torch.int32).reshape(-1)
+
+
+def tc_image(Wm: torch.Tensor, segs) -> torch.Tensor:
+    """(M outputs, sum(segs) inputs) matrix -> int32 words of the tcgen05 B-operand image used by the DSTD-GC channel
+    mixes: [K/8 chunks][4*Np rows][8 x 16 bit], Np = pad16(M); rows j*Np + m = bf16 term j (j < 3), rows 3*Np + m = fp16(w).
+    `segs` are the row blocks of the activation operand (e.g. [Co, Co] for cat(u1, u2)); each is padded to 16 channels
+    (one k-step), because the kernel converts and multiplies one row block at a time."""
+    M = Wm.shape[0]
+    Np = pad_up(M, 16)
+    kp = [pad_up(k, 16) for k in segs]
+    K = sum(kp)
+    full = torch.zeros(Np, K, dtype=torch.float64)
+    src = dst = 0
+    for k, kpad in zip(segs, kp):
+        full[:M, dst: dst + k] = Wm[:, src: src + k]
+        src += k
+        dst += kpad
+    kc = K // 8
+    img = torch.zeros(kc, 4 * Np, 8, dtype=torch.int16)
+    for j, part in enumerate(bf16_split3(full)):
+        img[:, j * Np: (j + 1) * Np, :] = part.view(torch.int16).reshape(Np, kc, 8).permute(1, 0, 2)
+    img[:, 3 * Np:, :] = full.to(torch.float32).to(torch.float16).view(torch.int16).reshape(Np, kc, 8).permute(1, 0, 2)
     return img.contiguous().view(torch.int32).reshape(-1)
 
 

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CISTGCN_ABI_VERSION 4
+#define CISTGCN_ABI_VERSION 5
 #define CISTGCN_MPAD 8          /* output-dimension padding of every k-major matrix */
 #define CISTGCN_MAX_BLOCKS 8    /* input + output DSTD-GC blocks in one plan */
 #define CISTGCN_MAX_FPN 8
@@ -79,6 +79,13 @@ enum cistgcn_block_field {
   CB_CP_WT, CB_CP_B, CB_CP_A,       /* compressor.0 (+BN .1): [2Co][pad(Co)], [Co], slope */
   CB_SE1_WT, CB_SE2_WT,             /* compressor.3.excitation.{0,2}: [Co][pad(Hs)], [Hs][pad(Co)] */
   CB_RS_WT, CB_RS_B,                /* block residual conv (+BN): [Ci][pad(Co)], [Co]  (HAS_RES only) */
+  /* tcgen05 operand images of the channel-mixing 1x1 convolutions (csrc/dstd_block.cuh, tc_gemm), 0 = absent:
+   * [K/8 k-chunks][4*Np rows][8 x 16 bit], rows j*Np + m = bf16 term j of output channel m (j = 0,1,2), rows 3*Np + m =
+   * its fp16 rounding; Np = pad16(outputs); K = the same row blocks as the fp32 matrix, each padded to 16 */
+  CB_TC_A0,                         /* Map2Adj first 1x1 convs stacked (4*Ch outputs, K = Ci) */
+  CB_TC_TCN_S, CB_TC_TCN_T,         /* tcn.0 (+BN) [+ residual conv rows]  (Co outputs, K = Ci [+ Ci]) */
+  CB_TC_CP,                         /* compressor.0 (+BN)  (Co outputs, K = Co + Co) */
+  CB_TC_RS,                         /* block residual conv (+BN)  (Co outputs, K = Ci; HAS_RES only) */
   CB_COUNT
 };
 
@@ -195,6 +202,11 @@ int cistgcn_mpjpe_f32(const float* pred, const float* target, int64_t batch, int
 /* FPN stack kernel choice (process-wide): 0 (default) = tcgen05 tensor-core kernel whenever the shape fits
  * (csrc/fpn_tc.cuh), 1 = FP32-FMA kernel (csrc/fpn_chain.cuh).  Both implement CISTGCN.py:38-79, 582-589. */
 int cistgcn_set_fpn_path(int path);
+/* DSTD-GC block channel mixes (Map2Adj entry convs, tcn, compressor, residual conv; CISTGCN.py:229-247, 305-318):
+ * 0 (default) = FP32-FMA loops; 1 = tcgen05 MMAs (same split-operand scheme as the FPN kernel) in the 512-thread kernel
+ * whenever the shared-memory plan fits (Ci >= 16, <= 64 outputs).  Parity-tested; measured slower than the FMA loops at
+ * K = 32 (the per-element operand conversion and epilogue cost what the 32 FMAs cost), see DESIGN.md section 4b. */
+int cistgcn_set_dstd_path(int path);
 
 /* Optional per-kernel timing for benchmarks (no reference counterpart).  While enabled every launch
  * is bracketed by CUDA events on its stream; cistgcn_profile_read synchronises the device, sums the

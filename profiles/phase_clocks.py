@@ -13,12 +13,14 @@ E = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 V = int(sys.argv[2]) if len(sys.argv) > 2 else 22
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 148 * 4
 ITER = int(sys.argv[4]) if len(sys.argv) > 4 else 0       # which sample of CTA 0 to stamp (0 = cold, >=1 = warm)
+PATH = int(sys.argv[5]) if len(sys.argv) > 5 else 0       # cistgcn_set_dstd_path: 0 FP32-FMA channel mixes, 1 tensor-core
 NAMES = ["load+norm", "stats", "gate conv(T,1)", "gate matvecs", "map2adj 1x1", "collapse convs", "dimseq/dsp+outer_s",
          "expansor_s", "gcn_space", "outer_t+expansor_t", "gcn_time", "tcn x2", "compressor", "SE", "store"]
 lib = _cabi.lib()
+lib.cistgcn_set_dstd_path(PATH)
 model = _make_model(E, V).cuda()
 pk = model.pack("cuda")
-clk = torch.zeros(16, dtype=torch.int64, device="cuda")
+clk = torch.zeros(24, dtype=torch.int64, device="cuda")
 lib.cistgcn_debug_phase_clocks(clk.data_ptr())
 lib.cistgcn_debug_stamp_iteration(ITER)
 for which, i in (("in", 0), ("in", 1), ("in", 4), ("out", 0)):
@@ -38,4 +40,8 @@ for which, i in (("in", 0), ("in", 1), ("in", 4), ("out", 0)):
     print(f"block {which}{i} ({ci}->{co}, T={T}, V={Vb}): {tot} cycles / sample")
     for k, n in enumerate(NAMES):
         print(f"   {n:22s} {c[k + 1] - c[k]:8d}  {100.0 * (c[k + 1] - c[k]) / tot:5.1f}%")
+    if c[19]:
+        ns = -(-B // 148)        # samples CTA 0 processed (counters accumulate over all of them)
+        print(f"   tensor-core channel mixes, per call ({c[19] / ns:.0f} calls / sample): conversion {c[16] / c[19]:.0f}, "
+              f"MMA wait {c[17] / c[19]:.0f}, epilogue {c[18] / c[19]:.0f} cycles")
 lib.cistgcn_debug_phase_clocks(None)

@@ -129,3 +129,32 @@ def test_fpn_path_switch_rejects_unknown():
     assert L.cistgcn_set_fpn_path(7) < 0
     assert b"unknown" in L.cistgcn_last_error()
     assert L.cistgcn_set_fpn_path(0) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("weights,scale", [("W1", "unit"), ("W2", "unit"), ("W1", "mm")])
+def test_dstd_tensor_core_channel_mixes_match_oracle(weights, scale):
+    """cistgcn_set_dstd_path(1): the E=32 blocks run their 1x1 channel mixes (Map2Adj entry convs, tcn, compressor,
+    residual conv) as tcgen05 MMAs; the whole forward must stay inside the fp32 tolerance and agree with the
+    FP32-FMA path to a fraction of it."""
+    import _golden as G
+    from cistgcn_b200 import _cabi
+    L = _cabi.lib()
+    dev = "cuda:0"
+    model, sd, cfg = M.build(32, 22, weights)
+    x, _ = O.synth_inputs(48, cfg, scale=scale)
+    with torch.no_grad():
+        ref = O.forward(sd, cfg, x)
+    model = model.to(dev)
+    try:
+        _cabi.check(L.cistgcn_set_dstd_path(1), "cistgcn_set_dstd_path", L)
+        tc = model(x.to(dev))[0].cpu()
+        _cabi.check(L.cistgcn_set_dstd_path(0), "cistgcn_set_dstd_path", L)
+        fm = model(x.to(dev))[0].cpu()
+    finally:
+        L.cistgcn_set_dstd_path(0)
+    assert torch.isfinite(tc).all()
+    assert (tc - ref).abs().max().item() <= G.tol(ref)
+    assert (fm - ref).abs().max().item() <= G.tol(ref)
+    assert not torch.equal(tc, fm)                       # the tensor-core path really ran
+    assert (tc - fm).abs().max().item() <= 0.5 * G.tol(ref)
