@@ -67,7 +67,7 @@ inline bool dstd_plan(DstdArgs& a, int nt, int max_smem_floats, bool tc_allowed 
   const int* d = a.d;
   const int Ci = d[CB_CI], Co = d[CB_CO], T = d[CB_T], V = d[CB_V], Ch = d[CB_CH], Cg = d[CB_CG], Hs = d[CB_HS];
   const bool has_res = d[CB_HAS_RES] != 0, interp = d[CB_INTERP] != 0;
-  const int TV = T * V, cmax = imax(Ci, Co), big = TV * imax(T, V), Cop = pad8i(Co);
+  const int TV = T * V, cmax = imax(Ci, Co), big = imax(TV * imax(T, V), T * pad4i(V * V)), Cop = pad8i(Co);
   for (int f = 0; f < CB_COUNT; ++f) { a.wsz[f] = 0; a.res[f] = -1; }
   int* z = a.wsz;
   z[CB_GN_S] = z[CB_GN_B] = Ci;
@@ -579,7 +579,7 @@ CG_DEV void gcn_space(const float* XN, const float* adjT, float* G, int C) {
 // "time" domain: g2[c][t][w] = sum_v XN[c][t][v] * Adj_t[t][v][w]  (natural layout).
 template <int T, int V, int TC, int NT>
 CG_DEV void gcn_time(const float* XN, const float* adj, float* G, int C) {
-  constexpr int TV = T * V, VV = V * V;
+  constexpr int TV = T * V, VVP = (V * V + 3) & ~3;        // padded row stride of the frame-axis adjacency
   constexpr int TW = (V % 11 == 0) ? 11 : ((V % 9 == 0) ? 9 : ((V % 5 == 0) ? 5 : 1));
   constexpr int NWG = V / TW;
   const int nct = (C + TC - 1) / TC;
@@ -595,7 +595,7 @@ CG_DEV void gcn_time(const float* XN, const float* adj, float* G, int C) {
       float xv[TC];
 #pragma unroll
       for (int i = 0; i < TC; ++i) xv[i] = (c0 + i < C) ? XN[(c0 + i) * TV + t * V + v] : 0.f;
-      const float* ap = adj + t * VV + v * V + w0;
+      const float* ap = adj + t * VVP + v * V + w0;
 #pragma unroll
       for (int j = 0; j < TW; ++j) {
         const float aj = ap[j];
@@ -619,8 +619,9 @@ CG_DEV void gcn_time(const float* XN, const float* adj, float* G, int C) {
 // sample, as tcgen05 MMAs with M = 128 positions (two tiles), N = channels, accumulators in tensor memory.
 //   1. every thread converts its share of the fp32 activation rows (X1: K1 rows, X2: K2 rows, row stride TV) into
 //      the staging operand [term][k-chunk][position][8 x 16 bit]: term 0 = bf16(x), term 1 = fp16(x - bf16(x));
-//   2. one elected lane of warp 0 issues, per tile and k-step, x_bf16 * [w1|w2|w3] (N = 3*Np) and x_fp16 * w_fp16
-//      (N = Np, accumulated into the first Np columns) against the resident weight image (pack.py tc_image);
+//   2. one elected lane of warp 0 issues, per tile and k-step, x_bf16 * w1, * w2, * w3 and x_fp16 * w_fp16, all
+//      accumulated into the same Np columns, against the weight image (pack.py tc_image) that cp.async.bulk streamed
+//      into the image buffer a phase earlier;
 //   3. after the commit's mbarrier fires, the 16 warps read their TMEM lane quadrant (thread = position, 16 channels
 //      per tcgen05.ld) and hand (first channel, position, 16 values) to the epilogue.
 // Same split scheme and accuracy as the FPN kernel (fpn_tc.cuh): ~1e-6 relative.
@@ -759,7 +760,8 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_block_kernel(const
   constexpr int NW = NT / 32;
   constexpr int TNW = (TV % 4 == 0) ? 4 : 2;            // column vector width of the wide GEMMs
   constexpr int TNS = (TT % 4 == 0) ? 4 : 2;            // ... of the joint-axis expansor (N = T*T)
-  constexpr int TNT = (VV % 4 == 0) ? 4 : (VV % 2 == 0 ? 2 : 1);   // ... of the frame-axis expansor (N = V*V)
+  constexpr int VVP = (VV + 3) & ~3;                    // row stride of Adj_t and of its hidden map: V*V padded to a float4
+  constexpr int TNT = 4;                                // ... of the frame-axis expansor (N = V*V, rows padded to VVP)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int* d = a.d;
   const float* __restrict__ W = a.w;
@@ -1111,39 +1113,40 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_block_kernel(const
     CG_STAMP(9);
     // ---------------- P11: time-domain outer product + expansor over the frame axis -> Adj_t
     if (interp) {
-      for (int i = tid; i < T * VV; i += NT) {                // o[t'][v][w] = dsp[v][t'] * dseq[t'][w]
-        const int tq = i / VV, r = i - tq * VV, v = r / V, w = r - v * V;
-        ADJ[i] = dsp[TV + v * T + tq] * dseq[TV + tq * V + w];
+      for (int i = tid; i < T * VVP; i += NT) {               // o[t'][v][w] = dsp[v][t'] * dseq[t'][w]
+        const int tq = i / VVP, r = i - tq * VVP, v = r / V, w = r - v * V;
+        ADJ[i] = r < VV ? dsp[TV + v * T + tq] * dseq[TV + tq * V + w] : 0.f;
       }
       __syncthreads();
       {
         const float* eb = P(CB_E0_B_T);
         const float ea = P(CB_E0_A_T)[0];
         const WideOp ops[1] = {{G(CB_E0_WT_T), RS(CB_E0_WT_T), ADJ, nullptr}};
-        gemm_wide_auto<TNT, VV, VV, NT, false, 1>(ops, pad8i(T), T, T, 0, ring, rb,
+        gemm_wide_auto<TNT, VVP, VVP, NT, false, 1>(ops, pad8i(T), T, T, 0, ring, rb,
           [&](int, int m, int n0, float (&v)[TNT]) {
             const float bias = eb[m];
 #pragma unroll
             for (int j = 0; j < TNT; ++j) v[j] = prelu(v[j] + bias, ea);
-            store_vec<TNT>(Bt + m * VV + n0, v);
+            store_vec<TNT>(Bt + m * VVP + n0, v);
           });
       }
       __syncthreads();
       {
         float* tp = a.tap_adj_t ? a.tap_adj_t + (size_t)b * T * VV : nullptr;
         const WideOp ops[1] = {{G(CB_E4_WT_T), RS(CB_E4_WT_T), Bt, nullptr}};
-        gemm_wide_auto<TNT, VV, VV, NT, false, 1>(ops, pad8i(T), T, T, 0, ring, rb,
+        gemm_wide_auto<TNT, VVP, VVP, NT, false, 1>(ops, pad8i(T), T, T, 0, ring, rb,
           [&](int, int m, int n0, float (&v)[TNT]) {
-            store_vec<TNT>(ADJ + m * VV + n0, v);
+            store_vec<TNT>(ADJ + m * VVP + n0, v);
             if (tp) {
 #pragma unroll
-              for (int j = 0; j < TNT; ++j) tp[m * VV + n0 + j] = v[j];
+              for (int j = 0; j < TNT; ++j)
+                if (n0 + j < VV) tp[m * VV + n0 + j] = v[j];
             }
           });
       }
     } else {
       const float* at = W + d[CB_ADJ_T];
-      for (int i = tid; i < T * VV; i += NT) ADJ[i] = __ldg(at + i);
+      for (int i = tid; i < T * VV; i += NT) ADJ[(i / VV) * VVP + i % VV] = __ldg(at + i);
     }
     __syncthreads();
     CG_STAMP(10);

@@ -10,8 +10,9 @@
 // [w1 | w2 | w3 | wh] side by side as 128 rows, so one k-step is two MMAs: x1 * [w1|w2|w3] (kind::f16 with bf16
 // operands, N = 96) and x2 * wh (fp16 operands, N = 32, accumulated into the first 32 columns); the epilogue adds
 // the three 32-column blocks.  Accumulation is fp32 in TMEM.  What is dropped is below 2^-20 |x||w|.
-// (The tensor pipe here is bound by shared-memory operand reads, ~70 B/clk: 12 KB per k-step this way against
-// 18 KB for three bf16 terms on both sides, which was the first version.)
+// (An M128 K16 MMA costs >= ~63 cycles here whatever N <= 96 is -- the A operand streams from shared memory at
+// ~64 B/clk, no-swizzle and SWIZZLE_128B alike (profiles/micro/umma_probe*.cu) -- so the MMA count, two per k-step,
+// sets the pace; the first version carried three bf16 terms on both sides in three MMAs per k-step.)
 //
 // Implicit GEMM without im2col: the sample's map lives in shared memory as [term][k-chunk of 8 channels]
 // [position][8 x 16 bit] with positions at a 16-byte pitch (row pitch W + 3: the three pad columns serve as
@@ -23,12 +24,12 @@
 // Roles (one CTA of 384 threads per SM, persistent over samples):
 //   warp 0   weight producer: cp.async.bulk (1-D TMA) of per-tap slices from L2 into a 10-slot ring,
 //            mbarrier complete_tx; the ring is refilled behind the second tile's pass over a branch
-//   warp 1   MMA issuer (one thread): conv(d, tile) -> acc[tile] in TMEM; compress(d, tile) accumulates into
+//   warp 1   MMA issuer (warp-uniform control flow, one elected lane issues): conv(d, tile) -> acc[tile] in TMEM; compress(d, tile) accumulates into
 //            cacc[tile]; schedule conv(d,0) cmp(d-1,1) conv(d,1) cmp(d,0) keeps the pipe busy while the
 //            epilogue of the other tile runs
 //   warps 2-3  input loader: next sample's (Tin, F, V) map -> the two terms in a separate input buffer (layer 0
 //            reads it, so the next sample's first layer overlaps this sample's last epilogue), average branch of layer 0
-//   warps 4-11 epilogue, one warpgroup per tile (TMEM lane = position): branch bias + PReLU -> bf16 terms into
+//   warps 4-11 epilogue, one warpgroup per tile (TMEM lane = position): branch bias + PReLU -> the two terms into
 //            the staging operand of `compress`; compress bias + average branch + PReLU (+ residual) -> next
 //            layer's map in place; last layer -> dim_conversor, cumsum, x7
 #pragma once
