@@ -15,7 +15,7 @@
 // Shared-memory map (floats):
 //   XN  [Ci][TV]          resident input tile (after global_norm)
 //   A | B [Cmax][TV]      work tiles: Map2Adj hidden maps -> g1/g2 -> u1/u2 -> c ; B also hosts the
-//                         expansor's hidden map
+//                         joint-axis expansor's hidden map where that runs as GEMMs
 //   ADJ [TV*max(T,V)]     row statistics / split-K partials, then o / Adj_s ([t][q][v]), then o / Adj_t
 //   SM                    small vectors (stats, gate activations, dseq/dsp, SE)
 //   RING                  RING_SLOTS x ring_floats streaming slots (absent when nothing streams)
@@ -96,7 +96,9 @@ inline bool dstd_plan(DstdArgs& a, int nt, int max_smem_floats, bool tc_allowed 
   a.tile = pad4i(cmax * TV);
   a.o_xn = 0;
   a.o_ab = pad4i(Ci * TV);
-  a.o_adj = a.o_ab + a.tile + imax(a.tile, pad4i(big));
+  // B also hosts the hidden map [V][T*T] of the joint-axis expansor where that runs as two GEMMs (few columns)
+  const int hs_need = (T * T * 2 <= nt) ? pad4i(T * T * V) : 0;
+  a.o_adj = a.o_ab + a.tile + imax(a.tile, hs_need);
   const int nw = nt / 32;
   // split-K partial sums of the narrow GEMMs (<= KSPLIT_MAX copies of an M x N output) and of the matvecs
   // (nw/2 copies of 2 x Co) share the adjacency region with the row statistics
@@ -613,6 +615,100 @@ CG_DEV void gcn_time(const float* XN, const float* adj, float* G, int C) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Adjacency expansor (Map2Adj.expansor, CISTGCN.py:165-170) as a per-column two-layer MLP.  The two N x N
+// convolutions mix the leading axis of the outer-product map o and every column of o is independent:
+//   out[:, c] = W4^T * PReLU(W0^T * o[:, c] + b0)        (weights k-major [k][pad8(N)], N = V or T <= 32)
+// so neither o nor the hidden map is materialised: a thread (or G adjacent lanes sharing a column: lane g owns the
+// output rows [g*R, (g+1)*R)) forms o[k, c] on the fly, keeps its hidden rows in registers and writes only the result.
+// With G > 1 the hidden column goes through `hs` ([NCOLS][N] floats) and a warp barrier.
+// ---------------------------------------------------------------------------------------------
+// NW floats (a multiple of 4) from a 16-byte aligned row in shared or global memory
+template <int NW>
+CG_DEV void load_row(const float* p, float (&w)[NW]) {
+#pragma unroll
+  for (int i = 0; i < NW / 4; ++i) {
+    const float4 v = *(reinterpret_cast<const float4*>(p) + i);
+    w[4 * i + 0] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+  }
+}
+
+template <int N, int NCOLS, int NT, int G, class OFN, class STORE>
+CG_DEV void expansor_fused(const float* __restrict__ w0, const float* __restrict__ b0, float a0,
+                           const float* __restrict__ w4, float* hs, OFN o_at, STORE store) {
+  static_assert(G == 1 || G == 2 || G == 4, "expansor_fused: lanes per column");
+  constexpr int NPW = (N + 7) & ~7;                 // row stride of the k-major weights
+  constexpr int R = (N + G - 1) / G;                // output rows per lane
+  const int lane = threadIdx.x & 31;
+  for (int it0 = threadIdx.x - lane; it0 < NCOLS * G; it0 += NT) {
+    const int item = it0 + lane;
+    const bool active = item < NCOLS * G;
+    const int col = active ? item / G : 0, g = item % G;
+    const int m0 = g * R;
+    float h[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) h[j] = 0.f;
+    if (active) {
+#pragma unroll 2
+      for (int k = 0; k < N; ++k) {
+        const float ok = o_at(k, col);
+        if constexpr (G == 1) {                    // whole weight row: warp-uniform 128-bit loads (rows are 32-byte aligned)
+          float wrow[NPW];
+          load_row<NPW>(w0 + k * NPW, wrow);
+#pragma unroll
+          for (int j = 0; j < N; ++j) h[j] = fmaf(wrow[j], ok, h[j]);
+        } else {
+          const float* wr = w0 + k * NPW + m0;
+#pragma unroll
+          for (int j = 0; j < R; ++j)
+            if (m0 + j < N) h[j] = fmaf(wr[j], ok, h[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+        if (m0 + j < N) h[j] = prelu(h[j] + b0[m0 + j], a0);
+    }
+    float o[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) o[j] = 0.f;
+    if constexpr (G == 1) {
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {              // h[k] must stay in registers: fully unrolled
+          float wrow[NPW];
+          load_row<NPW>(w4 + k * NPW, wrow);
+#pragma unroll
+          for (int j = 0; j < N; ++j) o[j] = fmaf(wrow[j], h[k], o[j]);
+        }
+      }
+    } else {
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if (m0 + j < N) hs[col * N + m0 + j] = h[j];
+      }
+      __syncwarp();
+      if (active) {
+        const float* hc = hs + col * N;
+#pragma unroll 2
+        for (int k = 0; k < N; ++k) {
+          const float hk = hc[k];
+          const float* wr = w4 + k * NPW + m0;
+#pragma unroll
+          for (int j = 0; j < R; ++j)
+            if (m0 + j < N) o[j] = fmaf(wr[j], hk, o[j]);
+        }
+      }
+      __syncwarp();
+    }
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+        if (m0 + j < N) store(m0 + j, col, o[j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 #ifndef CISTGCN_EMU
 // ---------------------------------------------------------------------------------------------
 // Tensor-core channel mix (512-thread CTAs): out(m, p) = sum_k W[m][k] * X[k][p] over the TV positions of the
@@ -759,9 +855,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_block_kernel(const
   constexpr int TV = T * V, TT = T * T, VV = V * V, VP = V | 1;   // VP: odd row stride of the transposed Adj_s
   constexpr int NW = NT / 32;
   constexpr int TNW = (TV % 4 == 0) ? 4 : 2;            // column vector width of the wide GEMMs
-  constexpr int TNS = (TT % 4 == 0) ? 4 : 2;            // ... of the joint-axis expansor (N = T*T)
   constexpr int VVP = (VV + 3) & ~3;                    // row stride of Adj_t and of its hidden map: V*V padded to a float4
-  constexpr int TNT = 4;                                // ... of the frame-axis expansor (N = V*V, rows padded to VVP)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int* d = a.d;
   const float* __restrict__ W = a.w;
@@ -1064,41 +1158,50 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_block_kernel(const
         dsp[i] = acc;
       }
       __syncthreads();
-      // ---------------- P8: space-domain outer product o[v'][t][q] = dsp[v'][t] * dseq[q][v']  (:187)
-      for (int i = tid; i < V * TT; i += NT) {
-        const int vq = i / TT, r = i - vq * TT, t = r / T, q = r - t * T;
-        ADJ[i] = dsp[vq * T + t] * dseq[q * V + vq];
-      }
-      __syncthreads();
       CG_STAMP(7);
-      // ---------------- P9: expansor over the joint axis -> Adj_s (kept as [t][q][v])  (:165-170)
-      {
-        const float* eb = P(CB_E0_B_S);
-        const float ea = P(CB_E0_A_S)[0];
-        const WideOp ops[1] = {{G(CB_E0_WT_S), RS(CB_E0_WT_S), ADJ, nullptr}};
-        gemm_wide_auto<TNS, TT, TT, NT, false, 1>(ops, pad8i(V), V, V, 0, ring, rb,
-          [&](int, int m, int n0, float (&v)[TNS]) {
-            const float bias = eb[m];
-#pragma unroll
-            for (int j = 0; j < TNS; ++j) v[j] = prelu(v[j] + bias, ea);
-            store_vec<TNS>(Bt + m * TT + n0, v);
-          });
-      }
-      __syncthreads();
-      {
+      // ---------------- P8-P9: space-domain outer product o[v'][t][q] = dsp[v'][t] * dseq[q][v'] (:187) and the expansor over
+      // the joint axis (:165-170), fused per column (t, q) -> Adj_s, kept as [t][q][v] with the odd row stride VP
+      if constexpr (TT * 2 > NT) {                            // enough columns to give every lane its own
         float* tp = a.tap_adj_s ? a.tap_adj_s + (size_t)b * V * TT : nullptr;
-        const WideOp ops[1] = {{G(CB_E4_WT_S), RS(CB_E4_WT_S), Bt, nullptr}};
-        gemm_wide_auto<TNS, TT, TT, NT, false, 1>(ops, pad8i(V), V, V, 0, ring, rb,
-          [&](int, int m, int n0, float (&v)[TNS]) {
+        expansor_fused<V, TT, NT, 1>(P(CB_E0_WT_S), P(CB_E0_B_S), P(CB_E0_A_S)[0], P(CB_E4_WT_S), Bt,
+          [&](int k, int col) { const int t = col / T, q = col - t * T; return dsp[k * T + t] * dseq[q * V + k]; },
+          [&](int m, int col, float val) { ADJ[col * VP + m] = val; if (tp) tp[m * TT + col] = val; });
+        __syncthreads();
+      } else {                                                // few columns (T*T = 100): materialise o and run the two mixes as GEMMs
+        constexpr int TNS = (TT % 4 == 0) ? 4 : 2;
+        for (int i = tid; i < V * TT; i += NT) {
+          const int vq = i / TT, r = i - vq * TT, t = r / T, q = r - t * T;
+          ADJ[i] = dsp[vq * T + t] * dseq[q * V + vq];
+        }
+        __syncthreads();
+        {
+          const float* eb = P(CB_E0_B_S);
+          const float ea = P(CB_E0_A_S)[0];
+          const WideOp ops[1] = {{G(CB_E0_WT_S), RS(CB_E0_WT_S), ADJ, nullptr}};
+          gemm_wide_auto<TNS, TT, TT, NT, false, 1>(ops, pad8i(V), V, V, 0, ring, rb,
+            [&](int, int m, int n0, float (&v)[TNS]) {
+              const float bias = eb[m];
 #pragma unroll
-            for (int j = 0; j < TNS; ++j) ADJ[(n0 + j) * VP + m] = v[j];
-            if (tp) {
+              for (int j = 0; j < TNS; ++j) v[j] = prelu(v[j] + bias, ea);
+              store_vec<TNS>(Bt + m * TT + n0, v);
+            });
+        }
+        __syncthreads();
+        {
+          float* tp = a.tap_adj_s ? a.tap_adj_s + (size_t)b * V * TT : nullptr;
+          const WideOp ops[1] = {{G(CB_E4_WT_S), RS(CB_E4_WT_S), Bt, nullptr}};
+          gemm_wide_auto<TNS, TT, TT, NT, false, 1>(ops, pad8i(V), V, V, 0, ring, rb,
+            [&](int, int m, int n0, float (&v)[TNS]) {
 #pragma unroll
-              for (int j = 0; j < TNS; ++j) tp[m * TT + n0 + j] = v[j];
-            }
-          });
+              for (int j = 0; j < TNS; ++j) ADJ[(n0 + j) * VP + m] = v[j];
+              if (tp) {
+#pragma unroll
+                for (int j = 0; j < TNS; ++j) tp[m * TT + n0 + j] = v[j];
+              }
+            });
+        }
+        __syncthreads();
       }
-      __syncthreads();
     } else {
       const float* as = W + d[CB_ADJ_S];                      // static (V,T,T) -> [t][q][v]
       for (int i = tid; i < V * TT; i += NT) { const int v = i / TT, r = i - v * TT; ADJ[r * VP + v] = __ldg(as + i); }
@@ -1113,36 +1216,15 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_block_kernel(const
     CG_STAMP(9);
     // ---------------- P11: time-domain outer product + expansor over the frame axis -> Adj_t
     if (interp) {
-      for (int i = tid; i < T * VVP; i += NT) {               // o[t'][v][w] = dsp[v][t'] * dseq[t'][w]
-        const int tq = i / VVP, r = i - tq * VVP, v = r / V, w = r - v * V;
-        ADJ[i] = r < VV ? dsp[TV + v * T + tq] * dseq[TV + tq * V + w] : 0.f;
-      }
-      __syncthreads();
-      {
-        const float* eb = P(CB_E0_B_T);
-        const float ea = P(CB_E0_A_T)[0];
-        const WideOp ops[1] = {{G(CB_E0_WT_T), RS(CB_E0_WT_T), ADJ, nullptr}};
-        gemm_wide_auto<TNT, VVP, VVP, NT, false, 1>(ops, pad8i(T), T, T, 0, ring, rb,
-          [&](int, int m, int n0, float (&v)[TNT]) {
-            const float bias = eb[m];
-#pragma unroll
-            for (int j = 0; j < TNT; ++j) v[j] = prelu(v[j] + bias, ea);
-            store_vec<TNT>(Bt + m * VVP + n0, v);
-          });
-      }
-      __syncthreads();
-      {
-        float* tp = a.tap_adj_t ? a.tap_adj_t + (size_t)b * T * VV : nullptr;
-        const WideOp ops[1] = {{G(CB_E4_WT_T), RS(CB_E4_WT_T), Bt, nullptr}};
-        gemm_wide_auto<TNT, VVP, VVP, NT, false, 1>(ops, pad8i(T), T, T, 0, ring, rb,
-          [&](int, int m, int n0, float (&v)[TNT]) {
-            store_vec<TNT>(ADJ + m * VVP + n0, v);
-            if (tp) {
-#pragma unroll
-              for (int j = 0; j < TNT; ++j)
-                if (n0 + j < VV) tp[m * VV + n0 + j] = v[j];
-            }
-          });
+      // o[t'][v][w] = dsp[v][t'] * dseq[t'][w] and the expansor over the frame axis, fused per column (v, w)
+      constexpr int GT = (VV * 4 <= NT) ? 4 : ((VV * 2 <= NT) ? 2 : 1);
+      float* tp = a.tap_adj_t ? a.tap_adj_t + (size_t)b * T * VV : nullptr;
+      expansor_fused<T, VV, NT, GT>(P(CB_E0_WT_T), P(CB_E0_B_T), P(CB_E0_A_T)[0], P(CB_E4_WT_T), Bt,
+        [&](int k, int col) { const int v = col / V, w = col - v * V; return dsp[TV + v * T + k] * dseq[TV + k * V + w]; },
+        [&](int m, int col, float val) { ADJ[m * VVP + col] = val; if (tp) tp[m * VV + col] = val; });
+      if constexpr (VVP > VV) {                               // padding columns of the float4-aligned rows
+        constexpr int PADC = VVP - VV;
+        for (int i = tid; i < T * PADC; i += NT) ADJ[(i / PADC) * VVP + VV + i % PADC] = 0.f;
       }
     } else {
       const float* at = W + d[CB_ADJ_T];
