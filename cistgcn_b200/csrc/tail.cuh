@@ -68,16 +68,27 @@ __global__ void __launch_bounds__(TAIL_NT, 3) tail_kernel(const TailArgs a) {
     for (int i = tid; i < To; i += NT) fsum[i] = 0.f;
     __syncthreads();
     // ---- context_conv1 (max over all positions), context_conv3 (mean), context_conv2 (max over columns)
+    // context_conv1 is a per-channel scale of the ONE input map followed by BN + PReLU: g_c(z) = PReLU(s_c z + b_c) is
+    // monotone in z (slope a >= 0) or V-shaped (a < 0), so its maximum over the positions is attained where z is
+    // smallest or largest -- exactly, rounding included.  Only the extremes of z are needed, not a pass per channel.
+    {
+      float lo = INFINITY, hi = -INFINITY;
+      for (int i = tid; i < NZ; i += NT) { const float zv = z[i]; lo = fminf(lo, zv); hi = fmaxf(hi, zv); }
+      lo = -warp_max(-lo);
+      hi = warp_max(hi);
+      if ((tid & 31) == 0) { yv[tid >> 5] = lo; yv[NT / 32 + (tid >> 5)] = hi; }      // yv is free until the next phase
+    }
+    __syncthreads();
     {
       const int ch = tid % H, sub = tid / H, nsub = NT / H;      // H = 64 -> 4 position slices per channel
+      float zlo = yv[0], zhi = yv[NT / 32];
+#pragma unroll
+      for (int w = 1; w < NT / 32; ++w) { zlo = fminf(zlo, yv[w]); zhi = fmaxf(zhi, yv[NT / 32 + w]); }
       const float s1 = W[t[CT_C1_S] + ch], b1 = W[t[CT_C1_B] + ch], a1 = W[t[CT_C1_A]];
       const float s3 = W[t[CT_C3_S] + ch], b3 = W[t[CT_C3_B] + ch], a3 = W[t[CT_C3_A]];
-      float mx = -INFINITY, sm = 0.f;
-      for (int i = sub; i < NZ; i += nsub) {
-        const float zv = z[i];
-        mx = fmaxf(mx, prelu(fmaf(s1, zv, b1), a1));
-        sm += prelu(fmaf(s3, zv, b3), a3);
-      }
+      const float mx = fmaxf(prelu(fmaf(s1, zlo, b1), a1), prelu(fmaf(s1, zhi, b1), a1));
+      float sm = 0.f;
+      for (int i = sub; i < NZ; i += nsub) sm += prelu(fmaf(s3, z[i], b3), a3);
       float mx2 = -INFINITY;
       const float b2 = W[t[CT_C2_B] + ch], a2 = W[t[CT_C2_A]];
       const float* w2 = W + t[CT_C2_WT] + ch;
