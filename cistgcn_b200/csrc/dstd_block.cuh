@@ -48,6 +48,7 @@ struct DstdArgs {
   int o_xn, o_ab, tile, o_adj, o_sm, o_ring, ring_floats, smem_floats;
   int scratch_floats;    // capacity of the split-K partial scratch (the adjacency region)
   // tensor-core channel mixes (tc_gemm): staging operand [2 terms][tc_kc chunks][256 positions][16 B] + mbarrier / TMEM slot
+  int g0_stage, o_gbar;  // gate-conv weights streamed by cp.async.bulk into the (idle) work tiles at the start of every sample
   int tc, o_stage, tc_kc, o_tcmisc, o_img;     // o_img: one weight-image buffer, refilled by cp.async.bulk between uses
   long long* phase_clocks;   // optional debug: first CTA / thread 0 stamps clock64() at phase boundaries
   int stamp_iter;            // ... of its stamp_iter-th sample (0 = first: cold caches)
@@ -108,7 +109,7 @@ inline bool dstd_plan(DstdArgs& a, int nt, int max_smem_floats, bool tc_allowed 
   a.o_sm = a.o_adj + adj;
   a.scratch_floats = adj;
   const int sm = pad4i(2 + 2 * T) + imax(pad4i(2 * Cg * V), pad4i(2 * Ch * V) + pad4i(2 * Ch * T)) + 3 * pad4i(2 * Co) +
-                 2 * pad4i(2 * TV) + 2 * pad4i(Co) + pad4i(Hs);
+                 2 * pad4i(2 * TV) + 2 * pad4i(Co) + pad4i(Hs) + 4;       // + one mbarrier (g0_stage)
   a.o_ring = a.o_sm + sm;
   const int widest = imax(pad8i(4 * Ch), imax(Cop, pad8i(2 * Cg)));      // longest streamed row
   const int vectors[] = {CB_GN_S, CB_GN_B, CB_G0_B, CB_G0_A, CB_G4_B, CB_G4_A, CB_M0_B, CB_M0_A, CB_A0_B, CB_A0_A,
@@ -182,6 +183,13 @@ inline bool dstd_plan(DstdArgs& a, int nt, int max_smem_floats, bool tc_allowed 
     if (ok && cur <= max_smem_floats) break;                     // else: plan again without the tensor-core path
   }
   if (a.tc && cur < 30 * 1024) cur = 30 * 1024;                  // > half an SM: the CTA must own all 512 TMEM columns
+  a.o_gbar = a.o_ring - 4;
+  a.g0_stage = 0;
+#ifndef CISTGCN_EMU
+  // gate conv (T,1) weights that found no room: the two work tiles are idle until Map2Adj starts, so the weights
+  // are bulk-copied into them at the top of every sample and the conv runs the resident-operand path
+  a.g0_stage = a.res[CB_G0_WT] < 0 && d[CB_IN_MODE] != 1 && a.wsz[CB_G0_WT] <= a.o_adj - a.o_ab;
+#endif
   a.smem_floats = cur;
   return ok && cur <= max_smem_floats;
 }
@@ -899,6 +907,10 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_block_kernel(const
   cp_async_commit();
   cp_async_wait_all();
 #ifndef CISTGCN_EMU
+  const bool g0_stage = a.g0_stage != 0;
+  const uint32_t gbar = smem_u32(smem + a.o_gbar);
+  uint32_t gpar = 0;
+  if (g0_stage && tid == 0) { mbar_init(gbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   TcState tc = {0, 0, 0, 0, 0, nullptr, nullptr, 0, nullptr};
   const float* tc_first = nullptr;       // first image a sample needs, and its size
   int tc_first_floats = 0;
@@ -934,6 +946,12 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_block_kernel(const
 
   for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
     CG_STAMP(0);
+#ifndef CISTGCN_EMU
+    if (g0_stage && tid == 0) {           // A | B are idle until P5 (the previous sample's last read is behind a barrier)
+      mbar_expect_tx(gbar, (uint32_t)a.wsz[CB_G0_WT] * 4u);
+      bulk_g2s(smem_u32(A), W + d[CB_G0_WT], (uint32_t)a.wsz[CB_G0_WT] * 4u, gbar);
+    }
+#endif
     // ---------------- P1: load + global_norm (:375); block 0 builds the 10 features (:568-577)
     if (d[CB_IN_MODE] == 1) {
       const float* src = a.in + (size_t)b * d[CB_IN_SB];
@@ -1058,8 +1076,14 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_block_kernel(const
       const float* gb = P(CB_G0_B);
       const float* ga = P(CB_G0_A);
       auto epi = [&](int m, int v, float acc) { h1[m * V + v] = prelu(acc + gb[m], ga[m / Cg]); };
-      if (RS(CB_G0_WT))
-        gemm_narrow_auto<V, false, NT>(G(CB_G0_WT), RS(CB_G0_WT), pad8i(2 * Cg), 2 * Cg, Ci * T, XN, T, TV, partial, a.scratch_floats, ring, rb, epi);
+#ifndef CISTGCN_EMU
+      if (g0_stage) { mbar_wait(gbar, gpar); gpar ^= 1; }
+      const float* g0s = g0_stage ? A : RS(CB_G0_WT);
+#else
+      const float* g0s = RS(CB_G0_WT);
+#endif
+      if (g0s)
+        gemm_narrow_auto<V, false, NT>(G(CB_G0_WT), g0s, pad8i(2 * Cg), 2 * Cg, Ci * T, XN, T, TV, partial, a.scratch_floats, ring, rb, epi);
       else          // not resident: deep-batched L2 reads; the (still unused) work tiles host the split-K partials
         gate_conv_l2<V, NT>(G(CB_G0_WT), pad8i(2 * Cg), 2 * Cg, Ci * T, XN, A, a.o_adj - a.o_ab, epi);
     }
@@ -1412,6 +1436,9 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_block_kernel(const
         }
       }
     }
+#ifndef CISTGCN_EMU
+    if (g0_stage) fence_proxy_async();     // generic reads of the work tiles before the next sample's bulk copy into them
+#endif
     __syncthreads();
     CG_STAMP(15);
   }
