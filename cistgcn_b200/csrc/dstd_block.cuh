@@ -443,6 +443,109 @@ CG_DEV void gemm_narrow(const float* __restrict__ wg_, const float* ws, int Mp, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The four collapsing convolutions of Map2Adj (time_compress.3 and joint_compress.3 of both domains, CISTGCN.py:141-150)
+// in ONE phase: the warps are split over the four problems and the K range of a problem over its warps, so all warps
+// work at once and the phase costs one barrier and one reduction instead of four of each.
+//   problem 2L   : out(m, v) = sum_{c,t} W[(c,t)][m] * map_tc[L][c][t][v]      (N = V, contiguous rows)
+//   problem 2L+1 : out(m, t) = sum_{c,v} W[(c,v)][m] * map_jc[L][c][t][v]      (N = T, strided rows)
+// Needs resident weights, ceil(Ch/8) row tiles per warp (Ch <= 8 * lanes-per-row-tile), partial >= (NT/128) * 2*Ch*(V+T).
+// ---------------------------------------------------------------------------------------------
+template <int T, int V>
+struct Collapse4 {
+  static constexpr int TNA = (V % 2 == 0) ? 2 : 1, NPA = V / TNA, MSA = 32 / NPA;     // contiguous problems: lane -> (row tile, column pair)
+  static constexpr int NPB = T, MSB = 32 / NPB;                                         // strided problems: lane -> (row tile, column)
+  static_assert(V <= 32 * TNA && T <= 32, "Collapse4: a row must fit a warp");
+  CG_DEV static bool fits(int Ch, int nt, int partial_cap) {
+    const int mt = (Ch + 7) / 8;
+    return (nt / 32) % 4 == 0 && mt <= MSA && mt <= MSB && partial_cap >= (nt / 128) * 2 * Ch * (V + T);
+  }
+};
+
+template <int T, int V, int NT, class EPI>
+CG_DEV void collapse4(const float* w_tc0, const float* w_jc0, const float* w_tc1, const float* w_jc1, int Ch,
+                      const float* maps, int tile, float* partial, EPI epi) {
+  using C4 = Collapse4<T, V>;
+  constexpr int TV = T * V, KSW = NT / 128;                  // warps per problem = split-K fan-out
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int prob = warp / KSW, ks = warp - prob * KSW, L = prob >> 1;
+  const int Mp = pad8i(Ch), mtiles = (Ch + 7) / 8;
+  const int szA = Ch * V, szB = Ch * T;                      // outputs of a contiguous / strided problem
+  const int pbase = KSW * ((prob >> 1) * (szA + szB) + (prob & 1) * szA);
+  const float* tl = maps + L * tile;
+  float acc[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
+  if ((prob & 1) == 0) {
+    const float* wc = L ? w_tc1 : w_tc0;
+    const int msub = lane / C4::NPA, np = lane - msub * C4::NPA;
+    const bool active = lane < C4::MSA * C4::NPA && msub < mtiles;
+    const int m0 = active ? msub * 8 : 0, n0 = active ? np * C4::TNA : 0;
+    const int K = Ch * T, r0 = (K * ks) / KSW, r1 = (K * (ks + 1)) / KSW;
+    if (active) {
+      const float* wp = wc + r0 * Mp + m0;
+      const float* xp = tl + r0 * V + n0;
+#pragma unroll 4
+      for (int r = r0; r < r1; ++r) {
+        float w[8], x[C4::TNA];
+        lds_vec<8>(wp, w);
+        lds_vec<C4::TNA>(xp, x);
+        wp += Mp;
+        xp += V;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < C4::TNA; ++j) acc[i][j] = fmaf(w[i], x[j], acc[i][j]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (m0 + i < Ch) {
+#pragma unroll
+          for (int j = 0; j < C4::TNA; ++j) partial[pbase + (ks * Ch + m0 + i) * V + n0 + j] = acc[i][j];
+        }
+    }
+  } else {
+    const float* wc = L ? w_jc1 : w_jc0;
+    const float* X = tl + Ch * TV;
+    const int msub = lane / C4::NPB, np = lane - msub * C4::NPB;
+    const bool active = lane < C4::MSB * C4::NPB && msub < mtiles;
+    const int m0 = active ? msub * 8 : 0, n0 = active ? np : 0;
+    const int K = Ch * V, r0 = (K * ks) / KSW, r1 = (K * (ks + 1)) / KSW;
+    if (active) {
+      const float* wp = wc + r0 * Mp + m0;
+      int cc = r0 / V, rr = r0 - cc * V;
+      const float* xp = X + cc * TV + rr + n0 * V;
+#pragma unroll 4
+      for (int r = r0; r < r1; ++r) {
+        float w[8];
+        lds_vec<8>(wp, w);
+        const float x = *xp;
+        wp += Mp;
+        ++xp;
+        if (++rr == V) { rr = 0; xp += TV - V; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i][0] = fmaf(w[i], x, acc[i][0]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (m0 + i < Ch) partial[pbase + (ks * Ch + m0 + i) * T + n0] = acc[i][0];
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 2 * (szA + szB); idx += NT) {
+    const int Lq = idx / (szA + szB), r = idx - Lq * (szA + szB);
+    const bool strided = r >= szA;
+    const int o = strided ? r - szA : r, sz = strided ? szB : szA;
+    const float* pp = partial + KSW * (Lq * (szA + szB) + (strided ? szA : 0)) + o;
+    float sum = 0.f;
+#pragma unroll
+    for (int q = 0; q < KSW; ++q) sum += pp[q * sz];
+    const int n = strided ? T : V;
+    epi(2 * Lq + (strided ? 1 : 0), o / n, o % n, sum);
+  }
+  __syncthreads();
+}
+
 template <int N, bool STRIDED, int NT, class EPI>
 CG_DEV void gemm_narrow_auto(const float* __restrict__ wg_, const float* ws, int Mp, int M, int K,
                              const float* X, int R, int CS, float* partial, int partial_cap, float* ring, int rb, EPI epi) {
@@ -1149,6 +1252,16 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_block_kernel(const
       __syncthreads();
       CG_STAMP(5);
       // ---------------- P6: collapsing convs (T,1) / (1,V) + BN  (:141-142, 149-150)
+      if (RS(CB_TC3_WT_S) && RS(CB_JC3_WT_S) && RS(CB_TC3_WT_T) && RS(CB_JC3_WT_T) && Collapse4<T, V>::fits(Ch, NT, a.scratch_floats)) {
+        const float* tb0 = P(CB_TC3_B_S); const float* tb1 = P(CB_TC3_B_T);
+        const float* jb0 = P(CB_JC3_B_S); const float* jb1 = P(CB_JC3_B_T);
+        collapse4<T, V, NT>(RS(CB_TC3_WT_S), RS(CB_JC3_WT_S), RS(CB_TC3_WT_T), RS(CB_JC3_WT_T), Ch, A, a.tile, partial,
+          [&](int prob, int m, int n, float acc) {
+            const int L = prob >> 1;
+            if (prob & 1) dspp[L * Ch * T + m * T + n] = acc + (L ? jb1 : jb0)[m];
+            else dseqp[L * Ch * V + m * V + n] = acc + (L ? tb1 : tb0)[m];
+          });
+      } else {
 #pragma unroll
       for (int L = 0; L < 2; ++L) {
         const float* tl = A + L * a.tile;
@@ -1160,6 +1273,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_block_kernel(const
                                 [&](int m, int v, float acc) { dq[m * V + v] = acc + tb[m]; });
         gemm_narrow_auto<T, true, NT>(G(CB_JC3_WT_S + L), RS(CB_JC3_WT_S + L), pad8i(Ch), Ch, Ch * V, tl + Ch * TV, V, TV, partial, a.scratch_floats, ring, rb,
                                 [&](int m, int t, float acc) { dp[m * T + t] = acc + jb[m]; });
+      }
       }
       CG_STAMP(6);
       // ---------------- P7: dim_seq / dim_space (last 1x1 of each compress branch)  (:144, 152)
