@@ -654,6 +654,50 @@ CG_DEV void gate_matvec(const float* wmat, int Mp, int M, int K1, const float* x
 }
 
 // ---------------------------------------------------------------------------------------------
+// Last two layers of a gate MLP (map_{s,t}.0 + BN + PReLU, map_{s,t}.4; CISTGCN.py:341-352) for ONE gate by ONE warp:
+// both are small (Co x (Co + 2 + 2T) and Co x Co), nothing else needs their result before the tcn epilogue, so warps
+// 0 / 1 run them with warp-level synchronisation only while the rest of the CTA moves on to Map2Adj.  Lanes own output
+// columns (coalesced weight rows, fixed-trip batches of 16 independent loads as in gate_matvec).
+// ---------------------------------------------------------------------------------------------
+CG_DEV float warp_matvec_col(const float* wgt, int Mp, int mc, int K1, const float* xa, int K2, const float* xb) {
+  float acc = 0.f;
+  for (int k0 = 0; k0 < K1; k0 += 16) {
+    float w[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) w[j] = wgt[(size_t)imin(k0 + j, K1 - 1) * Mp + mc];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc = fmaf(w[j], (k0 + j < K1) ? xa[k0 + j] : 0.f, acc);
+  }
+  for (int k0 = 0; k0 < K2; k0 += 8) {
+    float w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = wgt[(size_t)(K1 + imin(k0 + j, K2 - 1)) * Mp + mc];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(w[j], (k0 + j < K2) ? xb[k0 + j] : 0.f, acc);
+  }
+  return acc;
+}
+
+template <class EPI>
+CG_DEV void gate_mlp_tail(int g, const float* m0w, const float* m0b, float m0a, const float* m4w, int Mp, int Co, int nstats,
+                          const float* h2g, const float* stats, float* zgg, EPI epi) {
+  const int lane = threadIdx.x & 31;
+  const float* w0 = m0w + (size_t)g * (Co + nstats) * Mp;
+  for (int mb = 0; mb < Co; mb += 32) {
+    const int m = mb + lane, mc = m < Co ? m : Co - 1;
+    const float acc = warp_matvec_col(w0, Mp, mc, Co, h2g, nstats, stats);
+    if (m < Co) zgg[m] = prelu(acc + m0b[g * Co + m], m0a);
+  }
+  __syncwarp();
+  const float* w4 = m4w + (size_t)g * Co * Mp;
+  for (int mb = 0; mb < Co; mb += 32) {
+    const int m = mb + lane, mc = m < Co ? m : Co - 1;
+    const float acc = warp_matvec_col(w4, Mp, mc, Co, zgg, 0, nullptr);
+    if (m < Co) epi(m, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // adjacency products (ConvTemporalGraphical, CISTGCN.py:110,117,123)
 // ---------------------------------------------------------------------------------------------
 // "space" domain: g1[c][q][v] = sum_t XN[c][t][v] * Adj_s[v][t][q], Adj_s held as adjT[(t*T+q)*VP + v], VP = V|1.
@@ -1197,16 +1241,16 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_block_kernel(const
       const float* a4 = P(CB_G4_A);
       gate_matvec<NT>(P(CB_G4_WT), Cop, Co, Cg * V, h1, Cg * V, 0, nullptr, partial,
                       [&](int g, int o, float acc) { h2[g * Co + o] = prelu(acc + b4[g * Co + o], a4[g]); });
-      const float* b0 = P(CB_M0_B);
-      const float* a0 = P(CB_M0_A);
-      gate_matvec<NT>(P(CB_M0_WT), Cop, Co, Co, h2, Co, 2 + 2 * T, stats, partial,
-                      [&](int g, int o, float acc) { zg[g * Co + o] = prelu(acc + b0[g * Co + o], a0[g]); });
-      gate_matvec<NT>(P(CB_M4_WT), Cop, Co, Co, zg, Co, 0, nullptr, partial,
-                      [&](int g, int o, float acc) {
+      // map_{s,t}: one warp per gate, no block barrier; the other warps go on to Map2Adj (wg is needed in P13 only)
+      if (warp < 2) {
+        const int g = warp;
+        gate_mlp_tail(g, P(CB_M0_WT), P(CB_M0_B), P(CB_M0_A)[g], P(CB_M4_WT), Cop, Co, 2 + 2 * T, h2 + g * Co, stats, zg + g * Co,
+                      [&](int o, float acc) {
                         wg[g * Co + o] = acc;
                         float* tp = g == 0 ? a.tap_w1 : a.tap_w2;
                         if (tp) tp[(size_t)b * Co + o] = acc;
                       });
+      }
     }
     CG_STAMP(4);
 
