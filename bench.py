@@ -1,13 +1,16 @@
 #!/usr/bin/env python
-"""bench.py -- sequences/sec of the CIST-GCN forward hot path (BASELINE.json metric).
+"""bench.py -- sequences/sec of the CIST-GCN hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N --steps K --warmup W] [--embed 32 --joints 22 --batch 65536]
-    python bench.py --impl reference ...      # the reference's own CPU implementation (oracle port)
+    python bench.py [--gpus N --steps K --warmup W]                      # configs[1]: E=32, V=22, batch 65536 / GPU, fp32
+    python bench.py --embed 16 | --embed 8 --batch 256                   # configs[1] (E=16) / configs[0] shape on the GPU
+    python bench.py --mode mpjpe --embed 64 --joints 18 --batch 262144 --scaling strong --gpus N      # configs[2]
+    python bench.py --impl reference ...                                 # the reference's own CPU implementation
 
-A "step" is one forward pass over one batch of synthetic H36M-shaped sequences (configs[1] of
-BASELINE.json: E=32, 22 joints, 10 -> 25 frames, batch 65536 per GPU, fp32).  N > 1: launched by
-torchrun, one rank per GPU, the batch is sharded by rank ("weak": per-GPU work is fixed) and no
-collective is on the data path; only the timing is max-reduced over ranks.  Prints ONE JSON line.
+A "step" is one pass of the path over one batch of synthetic sequences.  --mode forward: CISTGCN.forward;
+--mode mpjpe: forward + losses.mpjpe (fused per-frame sums; with N > 1 the 208-byte sums are all-reduced over NCCL
+inside the timed region and both the `[]` and `(0, 2)` reductions are derived).  N > 1: launched by torchrun, one rank
+per GPU.  --scaling weak: every rank owns --batch sequences; strong: --batch is the GLOBAL batch, sharded by rank.
+No collective is on the forward's data path.  Prints ONE JSON line.
 """
 import argparse
 import ctypes
@@ -22,7 +25,6 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "sequences/sec CIST-GCN forward (H36M 10->25 frames, 22 joints)"
 UNIT = "sequences/s"
 FP32_FMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # CUDA-core FP32 FMA peak at max SM clock (74.5)
 # algorithmic FLOPs / sequence (2*MAC of conv+mm+bmm, measured on the reference)
@@ -31,9 +33,35 @@ FLOPS_PER_SEQ = {(22, 8): 37.06e6, (22, 16): 40.45e6, (22, 32): 52.22e6, (22, 64
 FPN_FLOPS_PER_SEQ = {22: 29.5e6, 18: 29.5e6 * 18 / 22}
 
 
+def metric_name(V, mode):
+    what = {"forward": "forward", "mpjpe": "forward + MPJPE eval"}[mode]
+    shape = "H36M 10->25 frames, 22 joints" if V == 22 else f"AMASS 10->25 frames, {V} joints"
+    return f"sequences/sec CIST-GCN {what} ({shape})"
+
+
 def bytes_per_seq(V, E, s=4):
     """one-kernel-per-block compulsory HBM traffic per sequence."""
     return s * V * (80 * E + 2683)
+
+
+def stage_bytes_per_seq(E, V, T=10, To=25):
+    """Compulsory HBM bytes per sequence of every kernel kind of THIS partition: each kernel
+    reads its inputs once and writes its outputs once, weights amortised over the batch.  Keys = profile kind names."""
+    blocks = [(10, E, T, V, True)] + [(E, E, T, V, False)] * 3 + [(E, 10, T, V, False), (3, 3, V, To, False)]
+    red = adj = mix = fused = 0
+    for ci, co, t, v, raw in blocks:
+        ch, cg, tv = ci // 2, max(co // 2, 1), t * v
+        x_in = 3 * tv if raw else ci * tv
+        rec = (2 + 2 * t) + 2 * cg * v + 2 * ch * v + 2 * ch * t
+        aj = 2 * co + v * t * t + t * v * v
+        red += x_in + rec
+        adj += rec + aj
+        mix += x_in + aj + co * tv
+        fused += x_in + co * tv
+    tv = T * V
+    return {"dstd_reduce_kernel": 4 * red, "dstd_adj_kernel": 4 * adj, "dstd_mix_kernel": 4 * mix,
+            "dstd_block_kernel": 4 * fused, "fpn_kernel": 4 * (10 * tv + 3 * To * V),
+            "tail_kernel": 4 * (3 * tv + 3 * 3 * To * V), "mpjpe_kernel": 4 * 2 * 3 * To * V}
 
 
 def measured_peaks():
@@ -97,64 +125,93 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_baseline(E, V, budget_s, batch=256):
-    """Oracle port (oracle/cistgcn_oracle.py = the reference's algorithm on PyTorch CPU kernels) timed on
-    this box's host cores on a bounded sample of the same workload."""
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the UNMODIFIED reference module (oracle/_ref, vendored by build(); kind "reference") when it is there,
+# otherwise the oracle port (kind "port").  The only places bench.py touches oracle/.
+# ---------------------------------------------------------------------------------------------------------------
+def _cpu_forward_fn(E, V, mode):
+    """(callable(x, target) -> None, kind, description).  Reference module in eval mode under no_grad, fp32."""
     import torch
-    import types
-    from cistgcn_b200 import CISTGCN
+    from oracle import ref_loader
+    if ref_loader.available():
+        ref = ref_loader.build(E, V)                              # torch.manual_seed(0) + reference constructor
+        def mpjpe(pred, target):                                  # losses.py:57-60 restated (SURVEY.md App. D)
+            return torch.mean(torch.norm(pred - target, 2, dim=-1), [])
+        def fn(x, tgt):
+            with torch.no_grad():
+                pred = ref(x)[0]
+                if mode == "mpjpe":
+                    mpjpe(pred, tgt)
+        return fn, "reference", f"unmodified reference CISTGCN module ({ref_loader.which()} copy), eval, no_grad"
     from oracle import cistgcn_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     model = _make_model(E, V)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     cfg = O.OracleConfig(joints=V, input_gcn=[E] * 4)
-    x, _ = O.synth_inputs(batch, cfg)
-    with torch.no_grad():
-        for _ in range(2):
-            O.forward(sd, cfg, x)
-        times, t_end = [], time.time() + budget_s
-        while len(times) < 3 or (time.time() < t_end and len(times) < 200):
-            t0 = time.perf_counter()
-            O.forward(sd, cfg, x)
-            times.append(time.perf_counter() - t0)
+    def fn(x, tgt):
+        with torch.no_grad():
+            pred = O.forward(sd, cfg, x)
+            if mode == "mpjpe":
+                O.mpjpe(pred, tgt)
+    return fn, "port", "oracle port of the reference algorithm (reference copy not vendored), eval, no_grad"
+
+
+def cpu_baseline(E, V, mode, budget_s, batch=256):
+    """The reference on this box's host cores, on a bounded sample of the same workload."""
+    import torch
+    from cistgcn_b200.synth import synth_inputs
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    fn, kind, what = _cpu_forward_fn(E, V, mode)
+    x, tgt = synth_inputs(batch, V)
+    for _ in range(2):
+        fn(x, tgt)
+    times, t_end = [], time.time() + budget_s
+    while len(times) < 3 or (time.time() < t_end and len(times) < 200):
+        t0 = time.perf_counter()
+        fn(x, tgt)
+        times.append(time.perf_counter() - t0)
     med = statistics.median(times)
-    return {"value": batch / med, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{len(times)} forwards of batch {batch} (E={E}, V={V}, fp32, eval), median; "
+    return {"value": batch / med, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{len(times)} passes over batch {batch} (E={E}, V={V}, fp32, {mode}), median; {what}; "
                       f"{torch.get_num_threads()} torch threads"}
 
 
 def _make_model(E, V):
-    import types
     import torch
     from cistgcn_b200 import CISTGCN
-    ns = types.SimpleNamespace
-    mp = ns(input_n=10, output_n=25, joints=V, n_txcnn_layers=4, txc_kernel_size=3, reduction=8, hidden_dim=64,
-            input_gcn=ns(model_complexity=[E] * 4, interpretable=[True] * 5),
-            output_gcn=ns(model_complexity=[3], interpretable=[True]), clipping=15)
+    from cistgcn_b200.synth import make_opt
+    opt = make_opt(E, V)
     torch.manual_seed(0)
-    return CISTGCN(ns(model_params=mp), ns(dropout=0.1)).eval()
+    return CISTGCN(opt.architecture_config, opt.learning_config).eval()
+
+
+def workload_name(args, world):
+    E, V = args.embed, args.joints
+    shape = f"{'H36M' if V == 22 else 'AMASS'} shape (10 in / 25 out frames, {V} joints x 3)"
+    what = "forward" if args.mode == "forward" else "forward + MPJPE eval"
+    if args.scaling == "strong":
+        bs = f"global batch {args.batch} sharded over {world} GPU(s)"
+    else:
+        bs = f"batch {args.batch} per GPU"
+    return f"CISTGCN embed={E} {what}, {shape}, {bs}, fp32, random-init weights"
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the Python
-    reference package cannot travel to the GPU box).  Rank 0 alone works; other ranks exit 0."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores.
+    Rank 0 alone works; other ranks exit 0."""
     if rank != 0:
         return
     import torch
-    from oracle import cistgcn_oracle as O
+    from cistgcn_b200.synth import synth_inputs
     E, V = args.embed, args.joints
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    model = _make_model(E, V)
-    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
-    cfg = O.OracleConfig(joints=V, input_gcn=[E] * 4)
+    fn, kind, what = _cpu_forward_fn(E, V, args.mode)
     step_seqs, sub = 1024, 256                       # one step = a bounded 1024-sequence sample, eval batch 256
-    x, _ = O.synth_inputs(step_seqs, cfg)
+    x, tgt = synth_inputs(step_seqs, V)
     def step():
-        with torch.no_grad():
-            for i in range(0, step_seqs, sub):
-                O.forward(sd, cfg, x[i:i + sub])
+        for i in range(0, step_seqs, sub):
+            fn(x[i:i + sub], tgt[i:i + sub])
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -162,14 +219,13 @@ def run_reference(args, rank, world):
         step()
     dt = time.perf_counter() - t0
     val = step_seqs * args.steps / dt
-    sample = f"{args.steps} steps x {step_seqs} sequences (batches of {sub}), E={E}, V={V}, fp32 eval, {cores} threads"
+    sample = f"{args.steps} steps x {step_seqs} sequences (batches of {sub}), E={E}, V={V}, fp32 eval, {args.mode}; {what}; {cores} threads"
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": metric_name(V, args.mode), "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"CISTGCN embed={E} forward, H36M shape (10 in / 25 out, {V} joints), fp32; "
-                               f"CPU sample of {step_seqs} sequences per step"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(args, world) + f"; CPU sample of {step_seqs} sequences per step"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -178,9 +234,11 @@ def run_native(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from cistgcn_b200 import _cabi
-    from oracle import cistgcn_oracle as O
+    from cistgcn_b200.dist import shard_bounds
+    from cistgcn_b200.synth import synth_inputs
 
-    E, V, B = args.embed, args.joints, args.batch
+    E, V = args.embed, args.joints
+    mode = args.mode
     # library chatter on stdout (e.g. the "NCCL version" banner) goes to stderr: stdout carries the ONE JSON line
     sys.stdout.flush()
     saved_stdout = os.dup(1)
@@ -190,15 +248,22 @@ def run_native(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _cabi.lib()                                   # fails loudly if the extension is missing
-    _cabi.check(lib.cistgcn_set_fpn_path(int(os.environ.get("CISTGCN_BENCH_FPN_PATH", "0"))), "cistgcn_set_fpn_path", lib)
     model = _make_model(E, V).to(dev)
-    cfg = O.OracleConfig(joints=V, input_gcn=[E] * 4)
-    # every rank owns its own shard of the global batch (different seed per rank); no data-path collective
-    x_host, _ = O.synth_inputs(B, cfg, seed=123 + rank)
+    model.kernel_flags = int(os.environ.get("CISTGCN_BENCH_FLAGS", "0"))
+    # weak: every rank owns its own --batch sequences; strong: --batch is the global batch, sharded by rank
+    if args.scaling == "strong":
+        lo, hi = shard_bounds(args.batch, rank, world)
+        B, global_B = hi - lo, args.batch
+    else:
+        B, global_B = args.batch, args.batch * world
+    x_host, t_host = synth_inputs(B, V, seed=123 + rank)
     x_pin = x_host.pin_memory()
     pred_pin = torch.empty(B, 25, V, 3).pin_memory()
     x = x_pin.to(dev)
-    in_bytes, out_bytes = x.numel() * 4, pred_pin.numel() * 4
+    tgt = t_host.to(dev) if mode == "mpjpe" else None
+    tgt_pin = t_host.pin_memory() if mode == "mpjpe" else None
+    in_bytes = x.numel() * 4 + (tgt.numel() * 4 if tgt is not None else 0)
+    out_bytes = pred_pin.numel() * 4 if mode == "forward" else 25 * 8 + 4
 
     def barrier():
         if world > 1:
@@ -212,37 +277,72 @@ def run_native(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident arm: inputs already in HBM (input 173 MB > 126 MB L2, so nothing is L2-warm)
+    count = torch.tensor([float(B * V)], device=dev, dtype=torch.float64)
+
+    def step(xd, td):
+        """One pass of the path on device-resident inputs.  mpjpe mode returns (mpjpe_all, mpjpe_per_frame) GLOBAL over
+        ranks: per-frame sums (25 doubles) + count all-reduced over NCCL, the only inter-GPU exchange."""
+        if mode == "forward":
+            return model(xd)[0]
+        _, sums = model.forward_mpjpe(xd, td)
+        buf = torch.cat([sums, count])
+        if world > 1:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        per_frame = buf[:-1] / buf[-1]                         # losses.mpjpe(..., reduce_axis=(0, 2))
+        return per_frame.mean(), per_frame                     # reduce_axis=[] and (0, 2)
+
+    # ---- device-resident arm: inputs already in HBM (inputs + activations per step exceed the 126 MB L2 at the
+    # benchmark batches; small batches are L2-flushed between steps)
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev) if B * 10 * V * 3 * 4 < 160e6 else None
+    l2_policy = "inputs_larger_than_L2" if flush is None else "L2 flushed between steps (192 MB memset, outside the events)"
     for _ in range(max(args.warmup, 3)):
-        model(x)
+        step(x, tgt)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     lib.cistgcn_profile_enable(1)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        out = model(x)
-    ev1.record()
-    barrier()
-    ms = max_over_ranks(ev0.elapsed_time(ev1))
-    kms = (ctypes.c_double * 4)()
-    kln = (ctypes.c_int64 * 4)()
+    if flush is None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            out = step(x, tgt)
+        ev1.record()
+        barrier()
+        ms_local = ev0.elapsed_time(ev1)
+    else:
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        for e0, e1 in evs:
+            flush.zero_()
+            e0.record()
+            out = step(x, tgt)
+            e1.record()
+        barrier()
+        ms_local = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    ms = max_over_ranks(ms_local)
+    NK = _cabi.PROFILE_KINDS
+    kms = (ctypes.c_double * NK)()
+    kln = (ctypes.c_int64 * NK)()
     lib.cistgcn_profile_read(kms, kln)
     lib.cistgcn_profile_enable(0)
     clocks = sampler.stop() if rank == 0 else None
-    value = world * B * args.steps / (ms / 1e3)
+    value = global_B * args.steps / (ms / 1e3)
+    result_note = None
+    if mode == "mpjpe":
+        result_note = {"mpjpe_all": float(out[0]), "mpjpe_frame0": float(out[1][0]), "mpjpe_frame24": float(out[1][-1])}
 
-    # ---- end-to-end arm: host buffers; every step copies its inputs host->device and its predictions
-    # device->host inside the timed region.  The step is split into sub-batches so the copies (second stream)
-    # overlap the forward of the neighbouring sub-batch -- plain stream pipelining around the public forward().
+    # ---- end-to-end arm: host buffers; every step copies its inputs host->device and its result device->host inside
+    # the timed region.  The step is split into sub-batches so the copies (second stream) overlap the forward of the
+    # neighbouring sub-batch -- plain stream pipelining around the public forward().
     n_sub = 4 if B % 4 == 0 and B >= 4096 else 1
     sub = B // n_sub
     copy_stream = torch.cuda.Stream(device=dev)
     compute_stream = torch.cuda.current_stream(dev)
     x_dev = [torch.empty(sub, 10, V, 3, device=dev) for _ in range(n_sub)]
+    t_dev = [torch.empty(sub, 25, V, 3, device=dev) for _ in range(n_sub)] if mode == "mpjpe" else None
+    res_pin = torch.empty(26, dtype=torch.float64).pin_memory()
 
     def e2e_step():
         ev_in = [torch.cuda.Event() for _ in range(n_sub)]
@@ -251,28 +351,45 @@ def run_native(args, rank, world, local_rank):
         with torch.cuda.stream(copy_stream):
             for i in range(n_sub):
                 x_dev[i].copy_(x_pin[i * sub:(i + 1) * sub], non_blocking=True)
+                if mode == "mpjpe":
+                    t_dev[i].copy_(tgt_pin[i * sub:(i + 1) * sub], non_blocking=True)
                 ev_in[i].record(copy_stream)
-        for i in range(n_sub):
-            compute_stream.wait_event(ev_in[i])
-            pr = model(x_dev[i])[0]
-            ev_out[i].record(compute_stream)
-            pr.record_stream(copy_stream)
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(ev_out[i])
-                pred_pin[i * sub:(i + 1) * sub].copy_(pr, non_blocking=True)
-        compute_stream.wait_stream(copy_stream)              # the step ends when its last D2H has landed
+        if mode == "forward":
+            for i in range(n_sub):
+                compute_stream.wait_event(ev_in[i])
+                pr = model(x_dev[i])[0]
+                ev_out[i].record(compute_stream)
+                pr.record_stream(copy_stream)
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(ev_out[i])
+                    pred_pin[i * sub:(i + 1) * sub].copy_(pr, non_blocking=True)
+            compute_stream.wait_stream(copy_stream)          # the step ends when its last D2H has landed
+        else:
+            tot = torch.zeros(26, device=dev, dtype=torch.float64)
+            for i in range(n_sub):
+                compute_stream.wait_event(ev_in[i])
+                _, sums = model.forward_mpjpe(x_dev[i], t_dev[i])
+                tot[:25] += sums
+            tot[25] = float(B * V)
+            if world > 1:
+                dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            res_pin.copy_(tot, non_blocking=True)            # per-frame sums + count: the step's result, read on the host
 
     for _ in range(2):
         e2e_step()
     barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
         e2e_step()
     ev1.record()
     barrier()
     ms_e2e = max_over_ranks(ev0.elapsed_time(ev1))
-    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
-    checksum = float(pred_pin[:16].double().abs().sum())          # the D2H result is really read
+    e2e_value = global_B * args.steps / (ms_e2e / 1e3)
+    if mode == "forward":
+        checksum = float(pred_pin[:16].double().abs().sum())          # the D2H result is really read
+    else:
+        checksum = float((res_pin[:25] / res_pin[25]).mean())
 
     if world > 1:
         dist.destroy_process_group()
@@ -280,25 +397,22 @@ def run_native(args, rank, world, local_rank):
         return
 
     hbm_peak, peak_src = measured_peaks()
+    names = [lib.cistgcn_profile_kind_name(i).decode() for i in range(NK)]
     launches = sum(int(v) for v in kln)                     # launches of OUR kernels inside the timed region
-    fpn_tc = V in (22, 18) and os.environ.get("CISTGCN_BENCH_FPN_PATH", "0") == "0"
-    names = ["dstd_block_kernel", "fpn_tc_kernel" if fpn_tc else "fpn_chain_kernel", "tail_kernel", "mpjpe_kernel"]
+    fpn_tc = V in (22, 18) and not (model.kernel_flags & _cabi.FLAG_FPN_FP32)
     kshare = {names[i]: {"ms_per_step": kms[i] / args.steps, "launches_per_step": int(kln[i]) / args.steps}
-              for i in range(4) if kln[i]}
-    dom = max(range(4), key=lambda i: kms[i])
+              for i in range(NK) if kln[i]}
+    if "fpn_kernel" in kshare:
+        kshare["fpn_kernel"]["variant"] = "fpn_tc_kernel (tcgen05)" if fpn_tc else "fpn_chain_kernel (FP32 FMA)"
+    dom = max(range(NK), key=lambda i: kms[i])
     total_kms = sum(kms)
     n_launch_dom = max(int(kln[dom]), 1)
-    seqs = B * args.steps                                   # sequences pushed through every kernel kind
-    # Algorithmic (compulsory) HBM bytes and FLOPs per sequence of each kernel kind -- DESIGN.md section 5:
-    # every kernel reads its input activation once and writes its output once; weights are amortised.
-    TV = 10 * V
-    dstd_bytes = 4 * ((3 * TV + E * TV) + 3 * 2 * E * TV + (E * TV + 10 * TV) + 2 * 75 * V)   # 5 input blocks + output block
-    kind_bytes = [dstd_bytes, 4 * (10 * TV + 75 * V), 4 * (30 * V + 3 * 75 * V), 4 * 2 * 75 * V]
+    seqs = B * args.steps                                   # sequences pushed through every kernel kind on this rank
+    kb = stage_bytes_per_seq(E, V)
     fl_total = FLOPS_PER_SEQ.get((V, E), 0.0)
-    kind_flops = [fl_total - FPN_FLOPS_PER_SEQ[V] - 0.7e6 * V / 22, FPN_FLOPS_PER_SEQ[V], 0.7e6 * V / 22, 0.0]
+    dstd_flops = fl_total - FPN_FLOPS_PER_SEQ[V] - 0.7e6 * V / 22
     dur_s = kms[dom] / 1e3 / n_launch_dom                   # average launch duration, CUDA events on the launch stream
-    bytes_launch = kind_bytes[dom] * seqs / n_launch_dom
-    flops_launch = kind_flops[dom] * seqs / n_launch_dom
+    bytes_launch = kb.get(names[dom], 0) * seqs / n_launch_dom
     achieved = bytes_launch / dur_s / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
@@ -311,9 +425,12 @@ def run_native(args, rank, world, local_rank):
                 "share_of_step": kms[dom] / total_kms if total_kms else None,
                 "bytes_per_launch": bytes_launch, "launch_ms": dur_s * 1e3,
                 "note": "the fp32 path is bound by the FP32 FMA pipe, not HBM (SURVEY.md 0.3 / 8d): see roofline_fp32_fma"}
-    tf = flops_launch / dur_s / 1e12
-    roofline_fma = {"bound": "fp32_fma", "kernel": names[dom], "achieved": tf, "peak": FP32_FMA_PEAK_TFLOPS,
-                    "unit": "TFLOP/s", "frac": tf / FP32_FMA_PEAK_TFLOPS,
+    # FP32-FMA view: all DSTD kinds together (their FLOPs cannot be split per stage from the reference's counter)
+    dstd_ms = sum(kms[i] for i in range(NK) if names[i].startswith("dstd_"))
+    dstd_tf = dstd_flops * seqs / (dstd_ms / 1e3) / 1e12 if dstd_ms else 0.0
+    roofline_fma = {"bound": "fp32_fma", "kernel": "dstd_* (all DSTD-GC stages)", "achieved": dstd_tf, "peak": FP32_FMA_PEAK_TFLOPS,
+                    "unit": "TFLOP/s", "frac": dstd_tf / FP32_FMA_PEAK_TFLOPS,
+                    "share_of_step": dstd_ms / total_kms if total_kms else None,
                     "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz; measured ceiling of a pure FFMA loop on this "
                                    "pool is 92/128 of it (profiles/microbench_r1.log)",
                     "whole_forward": {"achieved": fl_total * (value / world) / 1e12,
@@ -333,16 +450,17 @@ def run_native(args, rank, world, local_rank):
                                    "FLOPs incl. channel padding to 32 and the split-operand products that buy fp32 accuracy "
                                    "(x1*[w1|w2|w3] + x2*wh); the pipe is fed from shared memory at N <= 96, see DESIGN.md"}
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"CISTGCN embed={E} forward, H36M shape (10 in / 25 out frames, {V} joints x 3), "
-                               f"batch {B} per GPU, fp32, random-init weights (BASELINE.json configs[1])",
-                   "batch_per_gpu": B, "global_batch": B * world, "embed": E, "joints": V,
-                   "parallelism": f"batch-sharded x{world}, no data-path collective",
-                   "l2_policy": "inputs_larger_than_L2 (173 MB input + activations per step > 126 MB L2)"},
+        "metric": metric_name(V, mode), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args, world), "batch_per_gpu": B, "global_batch": global_B, "embed": E,
+                   "joints": V, "mode": mode,
+                   "parallelism": f"batch-sharded x{world}, no data-path collective" +
+                                  ("; MPJPE frame sums: one 208-byte NCCL all-reduce per step" if mode == "mpjpe" and world > 1 else ""),
+                   "l2_policy": l2_policy, "kernel_flags": model.kernel_flags},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
-                "ms_per_step": ms_e2e / args.steps, "api": f"CISTGCN.forward on pinned host buffers, {n_sub} sub-batches, copies overlapped on a second stream",
+                "ms_per_step": ms_e2e / args.steps,
+                "api": f"CISTGCN.{'forward' if mode == 'forward' else 'forward_mpjpe'} on pinned host buffers, {n_sub} sub-batches, copies overlapped on a second stream",
                 "checksum": checksum},
         "gpu_launches": launches * world,     # every rank launches the same kernels on its own GPU
         "kernels": kshare,
@@ -351,8 +469,10 @@ def run_native(args, rank, world, local_rank):
         "roofline_tensor": roofline_tensor,
         "clocks": clocks,
     }
+    if result_note:
+        line["result"] = result_note
     if world == 1:
-        line["cpu_baseline"] = cpu_baseline(E, V, args.cpu_budget)
+        line["cpu_baseline"] = cpu_baseline(E, V, mode, args.cpu_budget)
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
@@ -366,7 +486,9 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--embed", type=int, default=32)
     ap.add_argument("--joints", type=int, default=22)
-    ap.add_argument("--batch", type=int, default=65536, help="sequences per GPU per step")
+    ap.add_argument("--batch", type=int, default=65536, help="sequences per GPU per step (weak) / global batch (strong)")
+    ap.add_argument("--mode", default="forward", choices=["forward", "mpjpe"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline timing (N=1 only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -33,10 +33,19 @@ class Taps(ctypes.Structure):
                 ("ctx_seq_joints_n", _p), ("ctx_seq_joints_dims", _p)]
 
 
-EXPORTS = ("cistgcn_last_error", "cistgcn_abi_version", "cistgcn_workspace_bytes", "cistgcn_forward_f32",
-           "cistgcn_dstd_block_f32", "cistgcn_fpn_chain_f32", "cistgcn_tail_f32", "cistgcn_mpjpe_f32",
-           "cistgcn_profile_enable", "cistgcn_profile_read", "cistgcn_debug_phase_clocks", "cistgcn_debug_stamp_iteration",
-           "cistgcn_set_fpn_path", "cistgcn_set_dstd_path")
+def _declared_exports():
+    """Every function include/cistgcn_b200.h declares (the loader checks the library exports all of them)."""
+    import re
+    from .pack import _HEADER
+    src = re.sub(r"/\*.*?\*/", "", open(_HEADER).read(), flags=re.S)
+    return tuple(dict.fromkeys(re.findall(r"\b(cistgcn_\w+)\s*\(", src)))
+
+
+EXPORTS = _declared_exports()
+FLAG_FPN_FP32 = DEFINES["CISTGCN_FLAG_FPN_FP32"]
+FLAG_DSTD_FUSED = DEFINES["CISTGCN_FLAG_DSTD_FUSED"]
+FLAG_DSTD_TC = DEFINES["CISTGCN_FLAG_DSTD_TC"]
+PROFILE_KINDS = DEFINES["CISTGCN_PROFILE_KINDS"]
 
 
 def bind(path: str) -> ctypes.CDLL:
@@ -51,9 +60,14 @@ def bind(path: str) -> ctypes.CDLL:
     L.cistgcn_forward_f32.argtypes = [_i32p, ctypes.c_int32, _p, _p, _p, _p, _p, _p, ctypes.c_size_t,
                                       ctypes.c_int64, ctypes.POINTER(Taps), _p]
     L.cistgcn_dstd_block_f32.restype = ctypes.c_int
-    L.cistgcn_dstd_block_f32.argtypes = [_i32p, _p, _p, _p, ctypes.c_int64, ctypes.POINTER(BlockTaps), _p]
+    L.cistgcn_dstd_block_f32.argtypes = [_i32p, _p, _p, _p, ctypes.c_int64, ctypes.POINTER(BlockTaps), _p, ctypes.c_size_t,
+                                         ctypes.c_uint32, _p]
+    L.cistgcn_dstd_block_workspace_bytes.restype = ctypes.c_size_t
+    L.cistgcn_dstd_block_workspace_bytes.argtypes = [_i32p, ctypes.c_int64]
     L.cistgcn_fpn_chain_f32.restype = ctypes.c_int
-    L.cistgcn_fpn_chain_f32.argtypes = [_i32p, ctypes.c_int32, _i32p, _p, _p, _p, ctypes.c_int64, _p]
+    L.cistgcn_fpn_chain_f32.argtypes = [_i32p, ctypes.c_int32, _i32p, _p, _p, _p, ctypes.c_int64, ctypes.c_uint32, _p]
+    L.cistgcn_profile_kind_name.restype = ctypes.c_char_p
+    L.cistgcn_profile_kind_name.argtypes = [ctypes.c_int]
     L.cistgcn_tail_f32.restype = ctypes.c_int
     L.cistgcn_tail_f32.argtypes = [_i32p, _p, _p, _p, _p, _p, _p, _p, ctypes.c_int64, ctypes.POINTER(Taps), _p]
     L.cistgcn_mpjpe_f32.restype = ctypes.c_int
@@ -66,10 +80,6 @@ def bind(path: str) -> ctypes.CDLL:
     L.cistgcn_debug_phase_clocks.argtypes = [_p]
     L.cistgcn_debug_stamp_iteration.restype = ctypes.c_int
     L.cistgcn_debug_stamp_iteration.argtypes = [ctypes.c_int]
-    L.cistgcn_set_fpn_path.restype = ctypes.c_int
-    L.cistgcn_set_fpn_path.argtypes = [ctypes.c_int]
-    L.cistgcn_set_dstd_path.restype = ctypes.c_int
-    L.cistgcn_set_dstd_path.argtypes = [ctypes.c_int]
     if L.cistgcn_abi_version() != ABI_VERSION:
         raise RuntimeError(f"cistgcn_b200: {path} has ABI {L.cistgcn_abi_version()}, header says {ABI_VERSION}; "
                            "rebuild with `python -c 'import __graft_entry__ as g; g.build()'`")

@@ -1,0 +1,275 @@
+// DSTD-GC block, stage 2 of 3: the per-sample VECTOR path -- from the `red` record of stage 1 (dstd_reduce.cuh) to the
+// two context gates and the two sample-specific adjacencies (reference: models/CISTGCN/CISTGCN.py:327-352, 378-384 the
+// gate nets conv_{s,t}.4-7 + map_{s,t}; :144, :152 the last 1x1 of Map2Adj's compress branches; :155-170, :183-189 the
+// outer products and the expansor).
+//
+// In round 1 these were ~10 serial phases of one 16-warp CTA per sample (gate matvecs alone: 14 K cycles for 25 K MACs).
+// Here one WARP owns one sample, end to end, with warp-level synchronisation only; every weight matrix is resident in
+// shared memory and shared by all warps of the CTA; 8-16 samples are in flight per SM.
+//   gate conv (1,V) and the gate MLP: lanes = output channels, the input vector is broadcast from shared memory;
+//   dim_seq / dim_space: lanes = joints, register tile over the frames;
+//   expansor: lanes = columns of the outer-product map o (never materialised); the hidden column lives in registers,
+//             weight rows are warp-uniform 128-bit loads; the result is written with coalesced stores in the
+//             reference's own (V,T,T) / (T,V,V) layout, i.e. the interpretability taps of environment/test.py:146-157
+//             and the operand of stage 3 are the same buffer.
+#pragma once
+#include "../../include/cistgcn_b200.h"
+#include "dstd_reduce.cuh"
+#include "simt.h"
+
+namespace cg {
+
+constexpr int ADJ_MAX_WARPS = 12;     // 384 threads: up to 168 registers per thread
+
+struct AdjArgs {
+  int d[CB_COUNT];
+  int res[CB_COUNT];       // shared-memory float offset of the resident copy of weight field f, or -1 (read through L1/L2)
+  int wsz[CB_COUNT];       // floats of weight field f (multiple of 4), 0 if unused here
+  const float* w;
+  const float* red;
+  int red_stride;
+  float* wg;               // (B, 2, Co) gates w1 | w2
+  float* adj_s;            // (B, V, T, T)
+  float* adj_t;            // (B, T, V, V)
+  float* tap_w1;           // optional (B, Co) copies for the interpretability taps
+  float* tap_w2;
+  int batch, nwarps;
+  int o_warp, warp_floats, smem_floats;
+};
+
+__host__ __device__ inline int apad8(int n) { return (n + 7) & ~7; }
+
+// Host: residency plan.  Vectors first, then matrices by reuse; what does not fit is read through L1 / L2.
+inline bool adj_plan(AdjArgs& a, int max_smem_floats) {
+  const int* d = a.d;
+  const int Co = d[CB_CO], T = d[CB_T], V = d[CB_V], Ch = d[CB_CH], Cg = d[CB_CG];
+  const bool interp = d[CB_INTERP] != 0;
+  const int Cop = apad8(Co), TV = T * V;
+  if (Co > 32 || T > 32 || V > 32) return false;
+  for (int f = 0; f < CB_COUNT; ++f) { a.wsz[f] = 0; a.res[f] = -1; }
+  int* z = a.wsz;
+  z[CB_G4_WT] = 2 * Cg * V * Cop; z[CB_G4_B] = 2 * Co; z[CB_G4_A] = 2;
+  z[CB_M0_WT] = 2 * (Co + 2 + 2 * T) * Cop; z[CB_M0_B] = 2 * Co; z[CB_M0_A] = 2;
+  z[CB_M4_WT] = 2 * Co * Cop;
+  if (interp) {
+    for (int L = 0; L < 2; ++L) {
+      const int n = L == 0 ? V : T;
+      z[CB_TC6_WT_S + L] = Ch * apad8(T); z[CB_JC6_WT_S + L] = Ch * apad8(V);
+      z[CB_E0_WT_S + L] = n * apad8(n); z[CB_E0_B_S + L] = n; z[CB_E0_A_S + L] = 1; z[CB_E4_WT_S + L] = n * apad8(n);
+    }
+  }
+  for (int f = 0; f < CB_COUNT; ++f) z[f] = rpad4(z[f]);
+  const RedLayout RL(T, V, Cg, Ch, interp);
+  a.warp_floats = rpad4(RL.total) + (interp ? 4 * rpad4(TV) : 0) + 4 * rpad4(Co);
+  const int order[] = {CB_G4_B, CB_G4_A, CB_M0_B, CB_M0_A, CB_E0_B_S, CB_E0_B_T, CB_E0_A_S, CB_E0_A_T,
+                       CB_E0_WT_S, CB_E0_WT_T, CB_E4_WT_S, CB_E4_WT_T, CB_TC6_WT_S, CB_TC6_WT_T, CB_JC6_WT_S, CB_JC6_WT_T,
+                       CB_M0_WT, CB_M4_WT, CB_G4_WT};
+  const int min_warps = 8;
+  int cur = 0;
+  for (int f : order) {
+    if (z[f] == 0) continue;
+    if (cur + z[f] + min_warps * a.warp_floats <= max_smem_floats) { a.res[f] = cur; cur += z[f]; }
+  }
+  a.o_warp = cur;
+  int nw = (max_smem_floats - cur) / a.warp_floats;
+  if (nw > ADJ_MAX_WARPS) nw = ADJ_MAX_WARPS;
+  if (nw < 2) return false;
+  a.nwarps = nw;
+  a.smem_floats = cur + nw * a.warp_floats;
+  return true;
+}
+
+// One output column per lane of a two-layer N -> N -> N MLP over the leading axis of the outer-product map
+// (Map2Adj.expansor, CISTGCN.py:165-170): out[:, col] = W4^T PReLU(W0^T o[:, col] + b0).  Weights k-major [k][pad8(N)].
+template <int N, int NCOLS, class OFN, class STORE>
+CG_DEV void expansor_warp(const float* __restrict__ w0, const float* __restrict__ b0, float a0,
+                          const float* __restrict__ w4, OFN o_at, STORE store) {
+  constexpr int NPW = (N + 7) & ~7;
+  const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int c0 = 0; c0 < NCOLS; c0 += 32) {
+    const bool active = c0 + lane < NCOLS;
+    const int col = active ? c0 + lane : NCOLS - 1;
+    float h[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) h[j] = 0.f;
+#pragma unroll 2
+    for (int k = 0; k < N; ++k) {
+      const float ok = o_at(k, col);
+      float wrow[NPW];
+#pragma unroll
+      for (int i = 0; i < NPW / 4; ++i) {
+        const float4 q = *reinterpret_cast<const float4*>(w0 + k * NPW + 4 * i);
+        wrow[4 * i] = q.x; wrow[4 * i + 1] = q.y; wrow[4 * i + 2] = q.z; wrow[4 * i + 3] = q.w;
+      }
+#pragma unroll
+      for (int j = 0; j < N; ++j) h[j] = fmaf(wrow[j], ok, h[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) h[j] = prelu(h[j] + b0[j], a0);
+    float o[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) o[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {                  // h[k] must stay in registers: fully unrolled
+      float wrow[NPW];
+#pragma unroll
+      for (int i = 0; i < NPW / 4; ++i) {
+        const float4 q = *reinterpret_cast<const float4*>(w4 + k * NPW + 4 * i);
+        wrow[4 * i] = q.x; wrow[4 * i + 1] = q.y; wrow[4 * i + 2] = q.z; wrow[4 * i + 3] = q.w;
+      }
+#pragma unroll
+      for (int j = 0; j < N; ++j) o[j] = fmaf(wrow[j], h[k], o[j]);
+    }
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) store(j, col, o[j]);
+    }
+  }
+}
+
+// y[m] = sum_k W[k][m] * x[k] for the lane's output column m (clamped by the caller); x broadcast from shared memory.
+CG_DEV float warp_col_dot(const float* __restrict__ wcol, int Mp, int K, const float* x) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int k = 0;
+#pragma unroll 2
+  for (; k + 4 <= K; k += 4) {
+    const float4 xv = *reinterpret_cast<const float4*>(x + k);
+    a0 = fmaf(wcol[(k + 0) * Mp], xv.x, a0);
+    a1 = fmaf(wcol[(k + 1) * Mp], xv.y, a1);
+    a2 = fmaf(wcol[(k + 2) * Mp], xv.z, a2);
+    a3 = fmaf(wcol[(k + 3) * Mp], xv.w, a3);
+  }
+  for (; k < K; ++k) a0 = fmaf(wcol[k * Mp], x[k], a0);
+  return (a0 + a1) + (a2 + a3);
+}
+
+template <int T, int V>
+__global__ void __launch_bounds__(32 * ADJ_MAX_WARPS, 1) dstd_adj_kernel(const AdjArgs a) {
+  CG_DYN_SMEM(smem);
+  constexpr int TV = T * V, TT = T * T, VV = V * V;
+  constexpr int TP = (T + 3) & ~3, VQ = (V + 3) & ~3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nthreads = blockDim.x;
+  const int* d = a.d;
+  const int Co = d[CB_CO], Ch = d[CB_CH], Cg = d[CB_CG];
+  const bool interp = d[CB_INTERP] != 0;
+  const int Cop = apad8(Co);
+  const RedLayout RL(T, V, Cg, Ch, interp);
+  const float* __restrict__ W = a.w;
+
+  for (int f = 0; f < CB_COUNT; ++f)
+    if (a.res[f] >= 0)
+      for (int i = threadIdx.x; i < a.wsz[f]; i += nthreads) smem[a.res[f] + i] = __ldg(W + d[f] + i);
+  __syncthreads();
+  auto P = [&](int f) -> const float* { return a.res[f] >= 0 ? smem + a.res[f] : W + d[f]; };
+
+  float* rr = smem + a.o_warp + warp * a.warp_floats;      // the sample's red record
+  float* dseq = rr + rpad4(RL.total);                      // [2][T][V]   dim_seq of both domains
+  float* dsp = dseq + 2 * rpad4(TV);                       // [2][V][T]   dim_space
+  const int Co4 = rpad4(Co);                               // per-gate stride of the small vectors (16-byte aligned rows)
+  float* h2 = (interp ? dsp + 2 * rpad4(TV) : dseq);       // [2][Co4]
+  float* zz = h2 + 2 * Co4;                                // [2][Co4]
+  const int oc = lane < Co ? lane : Co - 1;
+
+  for (int b = blockIdx.x * a.nwarps + warp; warp < a.nwarps && b < a.batch; b += gridDim.x * a.nwarps) {
+    {
+      const float4* src = reinterpret_cast<const float4*>(a.red + (size_t)b * a.red_stride);
+      for (int i = lane; i < RL.total / 4; i += 32) reinterpret_cast<float4*>(rr)[i] = __ldg(src + i);
+    }
+    __syncwarp();
+    // ---------------- gate conv (1,V) + BN + PReLU -> h2 (:327-330), lanes = output channels
+    {
+      const float* w4 = P(CB_G4_WT);
+      const float* b4 = P(CB_G4_B);
+      const float* a4 = P(CB_G4_A);
+      const int K = Cg * V;
+#pragma unroll 1
+      for (int g = 0; g < 2; ++g) {
+        const float acc = warp_col_dot(w4 + (size_t)g * K * Cop + oc, Cop, K, rr + RL.h1 + g * RL.h1g);
+        if (lane < Co) h2[g * Co4 + lane] = prelu(acc + b4[g * Co + lane], a4[g]);
+      }
+    }
+    __syncwarp();
+    // ---------------- gate MLP: Linear(Co + 2 + 2T -> Co) + BN + PReLU, Linear(Co -> Co)  (:341-352, 378-384)
+    {
+      const float* m0 = P(CB_M0_WT);
+      const float* m0b = P(CB_M0_B);
+      const float* m0a = P(CB_M0_A);
+      const float* m4 = P(CB_M4_WT);
+      const int NS = 2 + 2 * T;
+#pragma unroll 1
+      for (int g = 0; g < 2; ++g) {
+        const float* w0 = m0 + (size_t)g * (Co + NS) * Cop + oc;
+        float acc = warp_col_dot(w0, Cop, Co, h2 + g * Co4);
+        acc += warp_col_dot(w0 + (size_t)Co * Cop, Cop, NS, rr + RL.stats);
+        if (lane < Co) zz[g * Co4 + lane] = prelu(acc + m0b[g * Co + lane], m0a[g]);
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int g = 0; g < 2; ++g) {
+        const float acc = warp_col_dot(m4 + (size_t)g * Co * Cop + oc, Cop, Co, zz + g * Co4);
+        if (lane < Co) {
+          a.wg[((size_t)b * 2 + g) * Co + lane] = acc;
+          float* tp = g == 0 ? a.tap_w1 : a.tap_w2;
+          if (tp) tp[(size_t)b * Co + lane] = acc;
+        }
+      }
+    }
+    if (interp) {
+      // ---------------- dim_seq / dim_space: last 1x1 of each compress branch (:144, :152); lanes = joints
+#pragma unroll 1
+      for (int L = 0; L < 2; ++L) {
+        const float* w6 = P(CB_TC6_WT_S + L);              // [Ch][pad8(T)]
+        const float* wj = P(CB_JC6_WT_S + L);              // [Ch][pad8(V)]
+        const float* tcv = rr + RL.tc + L * Ch * V;        // [Ch][V]
+        const float* jcv = rr + RL.jc + L * Ch * T;        // [Ch][T]
+        const int vl = lane < V ? lane : V - 1;
+        float s[T], p[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) { s[t] = 0.f; p[t] = 0.f; }
+#pragma unroll 2
+        for (int o = 0; o < Ch; ++o) {
+          const float xv = tcv[o * V + vl];                // dim_seq[t'][v] = sum_o W6[o][t'] * tc[o][v]
+          const float wv = wj[o * apad8(V) + vl];          // dim_space[v'][t] = sum_o Wj6[o][v'] * jc[o][t]
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            s[t] = fmaf(w6[o * apad8(T) + t], xv, s[t]);
+            p[t] = fmaf(wv, jcv[o * T + t], p[t]);
+          }
+        }
+        if (lane < V) {
+#pragma unroll
+          for (int t = 0; t < T; ++t) { dseq[L * rpad4(TV) + t * V + lane] = s[t]; dsp[L * rpad4(TV) + lane * T + t] = p[t]; }
+        }
+      }
+      __syncwarp();
+      // ---------------- space domain: o[v'][t][q] = dsp[v'][t] * dseq[q][v'] (:155-158, 187), expansor over the joint axis
+      {
+        float* out = a.adj_s + (size_t)b * V * TT;
+        const float* ds = dseq;
+        const float* dp = dsp;
+        expansor_warp<V, TT>(P(CB_E0_WT_S), P(CB_E0_B_S), P(CB_E0_A_S)[0], P(CB_E4_WT_S),
+          [&](int k, int col) { const int t = col / T, q = col - t * T; return dp[k * T + t] * ds[q * V + k]; },
+          [&](int m, int col, float val) { out[m * TT + col] = val; });
+      }
+      // ---------------- time domain: o[t'][v][w] = dsp[v][t'] * dseq[t'][w] (:159-162, 187), expansor over the frame axis
+      {
+        float* out = a.adj_t + (size_t)b * T * VV;
+        const float* ds = dseq + rpad4(TV);
+        const float* dp = dsp + rpad4(TV);
+        expansor_warp<T, VV>(P(CB_E0_WT_T), P(CB_E0_B_T), P(CB_E0_A_T)[0], P(CB_E4_WT_T),
+          [&](int k, int col) { const int v = col / V, w = col - v * V; return dp[v * T + k] * ds[k * V + w]; },
+          [&](int m, int col, float val) { out[m * VV + col] = val; });
+      }
+    }
+    __syncwarp();
+  }
+  (void)TP; (void)VQ;
+}
+
+template <int T, int V>
+inline int launch_adj_impl(const AdjArgs& a, void* stream) {
+  return launch_warp_per_sample(dstd_adj_kernel<T, V>, a, stream);
+}
+
+}  // namespace cg

@@ -27,10 +27,10 @@
 
 namespace cg {
 
-#ifdef CISTGCN_EMU
+#if defined(CISTGCN_EMU) || !defined(CISTGCN_PROFILE)
 #define CG_STAMP(i)
 #else
-#define CG_STAMP(i) do { if (a.phase_clocks && blockIdx.x == 0 && threadIdx.x == 0 && b == (int)blockIdx.x + a.stamp_iter * (int)gridDim.x) a.phase_clocks[i] = clock64(); } while (0)
+#define CG_STAMP(i) do { if (a.phase_clocks && blockIdx.x == 0 && threadIdx.x == 0 && b == (int)blockIdx.x + a.stamp_iter * (int)gridDim.x) a.phase_clocks[i] = CG_CLOCK(); } while (0)
 #endif
 
 struct DstdArgs {
@@ -50,7 +50,7 @@ struct DstdArgs {
   // tensor-core channel mixes (tc_gemm): staging operand [2 terms][tc_kc chunks][256 positions][16 B] + mbarrier / TMEM slot
   int g0_stage, o_gbar;  // gate-conv weights streamed by cp.async.bulk into the (idle) work tiles at the start of every sample
   int tc, o_stage, tc_kc, o_tcmisc, o_img;     // o_img: one weight-image buffer, refilled by cp.async.bulk between uses
-  long long* phase_clocks;   // optional debug: first CTA / thread 0 stamps clock64() at phase boundaries
+  long long* phase_clocks;   // optional debug: first CTA / thread 0 stamps CG_CLOCK() at phase boundaries
   int stamp_iter;            // ... of its stamp_iter-th sample (0 = first: cold caches)
 };
 
@@ -960,10 +960,10 @@ CG_DEV void tc_gemm(TcState& tc, const float* X1, int K1, const float* X2, int K
       mbar_wait(tc.bar, tc.parity);
       tc.parity ^= 1;
     }
-    const long long tq0 = clock64();
+    const long long tq0 = CG_CLOCK();
     tc_convert<TV, NT>(tc.stage, term_stride, X, K);
     __syncthreads();
-    if (tc.dbg && tid == 0) tc.dbg[0] += clock64() - tq0;
+    if (tc.dbg && tid == 0) tc.dbg[0] += CG_CLOCK() - tq0;
     if (warp == 0) {
       if (pass == 0) mbar_wait(tc.img_bar, tc.img_parity);
       tc_fence_after();
@@ -972,12 +972,12 @@ CG_DEV void tc_gemm(TcState& tc, const float* X1, int K1, const float* X2, int K
     img_chunk += kc;
   }
   tc.img_parity ^= 1;
-  const long long tq1 = clock64();
+  const long long tq1 = CG_CLOCK();
   mbar_wait(tc.bar, tc.parity);
   tc.parity ^= 1;
   tc_fence_after();
   if (next_img) tc_prefetch(tc, next_img, next_floats);     // the image buffer is free: fetch the next user's weights
-  const long long tq2 = clock64();
+  const long long tq2 = CG_CLOCK();
   {
     const int q = warp & 3, g = warp >> 2;
     const int t = g & 1;
@@ -998,7 +998,7 @@ CG_DEV void tc_gemm(TcState& tc, const float* X1, int K1, const float* X2, int K
   }
   tc_fence_before();
   __syncthreads();
-  if (tc.dbg && tid == 0) { tc.dbg[1] += tq2 - tq1; tc.dbg[2] += clock64() - tq2; tc.dbg[3] += 1; }
+  if (tc.dbg && tid == 0) { tc.dbg[1] += tq2 - tq1; tc.dbg[2] += CG_CLOCK() - tq2; tc.dbg[3] += 1; }
 }
 #endif  // CISTGCN_EMU
 

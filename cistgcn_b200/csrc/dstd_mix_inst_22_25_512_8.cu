@@ -1,0 +1,5 @@
+// Explicit instantiation: mix stage of the three-stage DSTD-GC path, (T, V) = (22, 25), 512 threads, TM = 8.
+#include "dstd_mix.cuh"
+namespace cg {
+int launch_mix_22_25_512_8(const MixArgs& a, void* stream) { return launch_mix_impl<22, 25, 512, 8>(a, stream); }
+}  // namespace cg

@@ -1,0 +1,351 @@
+// DSTD-GC block, stage 1 of 3: everything that REDUCES the normalised tile to small per-sample vectors
+// (reference: models/CISTGCN/CISTGCN.py:360-371 _get_stats_, :323-326 conv_{s,t}.0-3, :138-142 / :146-150 the first
+// two convolutions of Map2Adj's time_compress / joint_compress, for both domains).
+//
+// Round 1 ran these phases inside the fused per-sample CTA: ~8 barrier-separated phases on 16 warps at 7 % FMA
+// efficiency.  Here ONE WARP owns one sample and there is no block-level barrier at all: the warp streams the sample
+// frame by frame ("slab" = one t, Ci x V values), so its live state is a 3 KB slab instead of the 28 KB tile, and
+// 12-16 independent samples are in flight per SM.  Per slab:
+//   load     lanes = joints: coalesced row loads (or the 10-feature build of CISTGCN.py:568-577), global_norm folded
+//   stats    lanes = channels: row mean / variance over the joints; merged over frames with Chan's update
+//   mix      lanes = OUTPUT channels of the stacked 1x1 convolutions (4*Ch Map2Adj entry maps + 2*Cg gate-conv maps),
+//            register tile over the V joints: per input channel one conflict-free weight LDS per output + V/4 broadcast
+//            LDS.128 of the slab row feed 3*V FFMAs.  The gate conv (T,1) is the same GEMM with per-frame weights,
+//            accumulated over the slabs in registers.
+//   collapse lanes = the 2*Ch outputs (both domains) of time_compress.3 (accumulated over slabs) and
+//            joint_compress.3 (complete per slab).
+// Output per sample (the `red` record, float offsets from RedLayout): stats [2+2T], h1 [2*Cg][V] (after BN + PReLU),
+// tc [2*Ch][V] and jc [2*Ch][T] (after BN).  Stage 2 (dstd_adj.cuh) turns them into the gates and the adjacencies.
+#pragma once
+#include "../../include/cistgcn_b200.h"
+#include "host_util.h"
+#include "simt.h"
+
+namespace cg {
+
+__host__ __device__ inline int rpad4(int n) { return (n + 3) & ~3; }
+__host__ __device__ inline int rpad32(int n) { return (n + 31) & ~31; }
+__host__ __device__ inline int rmin(int a, int b) { return a < b ? a : b; }
+__host__ __device__ inline int rmax(int a, int b) { return a > b ? a : b; }
+constexpr int RED_MAX_WARPS = 12;      // 384 threads: up to 168 registers per thread
+
+// Float offsets inside one sample's `red` record.
+struct RedLayout {
+  int stats, h1, h1g, tc, jc, total;
+  __host__ __device__ RedLayout(int T, int V, int Cg, int Ch, bool interp) {
+    stats = 0;
+    h1 = rpad4(2 + 2 * T);
+    h1g = rpad4(Cg * V);                 // each gate's hidden map starts 16-byte aligned (stage 2 reads it with LDS.128)
+    tc = h1 + 2 * h1g;
+    jc = tc + (interp ? rpad4(2 * Ch * V) : 0);
+    total = jc + (interp ? rpad4(2 * Ch * T) : 0);
+  }
+};
+
+struct ReduceArgs {
+  int d[CB_COUNT];
+  const float* w;
+  const float* in;
+  float* red;
+  int batch, red_stride;
+  int nwarps;                       // warps per CTA (= samples in flight per CTA)
+  int o_a0, o_g0, o_tc3, o_jc3;     // resident matrices (shared-memory float offsets)
+  int o_gn_s, o_gn_b, o_a0_b, o_a0_a, o_g0_b, o_g0_a, o_tc3_b, o_jc3_b;   // resident vectors
+  int mp_e, mp_g, mp_c;             // row lengths: pad32(4Ch), pad32(2Cg), pad32(2Ch)
+  int o_warp, warp_floats, smem_floats;
+};
+
+// Host: shared-memory plan.  Returns false when the shape is outside this kernel's register tiling
+// (4*Ch <= 32*NE_MAX, 2*Cg <= 32, Ci <= 32) or the resident weights leave no room for >= 4 warps.
+constexpr int RED_NE_MAX = 2;
+inline bool reduce_plan(ReduceArgs& a, int max_smem_floats) {
+  const int* d = a.d;
+  const int Ci = d[CB_CI], T = d[CB_T], V = d[CB_V], Ch = d[CB_CH], Cg = d[CB_CG];
+  const bool interp = d[CB_INTERP] != 0;
+  if (Ci > 32 || 2 * Cg > 32 || (interp && 4 * Ch > 32 * RED_NE_MAX)) return false;
+  a.mp_e = rpad32(4 * Ch); a.mp_g = rpad32(2 * Cg); a.mp_c = rpad32(2 * Ch);
+  int cur = 0;
+  auto take = [&](int n) { const int o = cur; cur += rpad4(n); return o; };
+  a.o_g0 = take(Ci * T * a.mp_g);
+  a.o_a0 = interp ? take(Ci * a.mp_e) : 0;
+  a.o_tc3 = interp ? take(Ch * T * a.mp_c) : 0;
+  a.o_jc3 = interp ? take(Ch * V * a.mp_c) : 0;
+  a.o_gn_s = take(Ci); a.o_gn_b = take(Ci);
+  a.o_g0_b = take(a.mp_g); a.o_g0_a = take(2);
+  a.o_a0_b = take(a.mp_e); a.o_a0_a = take(4);
+  a.o_tc3_b = take(a.mp_c); a.o_jc3_b = take(a.mp_c);
+  const int XS = rpad4(V), XT = V | 1, AS = (rpad4(V) % 8 == 4) ? rpad4(V) : rpad4(V) + 4;
+  const int rows_ag = interp ? 4 * Ch : 0;
+  int region = Ci * XT;                                           // transposed slab copy (stats) aliases the map buffer
+  if (rows_ag * AS > region) region = rows_ag * AS;
+  if (2 * Cg * AS > region) region = 2 * Cg * AS;                 // output staging of h1 / tc
+  if (2 * Ch * AS > region) region = 2 * Ch * AS;
+  a.warp_floats = rpad4(Ci * XS) + rpad4(region);
+  a.o_warp = cur;
+  int nw = (max_smem_floats - cur) / a.warp_floats;
+  if (nw > RED_MAX_WARPS) nw = RED_MAX_WARPS;
+  if (nw < 4) return false;
+  a.nwarps = nw;
+  a.smem_floats = cur + nw * a.warp_floats;
+  return true;
+}
+
+template <int T, int V, int NE>
+__global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(const ReduceArgs a) {
+  CG_DYN_SMEM(smem);
+  constexpr int XS = (V + 3) & ~3;                 // slab row stride (LDS.128 broadcast reads)
+  constexpr int XT = V | 1;                        // transposed-use copy: odd stride, lanes = channels read columns
+  constexpr int AS = (XS % 8 == 4) ? XS : XS + 4;  // map rows: 4 x odd, so lanes = rows conflict only 4-way on the transposing store
+  constexpr int V4 = XS / 4;
+  constexpr int TV = T * V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nthreads = blockDim.x;
+  const int* d = a.d;
+  const int Ci = d[CB_CI], Ch = d[CB_CH], Cg = d[CB_CG];
+  const bool interp = d[CB_INTERP] != 0;
+  const RedLayout RL(T, V, Cg, Ch, interp);
+  const float* __restrict__ W = a.w;
+
+  // ---------------- once per launch: resident weights -> shared memory
+  {
+    auto cp = [&](int dst, int field, int n) {
+      for (int i = threadIdx.x; i < n; i += nthreads) smem[dst + i] = __ldg(W + d[field] + i);
+    };
+    cp(a.o_g0, CB_R_G0_WT, Ci * T * a.mp_g);
+    cp(a.o_gn_s, CB_GN_S, Ci); cp(a.o_gn_b, CB_GN_B, Ci);
+    cp(a.o_g0_b, CB_R_G0_B, a.mp_g); cp(a.o_g0_a, CB_G0_A, 2);
+    if (interp) {
+      cp(a.o_a0, CB_R_A0_WT, Ci * a.mp_e);
+      cp(a.o_tc3, CB_R_TC3_WT, Ch * T * a.mp_c);
+      cp(a.o_jc3, CB_R_JC3_WT, Ch * V * a.mp_c);
+      cp(a.o_a0_b, CB_R_A0_B, a.mp_e); cp(a.o_a0_a, CB_A0_A, 4);
+      cp(a.o_tc3_b, CB_R_TC3_B, a.mp_c); cp(a.o_jc3_b, CB_R_JC3_B, a.mp_c);
+    }
+  }
+  __syncthreads();
+  const float* gs = smem + a.o_gn_s;
+  const float* gb = smem + a.o_gn_b;
+  const float* wa0 = smem + a.o_a0;
+  const float* wg0 = smem + a.o_g0;
+  const float* wtc = smem + a.o_tc3;
+  const float* wjc = smem + a.o_jc3;
+  const int mpe = a.mp_e, mpg = a.mp_g, mpc = a.mp_c;
+  float* xs = smem + a.o_warp + warp * a.warp_floats;      // [Ci][XS]
+  float* ag = xs + rpad4(Ci * XS);                         // [4Ch][AS] maps | [Ci][XT] transposed slab | output staging
+  const bool wactive = warp < a.nwarps;
+
+  // per-lane constants of the collapse stage: lane = output (L, o) of both domains
+  const int L3 = (lane < 2 * Ch && Ch > 0) ? lane / Ch : 0;
+  const float* arow_tc = ag + (2 * L3 * Ch) * AS;          // time_compress map rows of domain L3
+  const float* arow_jc = ag + ((2 * L3 + 1) * Ch) * AS;    // joint_compress map rows
+  float e_b[NE], e_a[NE];
+#pragma unroll
+  for (int j = 0; j < NE; ++j) {
+    const int m = lane + 32 * j;
+    e_b[j] = interp ? smem[a.o_a0_b + m] : 0.f;
+    e_a[j] = interp ? smem[a.o_a0_a + rmin(m / rmax(Ch, 1), 3)] : 0.f;
+  }
+
+  for (int b = blockIdx.x * a.nwarps + warp; wactive && b < a.batch; b += gridDim.x * a.nwarps) {
+    float* red = a.red + (size_t)b * a.red_stride;
+    const float* src = a.in + (size_t)b * d[CB_IN_SB];
+    const int sc = d[CB_IN_SC], st = d[CB_IN_ST], sv = d[CB_IN_SV];
+    float ch_mean = 0.f, ch_m2 = 0.f;                      // Chan accumulators over (t, v), lane = channel
+    float acc_g[V], acc_tc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) { acc_g[v] = 0.f; acc_tc[v] = 0.f; }
+
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+      // ---- load slab t (lanes = joints), global_norm folded (:375); block 0 builds the 10 features (:568-577)
+      if (d[CB_IN_MODE] == 1) {
+        if (lane < V) {
+          float f[10];
+          float sp = 0.f;
+          const float* p = src + (t * V + lane) * 3;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const float p0 = __ldg(p + k);
+            float vel, acc;
+            if (t < T - 1) {
+              const float p1 = __ldg(p + V * 3 + k);
+              vel = p1 - p0;
+              const float veln = (t < T - 2) ? __ldg(p + 2 * V * 3 + k) - p1 : p1;   // vel[T-1] = x[T-1]
+              acc = veln - vel;
+            } else {
+              vel = p0;        // vel[:, -1] = x[:, -1]
+              acc = p0;        // acc[:, -1] = vel[:, -1]
+            }
+            f[k] = p0; f[3 + k] = acc; f[6 + k] = vel;
+            sp = fmaf(vel, vel, sp);
+          }
+          f[9] = sqrtf(sp);
+#pragma unroll
+          for (int c = 0; c < 10; ++c) {
+            const float val = fmaf(gs[c], f[c], gb[c]);
+            xs[c * XS + lane] = val;
+            ag[c * XT + lane] = val;
+          }
+        }
+      } else {
+        const float* p = src + t * st + lane * sv;
+        if (lane < V) {
+#pragma unroll 4
+          for (int c = 0; c < Ci; ++c) {
+            const float val = fmaf(gs[c], __ldg(p + c * sc), gb[c]);
+            xs[c * XS + lane] = val;
+            ag[c * XT + lane] = val;
+          }
+        }
+      }
+      // (the XS - V padding columns of a row are loaded by the LDS.128 reads below but never enter an FMA)
+      __syncwarp();
+      // ---- statistics of the slab (:360-371), lanes = channels; Bessel-corrected like torch.std
+      {
+        float mu = 0.f, q = 0.f;
+        if (lane < Ci) {
+          const float* xr = ag + lane * XT;
+          float xv[V];
+          float s = 0.f;
+#pragma unroll
+          for (int v = 0; v < V; ++v) { xv[v] = xr[v]; s += xv[v]; }
+          mu = s / V;
+#pragma unroll
+          for (int v = 0; v < V; ++v) { const float dd = xv[v] - mu; q = fmaf(dd, dd, q); }
+          // merge (n_b = V, mean mu, M2 q) into the running (n_a = t*V, ch_mean, ch_m2)
+          const float na = (float)(t * V), nb = (float)V;
+          const float delta = mu - ch_mean;
+          ch_mean += delta * (nb / (na + nb));
+          ch_m2 += q + delta * delta * (na * nb / (na + nb));
+        }
+        const float sd = lane < Ci ? sqrtf(q / (V - 1)) : 0.f;
+        const float s1 = warp_sum(lane < Ci ? mu : 0.f);
+        const float m2 = warp_sum(sd) / Ci;
+        const float dd = lane < Ci ? sd - m2 : 0.f;
+        const float q2 = warp_sum(dd * dd);
+        if (lane == 0) { red[RL.stats + 1 + t] = s1 / Ci; red[RL.stats + 2 + T + t] = sqrtf(q2 / (Ci - 1)); }
+      }
+      __syncwarp();            // the transposed copy is dead: its region becomes the map buffer
+      // ---- stacked 1x1 convolutions over the slab: lanes = output channels, registers = joints
+      float acc_e[NE][V];
+#pragma unroll
+      for (int j = 0; j < NE; ++j)
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc_e[j][v] = 0.f;
+      {
+        const float* we = wa0 + lane;
+        const float* wgp = wg0 + t * mpg + lane;                    // row (c*T + t)
+        const float* xr = xs;
+#pragma unroll 2
+        for (int c = 0; c < Ci; ++c) {
+          float x[XS];
+#pragma unroll
+          for (int i = 0; i < V4; ++i) {
+            const float4 q4 = *reinterpret_cast<const float4*>(xr + 4 * i);
+            x[4 * i] = q4.x; x[4 * i + 1] = q4.y; x[4 * i + 2] = q4.z; x[4 * i + 3] = q4.w;
+          }
+          const float wgv = wgp[0];
+          if (interp) {
+#pragma unroll
+            for (int j = 0; j < NE; ++j) {
+              const float wv = we[32 * j];
+#pragma unroll
+              for (int v = 0; v < V; ++v) acc_e[j][v] = fmaf(wv, x[v], acc_e[j][v]);
+            }
+          }
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc_g[v] = fmaf(wgv, x[v], acc_g[v]);
+          we += mpe;
+          wgp += T * mpg;
+          xr += XS;
+        }
+      }
+      if (interp) {
+        // ---- BN + PReLU of the entry maps -> ag[m][v]  (:139-140, :147-148)
+#pragma unroll
+        for (int j = 0; j < NE; ++j) {
+          const int m = lane + 32 * j;
+          if (m < 4 * Ch) {
+            float* ar = ag + m * AS;
+#pragma unroll
+            for (int v = 0; v < V; ++v) ar[v] = prelu(acc_e[j][v] + e_b[j], e_a[j]);
+          }
+        }
+        __syncwarp();
+        // ---- collapsing convolutions (:141-142, :149-150): lanes = outputs (domain L3, channel o)
+        {
+          const float* wt = wtc + t * mpc + lane;                   // row (c'*T + t)
+          const float* wj = wjc + lane;                             // row (c'*V + v)
+          float jsum = 0.f;
+#pragma unroll 2
+          for (int cp_ = 0; cp_ < Ch; ++cp_) {
+            float xa[XS], xg[XS];
+#pragma unroll
+            for (int i = 0; i < V4; ++i) {
+              const float4 q4 = *reinterpret_cast<const float4*>(arow_tc + cp_ * AS + 4 * i);
+              xa[4 * i] = q4.x; xa[4 * i + 1] = q4.y; xa[4 * i + 2] = q4.z; xa[4 * i + 3] = q4.w;
+              const float4 g4 = *reinterpret_cast<const float4*>(arow_jc + cp_ * AS + 4 * i);
+              xg[4 * i] = g4.x; xg[4 * i + 1] = g4.y; xg[4 * i + 2] = g4.z; xg[4 * i + 3] = g4.w;
+            }
+            const float wtv = wt[cp_ * T * mpc];
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc_tc[v] = fmaf(wtv, xa[v], acc_tc[v]);
+            const float* wjr = wj + cp_ * V * mpc;
+            float j0 = 0.f, j1 = 0.f;
+#pragma unroll
+            for (int v = 0; v + 1 < V; v += 2) {
+              j0 = fmaf(wjr[v * mpc], xg[v], j0);
+              j1 = fmaf(wjr[(v + 1) * mpc], xg[v + 1], j1);
+            }
+            if (V & 1) j0 = fmaf(wjr[(V - 1) * mpc], xg[V - 1], j0);
+            jsum += j0 + j1;
+          }
+          if (lane < 2 * Ch) red[RL.jc + lane * T + t] = jsum + smem[a.o_jc3_b + lane];
+        }
+      }
+      __syncwarp();              // slab and map rows are read: the next slab may overwrite them
+    }
+
+    // ---------------- per-sample results
+    {
+      // channel-level statistics: mean over channels of the channel means, std over channels of the channel stds
+      const float cm = lane < Ci ? ch_mean : 0.f;
+      const float sd = lane < Ci ? sqrtf(ch_m2 / (TV - 1)) : 0.f;
+      const float s1 = warp_sum(cm);
+      const float m2 = warp_sum(sd) / Ci;
+      const float dd = lane < Ci ? sd - m2 : 0.f;
+      const float q2 = warp_sum(dd * dd);
+      if (lane == 0) { red[RL.stats] = s1 / Ci; red[RL.stats + 1 + T] = sqrtf(q2 / (Ci - 1)); }
+    }
+    // gate conv (T,1) + BN + PReLU -> h1 (:323-326); staged through shared memory for coalesced stores
+    if (lane < 2 * Cg) {
+      const float bb = smem[a.o_g0_b + lane], sl = smem[a.o_g0_a + lane / Cg];
+      float* ar = ag + lane * AS;
+#pragma unroll
+      for (int v = 0; v < V; ++v) ar[v] = prelu(acc_g[v] + bb, sl);
+    }
+    __syncwarp();
+    for (int i = lane; i < 2 * RL.h1g; i += 32) {
+      const int g = i / RL.h1g, r = i - g * RL.h1g;
+      red[RL.h1 + i] = r < Cg * V ? ag[(g * Cg + r / V) * AS + (r % V)] : 0.f;
+    }
+    __syncwarp();
+    if (interp) {
+      if (lane < 2 * Ch) {
+        const float bb = smem[a.o_tc3_b + lane];
+        float* ar = ag + lane * AS;
+#pragma unroll
+        for (int v = 0; v < V; ++v) ar[v] = acc_tc[v] + bb;
+      }
+      __syncwarp();
+      for (int i = lane; i < 2 * Ch * V; i += 32) red[RL.tc + i] = ag[(i / V) * AS + (i % V)];
+      __syncwarp();
+    }
+  }
+}
+
+template <int T, int V, int NE>
+inline int launch_reduce_impl(const ReduceArgs& a, void* stream) {
+  return launch_warp_per_sample(dstd_reduce_kernel<T, V, NE>, a, stream);
+}
+
+}  // namespace cg

@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
       const uint32_t acc0 = tmem, cacc0 = tmem + 192;
       uint32_t u0 = 0, ar = 0, it = 0;
       long long w_in = 0, w_ar = 0, w_acc = 0, w_full = 0, w_stg = 0;
-      const long long t_begin = clock64();
+      const long long t_begin = CG_CLOCK();
       for (int b = blockIdx.x; b < a.batch; b += gridDim.x, ++it) {
         mbar_wait_timed(bar(FB_IN_READY), it & 1, w_in);
         tc_fence_after();
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
         }
       }
       if (a.dbg && blockIdx.x == 0 && lane == 0) {
-        a.dbg[0] = clock64() - t_begin; a.dbg[1] = w_in; a.dbg[2] = w_ar; a.dbg[3] = w_acc; a.dbg[4] = w_full; a.dbg[5] = w_stg;
+        a.dbg[0] = CG_CLOCK() - t_begin; a.dbg[1] = w_in; a.dbg[2] = w_ar; a.dbg[3] = w_acc; a.dbg[4] = w_full; a.dbg[5] = w_stg;
         a.dbg[6] = it;
       }
     }
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
     const int et = tid - 128;
     uint32_t u = 0, lv = 0, it = 0;
     long long w_in = 0, w_accf = 0, w_stge = 0, w_cacc = 0, w_nb = 0, c_ld = 0, c_e1 = 0, c_e2 = 0;
-    const long long t_begin = clock64();
+    const long long t_begin = CG_CLOCK();
     for (int b = blockIdx.x; b < a.batch; b += gridDim.x, ++it) {
       mbar_wait_timed(bar(FB_IN_READY), it & 1, w_in);      // cst_in of this sample is visible
       for (int l = 0; l < L; ++l) {
@@ -347,11 +347,11 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
           mbar_wait_timed(bar(FB_ACC_FULL + t), u & 1, w_accf);
           tc_fence_after();
           mbar_wait_timed(bar(FB_STG_EMPTY + t), (u & 1) ^ 1, w_stge);
-          const long long te1 = clock64();
+          const long long te1 = CG_CLOCK();
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             float o[16];
-            { const long long tl = clock64(); ftc_load_sum(acc + half * 16, o); c_ld += clock64() - tl; }
+            { const long long tl = CG_CLOCK(); ftc_load_sum(acc + half * 16, o); c_ld += CG_CLOCK() - tl; }
 #pragma unroll
             for (int i = 0; i < 16; ++i) o[i] = prelu(o[i] + prm[FTC_PRM_BIAS + d * 32 + half * 16 + i], slope);
             ftc_split_store8(&o[0], stage_row + (2 * half) * FTC_STAGE_CHUNK, 4 * FTC_STAGE_CHUNK);
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
           mbar_arrive(bar(FB_ACC_EMPTY + t));
           fence_proxy_async();
           mbar_arrive(bar(FB_STG_FULL + t));
-          c_e1 += clock64() - te1;
+          c_e1 += CG_CLOCK() - te1;
         }
         // ---- compress epilogue: bias + average branch, caller's PReLU (+ residual) ----
         const bool last = l == L - 1;
@@ -377,10 +377,10 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
         mbar_wait_timed(bar(FB_CACC_FULL + t), lv & 1, w_cacc);
         ++lv;
         tc_fence_after();
-        { const long long tb = clock64(); named_bar(1, 256); w_nb += clock64() - tb; }   // this layer's cst is in place
+        { const long long tb = CG_CLOCK(); named_bar(1, 256); w_nb += CG_CLOCK() - tb; }   // this layer's cst is in place
         const float* cst = l == 0 ? cst_in + (it & 1) * 32 : cstv + (l & 1) * 32;
         float* csn = chsum + ((l + 1) & 1) * 256;
-        const long long te2 = clock64();
+        const long long te2 = CG_CLOCK();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           float o[16];
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
         if (!last) {
           fence_proxy_async();
           mbar_arrive(bar(FB_A_READY));                     // the next layer's convolutions may start
-          c_e2 += clock64() - te2;
+          c_e2 += CG_CLOCK() - te2;
           float mine = 0.f;                                 // channel sums for its average branch, off the critical path
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
     }
     if (a.dbg && blockIdx.x == 0 && (tid == 128 || tid == 256)) {
       long long* o = a.dbg + (tid == 128 ? 8 : 16);
-      o[0] = clock64() - t_begin; o[1] = w_in; o[2] = w_accf; o[3] = w_stge; o[4] = w_cacc; o[5] = w_nb;
+      o[0] = CG_CLOCK() - t_begin; o[1] = w_in; o[2] = w_accf; o[3] = w_stge; o[4] = w_cacc; o[5] = w_nb;
       if (tid == 128) { a.dbg[24] = c_ld; a.dbg[25] = c_e1; a.dbg[26] = c_e2; }
     }
   }

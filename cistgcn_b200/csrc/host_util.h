@@ -87,4 +87,19 @@ inline int grid_for(long long batch, int per_sm) {
   return (int)(batch < g ? batch : g);
 }
 
+
+// Host: launch of a warp-per-sample kernel (`nwarps` samples per CTA pass).  Returns 0 or a CUDA error code.
+template <class K, class ARGS>
+inline int launch_warp_per_sample(K kfn, const ARGS& a, void* stream) {
+  const int nt = 32 * a.nwarps;
+  const size_t smem = (size_t)a.smem_floats * sizeof(float);
+  int err = 0;
+  const int per_sm = prepared_blocks_per_sm(kfn, nt, smem, &err);
+  if (err) return err;
+  const long long ctas = ((long long)a.batch + a.nwarps - 1) / a.nwarps;
+  const int grid = grid_for(ctas, per_sm);
+  CG_LAUNCH(kfn, grid, nt, smem, stream, a);
+  return last_launch_error();
+}
+
 }  // namespace cg

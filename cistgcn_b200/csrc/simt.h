@@ -19,6 +19,13 @@
 
 #define CG_DEV __device__ __forceinline__
 
+// Cycle accounting of the debug hooks exists only in -DCISTGCN_PROFILE builds; elsewhere it folds to constants.
+#if defined(CISTGCN_PROFILE) && !defined(CISTGCN_EMU)
+#define CG_CLOCK() clock64()
+#else
+#define CG_CLOCK() 0LL
+#endif
+
 namespace cg {
 
 CG_DEV float prelu(float v, float a) { return v >= 0.f ? v : a * v; }

@@ -17,6 +17,9 @@ def mpjpe(predicted: torch.Tensor, target: torch.Tensor, w=None, dim=-1, reduce_
     if predicted.dtype != torch.float32 or target.dtype != torch.float32 or not predicted.is_cuda \
             or predicted.device != target.device:
         raise ValueError("cistgcn_b200.mpjpe: float32 CUDA tensors on one device required (no CPU fallback)")
+    if torch.is_grad_enabled() and (predicted.requires_grad or target.requires_grad):
+        raise NotImplementedError("cistgcn_b200.mpjpe: the fused reduction is not differentiable (no backward kernel "
+                                  "on this path); call it under torch.no_grad() or on detached tensors")
     lib = _cabi.lib()
     B, T, V, _ = predicted.shape
     p, t = predicted.contiguous(), target.contiguous()
@@ -30,6 +33,10 @@ def mpjpe(predicted: torch.Tensor, target: torch.Tensor, w=None, dim=-1, reduce_
     if isinstance(reduce_axis, int):
         reduce_axis = (reduce_axis,)
     axes = tuple(sorted(a % 3 for a in reduce_axis))
+    if axes not in ((), (0, 2), (0, 1, 2)):
+        # other reductions (e.g. [1, 2]: per-sample MPJPE, adversarial_attacks.py:193, 521): mean of the kernel's
+        # per-joint errors over the requested axes
+        return mpjpe(predicted, target, w, dim, None).mean(axes)
     sums = torch.zeros(T, device=p.device, dtype=torch.float64)
     with torch.cuda.device(p.device):
         _cabi.check(lib.cistgcn_mpjpe_f32(p.data_ptr(), t.data_ptr(), B, T, V, None, sums.data_ptr(), stream),
@@ -38,7 +45,4 @@ def mpjpe(predicted: torch.Tensor, target: torch.Tensor, w=None, dim=-1, reduce_
         return (sums.sum() / (B * T * V)).to(torch.float32)
     if axes == (0, 2):
         return (sums / (B * V)).to(torch.float32)
-    if axes == (0, 1, 2):
-        return (sums.sum() / (B * T * V)).to(torch.float32)
-    raise ValueError(f"cistgcn_b200.mpjpe: reduce_axis {reduce_axis} is not used on this path "
-                     "(supported: [], (0, 2), None)")
+    return (sums.sum() / (B * T * V)).to(torch.float32)

@@ -14,17 +14,26 @@ under the same seed (checked in tests/test_module_contract.py when /root/referen
 from __future__ import annotations
 
 import copy
+import time
+import warnings
 from typing import Dict, List, Optional, Tuple
 
 import torch
 import torch.nn as nn
 
 from . import _cabi
-from .pack import ModelGeometry, PackedModel, pack_state_dict
+from .pack import F, ModelGeometry, PackedModel, pack_state_dict
+
+
+_TREE_EPOCH = [0]     # bumped by every attribute assignment on a container: cached tensor lists are rebuilt
 
 
 class _Node(nn.Module):
     """Anonymous container; children are attached by (possibly numeric) name."""
+
+    def __setattr__(self, name, value):
+        _TREE_EPOCH[0] += 1
+        super().__setattr__(name, value)
 
     def forward(self, *a, **k):  # pragma: no cover - containers are never called
         raise RuntimeError("cistgcn_b200: parameter container, not a callable layer")
@@ -265,9 +274,14 @@ class CISTGCN(nn.Module):
         self._packed: Optional[PackedModel] = None
         self._packed_key = None
         self._tensor_cache = None
+        self._tree_epoch = -1
+        self.check_weights = False      # True: checksum the state on the device before every forward (synchronises)
+        self.kernel_flags = 0           # CISTGCN_FLAG_* kernel choices, travels with every call (CP_FLAGS of the plan)
+        self.pack_count = 0
+        self.last_pack_ms = 0.0
+        self._warned_fpn_fallback = False
         # load_state_dict(assign=True) swaps Parameter objects: drop the cached tensor list afterwards
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate_pack())
-        self._workspace: Optional[torch.Tensor] = None
         self._taps_enabled = False
         self.last_taps: Dict[str, torch.Tensor] = {}
 
@@ -280,32 +294,75 @@ class CISTGCN(nn.Module):
                              reduction=self.reduction, feat_ch=self.in_ch)
 
     def _state_tensors(self):
-        # state_dict() rebuilds 1 178 prefixed keys per call (~1 ms); the tensor objects themselves only change
-        # when the module is moved (_apply replaces buffers), so cache the list and watch the version counters.
-        if self._tensor_cache is None:
-            self._tensor_cache = list(self.state_dict(keep_vars=True).values())
-        return self._tensor_cache
+        # state_dict() rebuilds 1 178 prefixed keys per call (~1 ms).  What is cached instead is the list of SLOTS
+        # (owning module's _parameters / _buffers dict + name), read afresh on every call, so a replaced Parameter
+        # object (`conv.weight = nn.Parameter(...)`) is seen.  The slot list itself is rebuilt whenever the module
+        # tree could have changed: _apply (.to / .cuda), load_state_dict, attribute assignment on a container.
+        if self._tensor_cache is None or self._tree_epoch != _TREE_EPOCH[0]:
+            slots = []
+            for mod in self.modules():
+                slots += [(mod._parameters, n) for n, v in mod._parameters.items() if v is not None]
+                slots += [(mod._buffers, n) for n, v in mod._buffers.items()
+                          if v is not None and v.is_floating_point() and n not in mod._non_persistent_buffers_set]
+            self._tensor_cache = slots
+            self._tree_epoch = _TREE_EPOCH[0]
+        return [d[n] for d, n in self._tensor_cache]
 
     def _invalidate_pack(self):
         self._tensor_cache = None
         self._packed = None
+
+    def invalidate_pack(self):
+        """Forget the packed device weights; the next forward re-packs from the current parameters.  Call this
+        (or ``repack()``) after writes that PyTorch's version counters cannot see, i.e. through ``.data``
+        (``p.data.copy_()``, EMA / weight averaging, ``gcn.A.data.uniform_()`` as in CISTGCN.py:120), unless
+        ``check_weights`` is on."""
+        self._invalidate_pack()
+        return self
+
+    def repack(self, device=None) -> PackedModel:
+        """Unconditionally re-pack from the current parameters / buffers (see ``invalidate_pack``)."""
+        self._invalidate_pack()
+        return self.pack(device)
 
     def _apply(self, fn, *args, **kwargs):
         self._invalidate_pack()
         return super()._apply(fn, *args, **kwargs)
 
     def _state_key(self, device):
-        return (str(device),) + tuple(t._version for t in self._state_tensors())
+        # (storage address, version) per tensor: catches in-place updates through the autograd-visible API
+        # (optimizer steps, load_state_dict, p.mul_()) and storage swaps (p.data = other).  Writes *through*
+        # p.data keep both unchanged; those need invalidate_pack() or check_weights.
+        ts = self._state_tensors()
+        return (str(device),) + tuple((t.data_ptr(), t._version) for t in ts)
+
+    def _state_checksum(self):
+        """Order-sensitive checksum of every floating-point state entry, computed on the tensors' device
+        (check_weights mode only: the comparison synchronises the stream)."""
+        ts = self._state_tensors()
+        flat = torch.cat([t.detach().reshape(-1).to(torch.float32) for t in ts])
+        bits = flat.view(torch.int32).to(torch.int64)
+        idx = torch.arange(1, bits.numel() + 1, device=bits.device, dtype=torch.int64)
+        return int(((bits * (idx % 65521 + 1)).sum() ^ bits.sum()).item())
 
     def pack(self, device=None) -> PackedModel:
         """Fold eval-mode BatchNorm + biases and lay the weights out in one device blob
         (re-run automatically whenever a parameter / buffer changed since the last forward)."""
         device = torch.device(device) if device is not None else next(self.parameters()).device
         key = self._state_key(device)
+        if self.check_weights:
+            key = key + (self._state_checksum(),)
         if self._packed is None or key != self._packed_key:
+            t0 = time.perf_counter()
             sd = {k: v.detach() for k, v in self.state_dict().items()}
             self._packed = pack_state_dict(sd, self.geometry(), device)
             self._packed_key = key
+            self.pack_count += 1
+            self.last_pack_ms = 1e3 * (time.perf_counter() - t0)
+            if not self._packed.fpn_tc and not self._warned_fpn_fallback:
+                self._warned_fpn_fallback = True
+                warnings.warn("cistgcn_b200: the FPN stack runs on the FP32-FMA kernel for these weights "
+                              f"({self._packed.fpn_tc_reason}); the tcgen05 kernel is ~2.5x faster", RuntimeWarning)
         return self._packed
 
     def enable_taps(self, on: bool = True):
@@ -341,6 +398,8 @@ class CISTGCN(nn.Module):
 
     def _run(self, x, target):
         self._check_input(x)
+        if torch.is_grad_enabled() and x.requires_grad and not self.training:
+            return self._run_differentiable(x, target)
         if self.training:
             raise NotImplementedError(
                 "cistgcn_b200: train-mode forward (batch-statistics BatchNorm + dropout) is not built yet; "
@@ -349,12 +408,14 @@ class CISTGCN(nn.Module):
         x = x.contiguous()
         B = x.shape[0]
         packed = self.pack(x.device)
+        packed.plan_c[F["CP_FLAGS"]] = int(self.kernel_flags)
         pred = torch.empty(B, self.n_output, self.n_joints, 3, device=x.device, dtype=torch.float32)
         if B == 0:
             return pred, torch.zeros(self.n_output, device=x.device, dtype=torch.float64)
+        # per-call scratch from the caching allocator: stream-ordered, so two forwards of one module on different
+        # streams never share a buffer (a cached per-module buffer would race)
         need = lib.cistgcn_workspace_bytes(packed.plan_c, B)
-        if self._workspace is None or self._workspace.device != x.device or self._workspace.numel() < need:
-            self._workspace = torch.empty(need, device=x.device, dtype=torch.uint8)
+        workspace = torch.empty(need, device=x.device, dtype=torch.uint8)
         sums = None
         if target is not None:
             sums = torch.zeros(self.n_output, device=x.device, dtype=torch.float64)
@@ -367,13 +428,20 @@ class CISTGCN(nn.Module):
                                          x.data_ptr(), pred.data_ptr(),
                                          target.data_ptr() if target is not None else None,
                                          sums.data_ptr() if sums is not None else None,
-                                         self._workspace.data_ptr(), self._workspace.numel(), B,
+                                         workspace.data_ptr(), workspace.numel(), B,
                                          taps_struct, stream)
         _cabi.check(rc, "cistgcn_forward_f32")
         if self._taps_enabled:
             self.last_taps = holders
             self._publish_taps(holders)
         return pred, sums
+
+    def _run_differentiable(self, x, target):
+        """Eval-mode forward with autograd w.r.t. the input (environment/adversarial_attacks.py:184, 422, 495-511)."""
+        raise NotImplementedError(
+            "cistgcn_b200: x.requires_grad is set, but the input-gradient path (SURVEY.md 8 f3) is not built; "
+            "the fused eval-mode forward returns tensors detached from autograd.  Wrap the call in "
+            "torch.no_grad() or pass x.detach() if no gradient is wanted.")
 
     def _publish_taps(self, taps: Dict[str, torch.Tensor]):
         """Expose the interpretability outputs as attributes on the same dotted paths the reference sets

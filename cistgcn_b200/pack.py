@@ -74,6 +74,8 @@ class PackedModel:
     plan_c: "ctypes.Array"        # (c_int32 * len(plan)), host memory
     geometry: ModelGeometry
     offsets: Dict[str, int]       # debug: entry name -> float offset
+    fpn_tc: bool = True           # every FPN layer carries its tcgen05 operand image (else: FP32-FMA kernel)
+    fpn_tc_reason: str = ""       # why not, when fpn_tc is False
 
     def block_desc(self, which: str, i: int) -> "ctypes.Array":
         g = self.geometry
@@ -130,22 +132,52 @@ class _Blob:
         return torch.cat(words).view(torch.float32).to(device).contiguous()
 
 
+def host_state(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """state_dict -> fp64 host tensors with ONE device-to-host transfer per source device: the floating-point
+    entries are flattened into a single buffer on their device (one concatenation kernel), copied once and
+    split into views on the host.  (Per-tensor `.double().cpu()` cost ~1.2 K cast kernels + ~1.2 K synchronous
+    copies per pack.)  `num_batches_tracked` counters are not needed for packing and are skipped."""
+    out: Dict[str, torch.Tensor] = {}
+    by_dev: Dict[torch.device, List[str]] = {}
+    for k, t in sd.items():
+        if not t.is_floating_point():
+            continue
+        by_dev.setdefault(t.device, []).append(k)
+    for dev, keys in by_dev.items():
+        ts = [sd[k].detach() for k in keys]
+        if len({t.dtype for t in ts}) != 1:
+            ts = [t.to(torch.float32) for t in ts]
+        flat = torch.cat([t.reshape(-1) for t in ts]).cpu().to(torch.float64)
+        off = 0
+        for k, t in zip(keys, ts):
+            n = t.numel()
+            out[k] = flat[off: off + n].view(t.shape)
+            off += n
+    return out
+
+
 def _fold(sd, p):
-    g, b = sd[p + ".weight"].double().cpu(), sd[p + ".bias"].double().cpu()
-    m, v = sd[p + ".running_mean"].double().cpu(), sd[p + ".running_var"].double().cpu()
+    g, b = sd[p + ".weight"], sd[p + ".bias"]
+    m, v = sd[p + ".running_mean"], sd[p + ".running_var"]
     s = g / torch.sqrt(v + BN_EPS)
     return s, b - m * s
 
 
 def _w(sd, k):
-    return sd[k].double().cpu()
+    return sd[k]
 
 
-def _kmajor(W: torch.Tensor) -> torch.Tensor:
-    """(M, K) -> [K][pad(M)] zero padded."""
+def _kmajor(W: torch.Tensor, pad: int = MPAD) -> torch.Tensor:
+    """(M, K) -> [K][pad_up(M, pad)] zero padded."""
     M, K = W.shape
-    out = torch.zeros(K, pad_up(M), dtype=torch.float64)
+    out = torch.zeros(K, pad_up(M, pad), dtype=torch.float64)
     out[:, :M] = W.t()
+    return out
+
+
+def _padvec(v: torch.Tensor, pad: int) -> torch.Tensor:
+    out = torch.zeros(pad_up(v.numel(), pad), dtype=torch.float64)
+    out[: v.numel()] = v.reshape(-1)
     return out
 
 
@@ -188,6 +220,8 @@ def _pack_block(blob: _Blob, sd, p: str, ci: int, co: int, T: int, V: int, inter
         m4.append(_kmajor(_w(sd, f"{p}.{mk}.4.weight")))
     put("CB_G0_WT", "g0_wt", _kmajor(torch.cat(w0, 0)))
     put("CB_G0_B", "g0_b", torch.cat(b0))
+    put("CB_R_G0_WT", "r_g0_wt", _kmajor(torch.cat(w0, 0), 32))     # reduce stage: lane = output channel
+    put("CB_R_G0_B", "r_g0_b", _padvec(torch.cat(b0), 32))
     put("CB_G0_A", "g0_a", torch.cat(a0))
     put("CB_G4_WT", "g4_wt", torch.stack(w4))
     put("CB_G4_B", "g4_b", torch.stack(b4))
@@ -199,6 +233,7 @@ def _pack_block(blob: _Blob, sd, p: str, ci: int, co: int, T: int, V: int, inter
     # ---- Map2Adj (CISTGCN.py:127-189) or static adjacency (:106-120)
     if interp:
         aw, ab, aa = [], [], []
+        tc3w, tc3b, jc3w, jc3b = [], [], [], []
         for li, Lname in enumerate(("dsgn", "tsgn")):
             q = f"{p}.{Lname}.map_to_adj"
             sfx = "_S" if li == 0 else "_T"
@@ -210,10 +245,14 @@ def _pack_block(blob: _Blob, sd, p: str, ci: int, co: int, T: int, V: int, inter
             s, b = _fold(sd, f"{q}.time_compress.4")
             put("CB_TC3_WT" + sfx, Lname + ".tc3_wt", _kmajor(s[:, None] * _w(sd, f"{q}.time_compress.3.weight").reshape(ch, ch * T)))
             put("CB_TC3_B" + sfx, Lname + ".tc3_b", b)
+            tc3w.append(s[:, None] * _w(sd, f"{q}.time_compress.3.weight").reshape(ch, ch * T))
+            tc3b.append(b)
             put("CB_TC6_WT" + sfx, Lname + ".tc6_wt", _kmajor(_w(sd, f"{q}.time_compress.6.weight").reshape(T, ch)))
             s, b = _fold(sd, f"{q}.joint_compress.4")
             put("CB_JC3_WT" + sfx, Lname + ".jc3_wt", _kmajor(s[:, None] * _w(sd, f"{q}.joint_compress.3.weight").reshape(ch, ch * V)))
             put("CB_JC3_B" + sfx, Lname + ".jc3_b", b)
+            jc3w.append(s[:, None] * _w(sd, f"{q}.joint_compress.3.weight").reshape(ch, ch * V))
+            jc3b.append(b)
             put("CB_JC6_WT" + sfx, Lname + ".jc6_wt", _kmajor(_w(sd, f"{q}.joint_compress.6.weight").reshape(V, ch)))
             n = V if li == 0 else T
             s, b = _fold(sd, f"{q}.expansor.1")
@@ -225,6 +264,12 @@ def _pack_block(blob: _Blob, sd, p: str, ci: int, co: int, T: int, V: int, inter
         tc_mats["CB_TC_A0"] = (torch.cat(aw, 0), [ci])
         put("CB_A0_B", "a0_b", torch.cat(ab))
         put("CB_A0_A", "a0_a", torch.cat(aa))
+        put("CB_R_A0_WT", "r_a0_wt", _kmajor(torch.cat(aw, 0), 32))
+        put("CB_R_A0_B", "r_a0_b", _padvec(torch.cat(ab), 32))
+        put("CB_R_TC3_WT", "r_tc3_wt", _kmajor(torch.cat(tc3w, 0), 32))
+        put("CB_R_TC3_B", "r_tc3_b", _padvec(torch.cat(tc3b), 32))
+        put("CB_R_JC3_WT", "r_jc3_wt", _kmajor(torch.cat(jc3w, 0), 32))
+        put("CB_R_JC3_B", "r_jc3_b", _padvec(torch.cat(jc3b), 32))
     else:
         put("CB_ADJ_S", "adj_s", _w(sd, f"{p}.dsgn.gcn.A"))
         put("CB_ADJ_T", "adj_t", _w(sd, f"{p}.tsgn.gcn.A"))
@@ -322,13 +367,14 @@ def tc_image(Wm: torch.Tensor, segs) -> torch.Tensor:
 TC_PRM_BIAS, TC_PRM_SLOPE, TC_PRM_OUT_A, TC_PRM_CPB, TC_PRM_WAVG, TC_PRM_FLOATS = 0, 96, 99, 100, 132, 132 + 32 * 32
 
 
-def _pack_fpn_tc(blob: _Blob, sd, p: str, prelu_key: str, cin: int, cout: int, d: List[int]) -> None:
-    """Tensor-core image of one FPN layer (only when it fits the kernel's 32-wide tiles)."""
+def _pack_fpn_tc(blob: _Blob, sd, p: str, prelu_key: str, cin: int, cout: int, d: List[int]) -> str:
+    """Tensor-core image of one FPN layer (only when it fits the kernel's 32-wide tiles).
+    Returns "" or the reason the layer has no image (the chain then runs on the FP32-FMA kernel)."""
     if cout > 32 or cin > 32:
-        return
+        return f"{p}: {cin}->{cout} channels exceed the 32-wide tensor-core tiles"
     folded = [_fold(sd, f"{p}.block{i}.1")[0][:, None, None, None] * _w(sd, f"{p}.block{i}.0.weight") for i in (1, 2, 3)]
     if max(float(t.abs().max()) for t in folded + [_w(sd, f"{p}.compress.weight")]) >= TC_FP16_MAX:
-        return      # the fp16 copy of the weights would overflow: this layer stays on the FP32-FMA kernel
+        return f"{p}: |weight| >= {TC_FP16_MAX:g} would overflow the fp16 operand copy"
     kc = pad_up(cin, 16) // 8
     words, prm = [], torch.zeros(TC_PRM_FLOATS, dtype=torch.float64)
     Wc = _w(sd, f"{p}.compress.weight").reshape(cout, 3 * cout + cin)
@@ -349,9 +395,10 @@ def _pack_fpn_tc(blob: _Blob, sd, p: str, prelu_key: str, cin: int, cout: int, d
     d[F["CF_TC_KC"]] = kc
     d[F["CF_TC_W"]] = blob.add_raw(f"{p}:tc_w", torch.cat(words))
     d[F["CF_TC_PRM"]] = blob.add(f"{p}:tc_prm", prm)
+    return ""
 
 
-def _pack_fpn(blob: _Blob, sd, p: str, prelu_key: str, cin: int, cout: int, resid: bool) -> List[int]:
+def _pack_fpn(blob: _Blob, sd, p: str, prelu_key: str, cin: int, cout: int, resid: bool, notes: List[str]) -> List[int]:
     if cout % 5 != 0:
         raise ValueError("cistgcn_b200 FPN kernel needs output_n to be a multiple of 5")
     d = [0] * F["CF_COUNT"]
@@ -371,7 +418,9 @@ def _pack_fpn(blob: _Blob, sd, p: str, prelu_key: str, cin: int, cout: int, resi
     d[F["CF_CP_AVG_WT"]] = blob.add(f"{p}:cp_avg_wt", _kmajor(Wc[:, 3 * cout:]))
     d[F["CF_CP_B"]] = blob.add(f"{p}:cp_b", _w(sd, f"{p}.compress.bias"))
     d[F["CF_OUT_A"]] = blob.add(f"{p}:out_a", _w(sd, prelu_key + ".weight"))
-    _pack_fpn_tc(blob, sd, p, prelu_key, cin, cout, d)
+    why = _pack_fpn_tc(blob, sd, p, prelu_key, cin, cout, d)
+    if why:
+        notes.append(why)
     return d
 
 
@@ -437,6 +486,7 @@ def _pack_tail(blob: _Blob, sd, g: ModelGeometry) -> List[int]:
 
 def pack_state_dict(sd: Dict[str, torch.Tensor], g: ModelGeometry, device) -> PackedModel:
     """Reference-named state_dict -> (device blob, plan).  Called by CISTGCN.pack()."""
+    sd = host_state(sd)                      # fp64 on the host, one transfer
     blob = _Blob()
     T, V, To, Fc = g.input_n, g.joints, g.output_n, g.feat_ch
     n_in, n_out = len(g.in_chain) - 1, len(g.out_chain) - 1
@@ -454,8 +504,9 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], g: ModelGeometry, device) -> Pa
         out_str = (T * co * V, V, co * V, 1) if i == n_in - 1 else (co * TV, TV, V, 1)
         plan += _pack_block(blob, sd, f"st_gcnns.{i}", ci, co, T, V, g.in_interp[i], g.reduction,
                             in_mode, in_str, out_str)
+    fpn_notes: List[str] = []
     for j in range(g.n_fpn):
-        plan += _pack_fpn(blob, sd, f"txcnns.{j}", f"prelus.{j}", T if j == 0 else To, To, j > 0)
+        plan += _pack_fpn(blob, sd, f"txcnns.{j}", f"prelus.{j}", T if j == 0 else To, To, j > 0, fpn_notes)
     plan += _pack_tail(blob, sd, g)
     for i in range(n_out):
         ci, co = g.out_chain[i], g.out_chain[i + 1]
@@ -472,4 +523,7 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], g: ModelGeometry, device) -> Pa
     plan[F["CP_WEIGHT_FLOATS"]] = blob.size
     dev_blob = blob.finish(device)
     plan_c = (ctypes.c_int32 * len(plan))(*plan)
-    return PackedModel(blob=dev_blob, plan=plan, plan_c=plan_c, geometry=g, offsets=blob.offsets)
+    if not fpn_notes and (V not in (22, 18) or To > 25 or T > 16 or g.n_fpn > 4):
+        fpn_notes.append(f"shape (input_n={T}, output_n={To}, joints={V}, {g.n_fpn} layers) has no tcgen05 instantiation")
+    return PackedModel(blob=dev_blob, plan=plan, plan_c=plan_c, geometry=g, offsets=blob.offsets,
+                       fpn_tc=not fpn_notes, fpn_tc_reason="; ".join(fpn_notes))

@@ -5,7 +5,11 @@
  * buffer (packed weights, activations, workspace) is allocated and owned by the caller on the
  * device the call runs on; `stream` is a cudaStream_t passed as void*.  All entry points
  * return 0 on success and a negative code on error; cistgcn_last_error() returns the message of
- * the last failing call on the calling thread.  There is no global mutable state besides that.
+ * the last failing call on the calling thread (thread-local).  Kernel choices travel with the call
+ * (CP_FLAGS in the plan, `flags` arguments): calls from different host threads on distinct streams,
+ * workspaces and outputs are independent.  The only process-wide state is instrumentation: the
+ * optional launch timer (cistgcn_profile_*, mutex-protected) and, in -DCISTGCN_PROFILE builds only,
+ * the phase-clock debug hooks.
  *
  * What each entry point replaces in the reference (QualityMinds/cistgcn, paths relative to
  * human_motion_prediction/):
@@ -31,11 +35,18 @@
 extern "C" {
 #endif
 
-#define CISTGCN_ABI_VERSION 5
+#define CISTGCN_ABI_VERSION 6
 #define CISTGCN_MPAD 8          /* output-dimension padding of every k-major matrix */
 #define CISTGCN_MAX_BLOCKS 8    /* input + output DSTD-GC blocks in one plan */
 #define CISTGCN_MAX_FPN 8
-#define CISTGCN_PROFILE_KINDS 4  /* 0 DSTD-GC block, 1 FPN chain, 2 context+assembly, 3 mpjpe */
+#define CISTGCN_PROFILE_KINDS 8  /* 0 fused DSTD-GC block, 1 FPN chain, 2 context+assembly, 3 mpjpe,
+                                    4 DSTD reduce stage, 5 DSTD adjacency stage, 6 DSTD mix stage, 7 other */
+
+/* kernel-choice flags (CP_FLAGS of a plan; `flags` of the per-stage entry points); 0 = defaults */
+#define CISTGCN_FLAG_FPN_FP32   1  /* FPN stack on the FP32-FMA kernel (csrc/fpn_chain.cuh) instead of tcgen05 (csrc/fpn_tc.cuh) */
+#define CISTGCN_FLAG_DSTD_FUSED 2  /* DSTD-GC blocks on the round-1 fused one-CTA-per-sample kernel (csrc/dstd_block.cuh) instead
+                                      of the three-stage reduce / adjacency / mix kernels */
+#define CISTGCN_FLAG_DSTD_TC    4  /* with DSTD_FUSED: channel mixes as tcgen05 MMAs where the shared-memory plan fits */
 
 /* ---- one DSTD-GC block (CISTGCN.py:273-390).  *_S/_T pairs: index +0 = dsgn ("space" domain,
  *      TxT adjacency per joint), +1 = tsgn ("time" domain, VxV adjacency per frame). ---------- */
@@ -86,6 +97,11 @@ enum cistgcn_block_field {
   CB_TC_TCN_S, CB_TC_TCN_T,         /* tcn.0 (+BN) [+ residual conv rows]  (Co outputs, K = Ci [+ Ci]) */
   CB_TC_CP,                         /* compressor.0 (+BN)  (Co outputs, K = Co + Co) */
   CB_TC_RS,                         /* block residual conv (+BN)  (Co outputs, K = Ci; HAS_RES only) */
+  /* operands of the reduce stage (csrc/dstd_reduce.cuh): rows padded to 32 outputs so that lane = output channel */
+  CB_R_A0_WT, CB_R_A0_B,            /* Map2Adj first 1x1 convs stacked: [Ci][pad32(4Ch)], bias [pad32(4Ch)] */
+  CB_R_G0_WT, CB_R_G0_B,            /* conv_{s,t}.0 stacked: [Ci*T][pad32(2Cg)] (row c*T + t), bias [pad32(2Cg)] */
+  CB_R_TC3_WT, CB_R_TC3_B,          /* time_compress.3 of dsgn | tsgn side by side: [Ch*T][pad32(2Ch)] (row c*T + t), bias */
+  CB_R_JC3_WT, CB_R_JC3_B,          /* joint_compress.3 of dsgn | tsgn side by side: [Ch*V][pad32(2Ch)] (row c*V + v), bias */
   CB_COUNT
 };
 
@@ -144,6 +160,7 @@ enum cistgcn_plan_field {
   CP_N_OUT_BLOCKS,/* DSTD-GC blocks after the ContextLayer (1) */
   CP_CMAX,        /* widest channel count of any inter-block activation */
   CP_WEIGHT_FLOATS, /* size of the packed weight blob, for bounds checking */
+  CP_FLAGS,       /* CISTGCN_FLAG_* kernel choices for this plan (0 = defaults) */
   CP_HEADER_COUNT
 };
 /* plan layout: [CP_HEADER_COUNT] [n_in x CB_COUNT] [n_fpn x CF_COUNT] [CT_COUNT] [n_out x CB_COUNT] */
@@ -182,13 +199,17 @@ int cistgcn_forward_f32(const int32_t* plan, int32_t plan_len, const float* weig
                         void* workspace, size_t workspace_bytes, int64_t batch,
                         const cistgcn_taps* taps, void* stream);
 
-/* One DSTD-GC block on `batch` samples with the strides in the descriptor. */
+/* One DSTD-GC block on `batch` samples with the strides in the descriptor.  The three-stage path needs
+ * cistgcn_dstd_block_workspace_bytes(desc, batch) bytes of scratch (stage records + gates + adjacencies). */
+size_t cistgcn_dstd_block_workspace_bytes(const int32_t* block_desc, int64_t batch);
 int cistgcn_dstd_block_f32(const int32_t* block_desc, const float* weights, const float* in,
-                           float* out, int64_t batch, const cistgcn_block_taps* taps, void* stream);
+                           float* out, int64_t batch, const cistgcn_block_taps* taps,
+                           void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
 
 /* FPN stack + dim_conversor + cumsum.  in: (B, Tin, F, V) (frames as channels); out x7: (B, Tout, V, 3). */
 int cistgcn_fpn_chain_f32(const int32_t* fpn_descs, int32_t n_fpn, const int32_t* tail_desc,
-                          const float* weights, const float* in, float* x7, int64_t batch, void* stream);
+                          const float* weights, const float* in, float* x7, int64_t batch,
+                          uint32_t flags, void* stream);
 
 /* ContextLayer(x7) + output assembly: pred = x[:, -1:] + x8 + act (+ optional MPJPE partial sums). */
 int cistgcn_tail_f32(const int32_t* tail_desc, const float* weights, const float* x, const float* x7,
@@ -199,26 +220,20 @@ int cistgcn_tail_f32(const int32_t* tail_desc, const float* weights, const float
 int cistgcn_mpjpe_f32(const float* pred, const float* target, int64_t batch, int32_t T, int32_t V,
                       float* err, double* frame_sums, void* stream);
 
-/* FPN stack kernel choice (process-wide): 0 (default) = tcgen05 tensor-core kernel whenever the shape fits
- * (csrc/fpn_tc.cuh), 1 = FP32-FMA kernel (csrc/fpn_chain.cuh).  Both implement CISTGCN.py:38-79, 582-589. */
-int cistgcn_set_fpn_path(int path);
-/* DSTD-GC block channel mixes (Map2Adj entry convs, tcn, compressor, residual conv; CISTGCN.py:229-247, 305-318):
- * 0 (default) = FP32-FMA loops; 1 = tcgen05 MMAs (same split-operand scheme as the FPN kernel) in the 512-thread kernel
- * whenever the shared-memory plan fits (Ci >= 16, <= 64 outputs).  Parity-tested; measured slower than the FMA loops at
- * K = 32 (the per-element operand conversion and epilogue cost what the 32 FMAs cost), see DESIGN.md section 4b. */
-int cistgcn_set_dstd_path(int path);
-
 /* Optional per-kernel timing for benchmarks (no reference counterpart).  While enabled every launch
- * is bracketed by CUDA events on its stream; cistgcn_profile_read synchronises the device, sums the
- * elapsed milliseconds and launch counts per kernel kind (arrays of CISTGCN_PROFILE_KINDS) and
- * resets the counters.  Not thread-safe; leave disabled in production. */
+ * (of every host thread) is bracketed by CUDA events on its stream; cistgcn_profile_read synchronises
+ * the device, sums the elapsed milliseconds and launch counts per kernel kind (arrays of
+ * CISTGCN_PROFILE_KINDS) and resets the counters.  Process-wide instrumentation behind a mutex; leave
+ * disabled in production. */
 int cistgcn_profile_enable(int on);
-/* Debug: while non-NULL, thread 0 of the first CTA of every DSTD-GC launch stamps clock64() at its
- * phase boundaries into device_buffer (>= 16 x int64).  Pass NULL to switch off. */
+int cistgcn_profile_read(double* ms_by_kind, int64_t* launches_by_kind);
+const char* cistgcn_profile_kind_name(int kind);
+/* Debug, -DCISTGCN_PROFILE builds only (otherwise they return -5 and the kernels carry no clock reads):
+ * while non-NULL, thread 0 of the first CTA of every fused DSTD-GC / tcgen05 FPN launch stamps clock64() at
+ * its phase boundaries into device_buffer (>= 32 x int64).  Process-wide, not thread-safe. */
 int cistgcn_debug_phase_clocks(void* device_buffer);
 /* Debug: stamp the CTA's `iteration`-th sample instead of its first (0 = cold caches, >= 1 = steady state). */
 int cistgcn_debug_stamp_iteration(int iteration);
-int cistgcn_profile_read(double* ms_by_kind, int64_t* launches_by_kind);
 
 #ifdef __cplusplus
 }

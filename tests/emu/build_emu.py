@@ -10,11 +10,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(HERE, "_build", "libcistgcn_emu.so")
 CSRC = os.path.join(ROOT, "cistgcn_b200", "csrc")
-UNITS = ["cistgcn_api.cu", "dstd_inst_10_22_256.cu", "dstd_inst_10_22_512.cu", "dstd_inst_10_18_256.cu", "dstd_inst_10_18_512.cu",
-           "dstd_inst_22_25_256.cu", "dstd_inst_22_25_512.cu", "dstd_inst_18_25_256.cu", "dstd_inst_18_25_512.cu",
-         "fpn_inst_22.cu", "fpn_inst_18.cu", "dstd_inst_10_22_512_tc.cu", "dstd_inst_10_18_512_tc.cu"]
-SRCS = [os.path.join(CSRC, f) for f in UNITS + ["dstd_block.cuh", "fpn_chain.cuh", "tail.cuh", "simt.h", "host_util.h",
-                                                 "dstd_launch.h", "fpn_launch.h", "umma.cuh"]] + \
+# every translation unit except the tcgen05 ones (inline PTX: GPU only)
+UNITS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu") and not f.startswith("fpn_tc_inst"))
+SRCS = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))] + \
        [os.path.join(HERE, "simt_emu.h"), os.path.join(ROOT, "include", "cistgcn_b200.h")]
 
 

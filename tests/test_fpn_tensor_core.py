@@ -57,8 +57,9 @@ def test_packed_plan_has_tensor_core_image():
         assert torch.allclose(prm[P.TC_PRM_CPB: P.TC_PRM_CPB + 25], bias.float())
     # raw bf16 words survive the float32 blob bit-exactly
     off = descs[P.F["CF_TC_W"]]
-    s, b = P._fold(sd, "txcnns.0.block1.1")
-    W = s[:, None, None, None] * sd["txcnns.0.block1.0.weight"].double()
+    hs = P.host_state(sd)                                  # fp64 host copies, as the packer sees them
+    s, b = P._fold(hs, "txcnns.0.block1.1")
+    W = s[:, None, None, None] * hs["txcnns.0.block1.0.weight"]
     want = P.tc_slice(W[:, :, 0, 0], 2)
     got = pk.blob[off: off + want.numel()].view(torch.int32)
     assert torch.equal(got, want)
@@ -105,17 +106,13 @@ def test_fpn_kernels_match_oracle(V, weights, scale, B):
     ref = O.fpn_stack_eval(sd, cfg, x5)
     xd = x5.to(dev)
     outs = {}
-    try:
-        for path in (0, 1):                                  # 0: tcgen05 kernel, 1: FP32-FMA kernel
-            _cabi.check(L.cistgcn_set_fpn_path(path), "cistgcn_set_fpn_path", L)
-            x7 = torch.full((B, 25, V, 3), float("nan"), device=dev)
-            rc = L.cistgcn_fpn_chain_f32(pk.fpn_descs(), 4, pk.tail_desc(), pk.blob.data_ptr(), xd.data_ptr(),
-                                         x7.data_ptr(), B, torch.cuda.current_stream().cuda_stream)
-            _cabi.check(rc, "cistgcn_fpn_chain_f32", L)
-            torch.cuda.synchronize()
-            outs[path] = x7.cpu()
-    finally:
-        L.cistgcn_set_fpn_path(0)
+    for path, flags in ((0, 0), (1, _cabi.FLAG_FPN_FP32)):      # 0: tcgen05 kernel, 1: FP32-FMA kernel (per-call flag)
+        x7 = torch.full((B, 25, V, 3), float("nan"), device=dev)
+        rc = L.cistgcn_fpn_chain_f32(pk.fpn_descs(), 4, pk.tail_desc(), pk.blob.data_ptr(), xd.data_ptr(),
+                                     x7.data_ptr(), B, flags, torch.cuda.current_stream().cuda_stream)
+        _cabi.check(rc, "cistgcn_fpn_chain_f32", L)
+        torch.cuda.synchronize()
+        outs[path] = x7.cpu()
     for path, x7 in outs.items():
         assert torch.isfinite(x7).all(), path
         assert (x7 - ref).abs().max().item() <= _tol(ref), path
@@ -123,38 +120,46 @@ def test_fpn_kernels_match_oracle(V, weights, scale, B):
 
 
 @pytest.mark.gpu
-def test_fpn_path_switch_rejects_unknown():
+def test_fpn_chain_rejects_inconsistent_descriptors():
+    """Descriptor consistency is checked before EITHER kernel is dispatched (a direct C-ABI caller with mismatched
+    channel counts must get an error, not an out-of-range shared-memory access in the tensor-core kernel)."""
     from cistgcn_b200 import _cabi
+    from cistgcn_b200.pack import F
     L = _cabi.lib()
-    assert L.cistgcn_set_fpn_path(7) < 0
-    assert b"unknown" in L.cistgcn_last_error()
-    assert L.cistgcn_set_fpn_path(0) == 0
+    model, sd, cfg = M.build(8, 22, "W1")
+    pk = model.to("cuda:0").pack()
+    descs = pk.fpn_descs()
+    descs[F["CF_CIN"]] = 7                                       # layer 0 claims 7 input frames, the tail says 10
+    x5 = torch.zeros(2, 10, 10, 22, device="cuda:0")
+    x7 = torch.zeros(2, 25, 22, 3, device="cuda:0")
+    rc = L.cistgcn_fpn_chain_f32(descs, 4, pk.tail_desc(), pk.blob.data_ptr(), x5.data_ptr(), x7.data_ptr(), 2, 0, None)
+    assert rc < 0 and b"mismatch" in L.cistgcn_last_error()
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("E,V", [(32, 22), (32, 18)])
 @pytest.mark.parametrize("weights,scale", [("W1", "unit"), ("W2", "unit"), ("W1", "mm")])
-def test_dstd_tensor_core_channel_mixes_match_oracle(weights, scale):
-    """cistgcn_set_dstd_path(1): the E=32 blocks run their 1x1 channel mixes (Map2Adj entry convs, tcn, compressor,
-    residual conv) as tcgen05 MMAs; the whole forward must stay inside the fp32 tolerance and agree with the
-    FP32-FMA path to a fraction of it."""
+def test_dstd_tensor_core_channel_mixes_match_oracle(E, V, weights, scale):
+    """CISTGCN_FLAG_DSTD_TC: the round-1 fused kernel with its 1x1 channel mixes (Map2Adj entry convs, tcn, compressor,
+    residual conv) as tcgen05 MMAs; the whole forward must stay inside the fp32 tolerance and agree with the default
+    (three-stage FP32) path to a fraction of it."""
     import _golden as G
     from cistgcn_b200 import _cabi
-    L = _cabi.lib()
     dev = "cuda:0"
-    model, sd, cfg = M.build(32, 22, weights)
+    model, sd, cfg = M.build(E, V, weights)
     x, _ = O.synth_inputs(48, cfg, scale=scale)
     with torch.no_grad():
         ref = O.forward(sd, cfg, x)
     model = model.to(dev)
-    try:
-        _cabi.check(L.cistgcn_set_dstd_path(1), "cistgcn_set_dstd_path", L)
-        tc = model(x.to(dev))[0].cpu()
-        _cabi.check(L.cistgcn_set_dstd_path(0), "cistgcn_set_dstd_path", L)
-        fm = model(x.to(dev))[0].cpu()
-    finally:
-        L.cistgcn_set_dstd_path(0)
+    model.kernel_flags = _cabi.FLAG_DSTD_FUSED | _cabi.FLAG_DSTD_TC
+    tc = model(x.to(dev))[0].cpu()
+    model.kernel_flags = _cabi.FLAG_DSTD_FUSED
+    fused = model(x.to(dev))[0].cpu()
+    model.kernel_flags = 0
+    fm = model(x.to(dev))[0].cpu()
     assert torch.isfinite(tc).all()
-    assert (tc - ref).abs().max().item() <= G.tol(ref)
-    assert (fm - ref).abs().max().item() <= G.tol(ref)
-    assert not torch.equal(tc, fm)                       # the tensor-core path really ran
+    for name, out in (("tc", tc), ("fused", fused), ("split", fm)):
+        assert (out - ref).abs().max().item() <= G.tol(ref), name
+    assert not torch.equal(tc, fused)                    # the tensor-core path really ran
     assert (tc - fm).abs().max().item() <= 0.5 * G.tol(ref)
+    assert (fused - fm).abs().max().item() <= 0.5 * G.tol(ref)

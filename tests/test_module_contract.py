@@ -77,3 +77,41 @@ def test_forward_rejects_bad_inputs():
         m(torch.zeros(2, 9, 22, 3))
     with pytest.raises(ValueError):
         m(torch.zeros(2, 10, 22, 3, dtype=torch.float64))
+
+
+def test_pack_cache_sees_parameter_changes():
+    """the packed-weight cache must not serve stale weights.  In-place updates through the autograd-visible
+    API, storage swaps and replaced Parameter objects are detected by the (data_ptr, version) key; writes through
+    `.data` (invisible to PyTorch's version counters) need repack() / invalidate_pack() or check_weights=True."""
+    import torch
+    import _models as M
+    model, sd, cfg = M.build(8, 22, "W2")
+    first = model.pack("cpu")
+    assert model.pack("cpu") is first                                       # unchanged state: cached
+    conv = model.st_gcnns._modules["0"].dsgn.tcn._modules["0"]
+    with torch.no_grad():
+        conv.weight.mul_(1.5)                                               # bumps _version
+    second = model.pack("cpu")
+    assert second is not first and not torch.equal(second.blob, first.blob)
+    conv.weight = torch.nn.Parameter(conv.weight.detach() * 0.5)            # replaced Parameter object
+    third = model.pack("cpu")
+    assert third is not second and not torch.equal(third.blob, second.blob)
+    conv.weight.data.mul_(2.0)                                              # invisible to the version counter
+    assert model.pack("cpu") is third                                       # documented blind spot ...
+    fourth = model.repack("cpu")                                            # ... closed by an explicit repack
+    assert fourth is not third and not torch.equal(fourth.blob, third.blob)
+    model.check_weights = True                                              # or by the checksum mode
+    fifth = model.pack("cpu")
+    conv.weight.data.mul_(0.5)
+    sixth = model.pack("cpu")
+    assert sixth is not fifth and not torch.equal(sixth.blob, fifth.blob)
+    assert model.pack_count >= 5 and model.last_pack_ms > 0
+
+
+def test_forward_with_grad_input_raises_clearly():
+    import torch
+    import _models as M
+    model, sd, cfg = M.build(8, 22, "W1")
+    x = torch.zeros(1, 10, 22, 3, requires_grad=True)
+    with pytest.raises((NotImplementedError, ValueError)):
+        model(x)
