@@ -37,6 +37,23 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr int kMaxSmemBytes = 227 * 1024;
 
+}  // namespace
+
+namespace cgt {
+// error sink of the training-op translation unit (train_ops.cu): same thread-local message as every other entry point
+int fail_train(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+}  // namespace cgt
+
+namespace {
+
 using cg::sm_count;
 using cg::grid_for;
 
@@ -124,10 +141,11 @@ int launch_dstd_fused(const int32_t* desc, const float* weights, const float* in
   a.stamp_iter = g_stamp_iter;
   // narrow blocks: 256 threads, two CTAs per SM (if the whole plan fits half an SM's shared memory);
   // wide blocks: 512 threads, one CTA per SM
+  // (the tensor-core flag asks for the wide plan outright: only that instantiation carries the tcgen05 channel mixes)
+  const bool tc_ok = (flags & CISTGCN_FLAG_DSTD_TC) && T == 10 && (V == 22 || V == 18);   // shapes with a tensor-core instantiation
   int nt = cg::DSTD_NT_NARROW;
-  if (!cg::dstd_plan(a, nt, cg::DSTD_SMEM_NARROW_BYTES / 4)) {
+  if (tc_ok || !cg::dstd_plan(a, nt, cg::DSTD_SMEM_NARROW_BYTES / 4)) {
     nt = cg::DSTD_NT_WIDE;
-    const bool tc_ok = (flags & CISTGCN_FLAG_DSTD_TC) && T == 10 && (V == 22 || V == 18);   // shapes with a tensor-core instantiation
     if (!cg::dstd_plan(a, nt, kMaxSmemBytes / 4, tc_ok) || (size_t)a.smem_floats * 4 > (size_t)kMaxSmemBytes)
       return fail(-2, "DSTD-GC block (%d->%d, T=%d, V=%d) needs %zu B of shared memory (> %d)", Ci, Co, T, V,
                   (size_t)a.smem_floats * 4, kMaxSmemBytes);

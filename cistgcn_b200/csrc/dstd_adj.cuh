@@ -19,7 +19,7 @@
 
 namespace cg {
 
-constexpr int ADJ_MAX_WARPS = 12;     // 384 threads: up to 168 registers per thread
+constexpr int ADJ_MAX_WARPS = 8;      // 256 threads: up to 255 registers per thread (the 25-wide expansor columns need ~200)
 
 struct AdjArgs {
   int d[CB_COUNT];
@@ -55,14 +55,14 @@ inline bool adj_plan(AdjArgs& a, int max_smem_floats) {
     for (int L = 0; L < 2; ++L) {
       const int n = L == 0 ? V : T;
       z[CB_TC6_WT_S + L] = Ch * apad8(T); z[CB_JC6_WT_S + L] = Ch * apad8(V);
-      z[CB_E0_WT_S + L] = n * apad8(n); z[CB_E0_B_S + L] = n; z[CB_E0_A_S + L] = 1; z[CB_E4_WT_S + L] = n * apad8(n);
+      z[CB_E0_WT_S + L] = n * apad8(n); z[CB_E0_B_S + L] = n; z[CB_E0_A_S + L] = 1; z[CB_E4N_WT_S + L] = n * apad8(n);
     }
   }
   for (int f = 0; f < CB_COUNT; ++f) z[f] = rpad4(z[f]);
   const RedLayout RL(T, V, Cg, Ch, interp);
   a.warp_floats = rpad4(RL.total) + (interp ? 4 * rpad4(TV) : 0) + 4 * rpad4(Co);
   const int order[] = {CB_G4_B, CB_G4_A, CB_M0_B, CB_M0_A, CB_E0_B_S, CB_E0_B_T, CB_E0_A_S, CB_E0_A_T,
-                       CB_E0_WT_S, CB_E0_WT_T, CB_E4_WT_S, CB_E4_WT_T, CB_TC6_WT_S, CB_TC6_WT_T, CB_JC6_WT_S, CB_JC6_WT_T,
+                       CB_E0_WT_S, CB_E0_WT_T, CB_E4N_WT_S, CB_E4N_WT_T, CB_TC6_WT_S, CB_TC6_WT_T, CB_JC6_WT_S, CB_JC6_WT_T,
                        CB_M0_WT, CB_M4_WT, CB_G4_WT};
   const int min_warps = 8;
   int cur = 0;
@@ -80,16 +80,18 @@ inline bool adj_plan(AdjArgs& a, int max_smem_floats) {
 }
 
 // One output column per lane of a two-layer N -> N -> N MLP over the leading axis of the outer-product map
-// (Map2Adj.expansor, CISTGCN.py:165-170): out[:, col] = W4^T PReLU(W0^T o[:, col] + b0).  Weights k-major [k][pad8(N)].
+// (Map2Adj.expansor, CISTGCN.py:165-170): out[:, col] = W4 PReLU(W0 o[:, col] + b0).  w0 k-major [k][pad8(N)], w4 row-major [m][pad8(N)].
 template <int N, int NCOLS, class OFN, class STORE>
-CG_DEV void expansor_warp(const float* __restrict__ w0, const float* __restrict__ b0, float a0,
-                          const float* __restrict__ w4, OFN o_at, STORE store) {
+CG_DEV void expansor_warp(const float* w0, const float* b0, float a0, const float* w4, OFN o_at, STORE store) {
   constexpr int NPW = (N + 7) & ~7;
   const int lane = threadIdx.x & 31;
 #pragma unroll 1
   for (int c0 = 0; c0 < NCOLS; c0 += 32) {
     const bool active = c0 + lane < NCOLS;
     const int col = active ? c0 + lane : NCOLS - 1;
+    w0 = opaque_ptr(w0);                            // the weight rows are re-read every round, not hoisted out of it
+    w4 = opaque_ptr(w4);
+    b0 = opaque_ptr(b0);
     float h[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) h[j] = 0.f;
@@ -107,23 +109,21 @@ CG_DEV void expansor_warp(const float* __restrict__ w0, const float* __restrict_
     }
 #pragma unroll
     for (int j = 0; j < N; ++j) h[j] = prelu(h[j] + b0[j], a0);
-    float o[N];
-#pragma unroll
-    for (int j = 0; j < N; ++j) o[j] = 0.f;
-#pragma unroll
-    for (int k = 0; k < N; ++k) {                  // h[k] must stay in registers: fully unrolled
+    // second layer, one output row at a time (weights row-major [m][pad8(N)]): the hidden column stays in registers, the
+    // result goes straight to memory -- no second register array
+#pragma unroll 1
+    for (int m = 0; m < N; ++m) {
       float wrow[NPW];
 #pragma unroll
       for (int i = 0; i < NPW / 4; ++i) {
-        const float4 q = *reinterpret_cast<const float4*>(w4 + k * NPW + 4 * i);
+        const float4 q = *reinterpret_cast<const float4*>(w4 + m * NPW + 4 * i);
         wrow[4 * i] = q.x; wrow[4 * i + 1] = q.y; wrow[4 * i + 2] = q.z; wrow[4 * i + 3] = q.w;
       }
+      float o0 = 0.f, o1 = 0.f;
 #pragma unroll
-      for (int j = 0; j < N; ++j) o[j] = fmaf(wrow[j], h[k], o[j]);
-    }
-    if (active) {
-#pragma unroll
-      for (int j = 0; j < N; ++j) store(j, col, o[j]);
+      for (int k = 0; k + 1 < N; k += 2) { o0 = fmaf(wrow[k], h[k], o0); o1 = fmaf(wrow[k + 1], h[k + 1], o1); }
+      if (N & 1) o0 = fmaf(wrow[N - 1], h[N - 1], o0);
+      if (active) store(m, col, o0 + o1);
     }
   }
 }
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(32 * ADJ_MAX_WARPS, 1) dstd_adj_kernel(const A
         float* out = a.adj_s + (size_t)b * V * TT;
         const float* ds = dseq;
         const float* dp = dsp;
-        expansor_warp<V, TT>(P(CB_E0_WT_S), P(CB_E0_B_S), P(CB_E0_A_S)[0], P(CB_E4_WT_S),
+        expansor_warp<V, TT>(P(CB_E0_WT_S), P(CB_E0_B_S), P(CB_E0_A_S)[0], P(CB_E4N_WT_S),
           [&](int k, int col) { const int t = col / T, q = col - t * T; return dp[k * T + t] * ds[q * V + k]; },
           [&](int m, int col, float val) { out[m * TT + col] = val; });
       }
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(32 * ADJ_MAX_WARPS, 1) dstd_adj_kernel(const A
         float* out = a.adj_t + (size_t)b * T * VV;
         const float* ds = dseq + rpad4(TV);
         const float* dp = dsp + rpad4(TV);
-        expansor_warp<T, VV>(P(CB_E0_WT_T), P(CB_E0_B_T), P(CB_E0_A_T)[0], P(CB_E4_WT_T),
+        expansor_warp<T, VV>(P(CB_E0_WT_T), P(CB_E0_B_T), P(CB_E0_A_T)[0], P(CB_E4N_WT_T),
           [&](int k, int col) { const int v = col / V, w = col - v * V; return dp[v * T + k] * ds[k * V + w]; },
           [&](int m, int col, float val) { out[m * VV + col] = val; });
       }

@@ -145,10 +145,21 @@ __global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(cons
     e_a[j] = interp ? smem[a.o_a0_a + rmin(m / rmax(Ch, 1), 3)] : 0.f;
   }
 
+  bool first_sample = true;
   for (int b = blockIdx.x * a.nwarps + warp; wactive && b < a.batch; b += gridDim.x * a.nwarps) {
     float* red = a.red + (size_t)b * a.red_stride;
     const float* src = a.in + (size_t)b * d[CB_IN_SB];
     const int sc = d[CB_IN_SC], st = d[CB_IN_ST], sv = d[CB_IN_SV];
+    auto gather_slab = [&](const float* sample, int tt) {  // lanes = joints: Ci coalesced row copies, no register staging
+      if (lane < V) {
+        const float* p = sample + tt * st + lane * sv;
+#pragma unroll 8
+        for (int c = 0; c < Ci; ++c) cp_async4(xs + c * XS + lane, p + c * sc);
+      }
+      cp_async_commit();
+    };
+    const bool gathered = d[CB_IN_MODE] != 1;
+    if (gathered && first_sample) { gather_slab(src, 0); first_sample = false; }
     float ch_mean = 0.f, ch_m2 = 0.f;                      // Chan accumulators over (t, v), lane = channel
     float acc_g[V], acc_tc[V];
 #pragma unroll
@@ -187,11 +198,14 @@ __global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(cons
           }
         }
       } else {
-        const float* p = src + t * st + lane * sv;
+        // the raw slab was gathered into xs by cp.async one stage ahead (below): every row load of the slab is in
+        // flight at once and its latency hides behind the previous slab's collapse stage.  Normalise in place.
+        cp_async_wait_all();
+        __syncwarp();
         if (lane < V) {
-#pragma unroll 4
+#pragma unroll 8
           for (int c = 0; c < Ci; ++c) {
-            const float val = fmaf(gs[c], __ldg(p + c * sc), gb[c]);
+            const float val = fmaf(gs[c], xs[c * XS + lane], gb[c]);
             xs[c * XS + lane] = val;
             ag[c * XT + lane] = val;
           }
@@ -258,6 +272,12 @@ __global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(cons
           wgp += T * mpg;
           xr += XS;
         }
+      }
+      if (gathered) {
+        __syncwarp();            // every lane is done reading the slab: gather the next one (or the next sample's first)
+        const int bn = b + gridDim.x * a.nwarps;
+        if (t + 1 < T) gather_slab(src, t + 1);
+        else if (bn < a.batch) gather_slab(a.in + (size_t)bn * d[CB_IN_SB], 0);
       }
       if (interp) {
         // ---- BN + PReLU of the entry maps -> ag[m][v]  (:139-140, :147-148)

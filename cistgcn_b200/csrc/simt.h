@@ -28,6 +28,16 @@
 
 namespace cg {
 
+// Launders a pointer so that the compiler cannot prove loads through it loop-invariant (it would hoist a whole
+// weight matrix into registers -- and spill it -- out of a loop whose iterations re-read the same shared-memory rows).
+template <class T>
+CG_DEV const T* opaque_ptr(const T* p) {
+#ifndef CISTGCN_EMU
+  asm volatile("" : "+l"(p));
+#endif
+  return p;
+}
+
 CG_DEV float prelu(float v, float a) { return v >= 0.f ? v : a * v; }
 CG_DEV float sigmoidf(float v) { return 1.f / (1.f + expf(-v)); }
 
@@ -69,6 +79,15 @@ CG_DEV void cp_async16(float* smem_dst, const float* __restrict__ gsrc) {
 #else
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+#endif
+}
+// 4-byte variant (any 4-byte aligned addresses): gathers of strided rows
+CG_DEV void cp_async4(float* smem_dst, const float* __restrict__ gsrc) {
+#ifdef CISTGCN_EMU
+  smem_dst[0] = gsrc[0];
+#else
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gsrc));
 #endif
 }
 CG_DEV void cp_async_commit() {

@@ -260,6 +260,7 @@ def _pack_block(blob: _Blob, sd, p: str, ci: int, co: int, T: int, V: int, inter
             put("CB_E0_B" + sfx, Lname + ".e0_b", b)
             put("CB_E0_A" + sfx, Lname + ".e0_a", _w(sd, f"{q}.expansor.3.weight"))
             put("CB_E4_WT" + sfx, Lname + ".e4_wt", _kmajor(_w(sd, f"{q}.expansor.4.weight").reshape(n, n)))
+            put("CB_E4N_WT" + sfx, Lname + ".e4n_wt", _kmajor(_w(sd, f"{q}.expansor.4.weight").reshape(n, n).t()))
         put("CB_A0_WT", "a0_wt", _kmajor(torch.cat(aw, 0)))
         tc_mats["CB_TC_A0"] = (torch.cat(aw, 0), [ci])
         put("CB_A0_B", "a0_b", torch.cat(ab))

@@ -102,6 +102,8 @@ enum cistgcn_block_field {
   CB_R_G0_WT, CB_R_G0_B,            /* conv_{s,t}.0 stacked: [Ci*T][pad32(2Cg)] (row c*T + t), bias [pad32(2Cg)] */
   CB_R_TC3_WT, CB_R_TC3_B,          /* time_compress.3 of dsgn | tsgn side by side: [Ch*T][pad32(2Ch)] (row c*T + t), bias */
   CB_R_JC3_WT, CB_R_JC3_B,          /* joint_compress.3 of dsgn | tsgn side by side: [Ch*V][pad32(2Ch)] (row c*V + v), bias */
+  /* operand of the adjacency stage (csrc/dstd_adj.cuh): expansor.4 row-major (output row, inputs padded to 8) */
+  CB_E4N_WT_S, CB_E4N_WT_T,         /* [n][pad(n)], n = V (dsgn) / T (tsgn) */
   CB_COUNT
 };
 
