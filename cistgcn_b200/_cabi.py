@@ -86,6 +86,61 @@ def bind(path: str) -> ctypes.CDLL:
     return L
 
 
+def _declared_train_exports():
+    import re
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "cistgcn_b200_train.h")
+    src = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)
+    return tuple(dict.fromkeys(re.findall(r"\b(cistgcn_\w+)\s*\(", src)))
+
+
+TRAIN_EXPORTS = _declared_train_exports()
+
+
+def bind_train(L: ctypes.CDLL) -> ctypes.CDLL:
+    """Prototypes of include/cistgcn_b200_train.h (the differentiable path); idempotent."""
+    if getattr(L, "_cistgcn_train_bound", False):
+        return L
+    i32, i64, f32, u64 = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_uint64
+    protos = {
+        "cistgcn_conv2d_fwd": [_p, _p, _p, _p, _p, _p],
+        "cistgcn_conv2d_bwd_input": [_p, _p, _p, _p, _p],
+        "cistgcn_conv2d_bwd_weight": [_p, _p, _p, _p, _p, _p],
+        "cistgcn_bn_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, i64, i32, i32, i32, f32, f32, _p],
+        "cistgcn_bn_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, i64, i32, i32, i32, _p],
+        "cistgcn_prelu_fwd": [_p, _p, _p, i64, i32, i32, i32, _p],
+        "cistgcn_prelu_bwd": [_p, _p, _p, _p, _p, _p, i64, i32, i32, i32, _p],
+        "cistgcn_act_fwd": [_p, _p, i64, i32, _p],
+        "cistgcn_act_bwd": [_p, _p, _p, i64, i32, _p],
+        "cistgcn_dropout": [_p, _p, i64, f32, u64, _p],
+        "cistgcn_copy4d": [_p, ctypes.POINTER(i64), _p, ctypes.POINTER(i64), ctypes.POINTER(i64), i32, _p],
+        "cistgcn_axpby": [f32, _p, f32, _p, i64, _p],
+        "cistgcn_gcn_fwd": [_p, _p, _p, i64, i32, i32, i32, i32, i32, _p],
+        "cistgcn_gcn_bwd": [_p, _p, _p, _p, _p, i64, i32, i32, i32, i32, i32, _p],
+        "cistgcn_outer_fwd": [_p, _p, _p, i64, i32, i32, i32, _p],
+        "cistgcn_outer_bwd": [_p, _p, _p, _p, _p, i64, i32, i32, i32, _p],
+        "cistgcn_stats_fwd": [_p, _p, i64, i32, i32, i32, _p],
+        "cistgcn_stats_bwd": [_p, _p, _p, _p, i64, i32, i32, i32, _p],
+        "cistgcn_spatial_mean_fwd": [_p, _p, i64, i32, i32, _p],
+        "cistgcn_spatial_mean_bwd": [_p, _p, i64, i32, i32, i32, _p],
+        "cistgcn_scale_fwd": [_p, _p, _p, i64, i32, i32, _p],
+        "cistgcn_scale_bwd": [_p, _p, _p, _p, _p, i64, i32, i32, _p],
+        "cistgcn_rowmax_fwd": [_p, _p, _p, i64, i32, _p],
+        "cistgcn_rowmax_bwd": [_p, _p, _p, i64, i32, _p],
+        "cistgcn_cumsum": [_p, _p, i64, i32, i32, i32, _p],
+        "cistgcn_features_fwd": [_p, _p, i64, i32, i32, _p],
+        "cistgcn_features_bwd": [_p, _p, _p, i64, i32, i32, _p],
+        "cistgcn_mpjpe_bwd": [_p, _p, _p, i64, f32, _p],
+        "cistgcn_adam_step": [_p, _p, _p, _p, i64, f32, f32, f32, f32, f32, i32, f32, _p],
+    }
+    assert set(protos) == set(TRAIN_EXPORTS), sorted(set(protos) ^ set(TRAIN_EXPORTS))
+    for name, args in protos.items():
+        fn = getattr(L, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = args
+    L._cistgcn_train_bound = True
+    return L
+
+
 _LIB = None
 
 

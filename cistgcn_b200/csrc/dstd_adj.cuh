@@ -19,6 +19,7 @@
 
 namespace cg {
 
+constexpr int ADJ_CPL = 2;            // expansor columns per lane and weight-row read
 constexpr int ADJ_MAX_WARPS = 8;      // 256 threads: up to 255 registers per thread (the 25-wide expansor columns need ~200)
 
 struct AdjArgs {
@@ -79,25 +80,37 @@ inline bool adj_plan(AdjArgs& a, int max_smem_floats) {
   return true;
 }
 
-// One output column per lane of a two-layer N -> N -> N MLP over the leading axis of the outer-product map
-// (Map2Adj.expansor, CISTGCN.py:165-170): out[:, col] = W4 PReLU(W0 o[:, col] + b0).  w0 k-major [k][pad8(N)], w4 row-major [m][pad8(N)].
-template <int N, int NCOLS, class OFN, class STORE>
+// Map2Adj.expansor (CISTGCN.py:165-170) as an independent two-layer N -> N -> N MLP for every column of the outer-product
+// map: out[:, col] = W4 PReLU(W0 o[:, col] + b0).  w0 k-major [k][pad8(N)], w4 row-major [m][pad8(N)].
+// Every lane owns CPL columns at a time (col, col + 32, ...): a warp-uniform weight row is read ONCE (128-bit broadcast
+// loads, the scarce resource: 2 wavefronts per 4 floats) and feeds CPL * N FFMAs per lane; the hidden columns live in
+// registers and the result goes straight to memory, one output row at a time (coalesced over the lanes).
+template <int N, int NCOLS, int CPL, class OFN, class STORE>
 CG_DEV void expansor_warp(const float* w0, const float* b0, float a0, const float* w4, OFN o_at, STORE store) {
   constexpr int NPW = (N + 7) & ~7;
   const int lane = threadIdx.x & 31;
 #pragma unroll 1
-  for (int c0 = 0; c0 < NCOLS; c0 += 32) {
-    const bool active = c0 + lane < NCOLS;
-    const int col = active ? c0 + lane : NCOLS - 1;
+  for (int c0 = 0; c0 < NCOLS; c0 += 32 * CPL) {
+    bool active[CPL];
+    int col[CPL];
+#pragma unroll
+    for (int u = 0; u < CPL; ++u) {
+      active[u] = c0 + 32 * u + lane < NCOLS;
+      col[u] = active[u] ? c0 + 32 * u + lane : NCOLS - 1;
+    }
     w0 = opaque_ptr(w0);                            // the weight rows are re-read every round, not hoisted out of it
     w4 = opaque_ptr(w4);
     b0 = opaque_ptr(b0);
-    float h[N];
+    float h[CPL][N];
 #pragma unroll
-    for (int j = 0; j < N; ++j) h[j] = 0.f;
+    for (int u = 0; u < CPL; ++u)
+#pragma unroll
+      for (int j = 0; j < N; ++j) h[u][j] = 0.f;
 #pragma unroll 2
     for (int k = 0; k < N; ++k) {
-      const float ok = o_at(k, col);
+      float ok[CPL];
+#pragma unroll
+      for (int u = 0; u < CPL; ++u) ok[u] = o_at(k, col[u]);
       float wrow[NPW];
 #pragma unroll
       for (int i = 0; i < NPW / 4; ++i) {
@@ -105,12 +118,16 @@ CG_DEV void expansor_warp(const float* w0, const float* b0, float a0, const floa
         wrow[4 * i] = q.x; wrow[4 * i + 1] = q.y; wrow[4 * i + 2] = q.z; wrow[4 * i + 3] = q.w;
       }
 #pragma unroll
-      for (int j = 0; j < N; ++j) h[j] = fmaf(wrow[j], ok, h[j]);
+      for (int u = 0; u < CPL; ++u)
+#pragma unroll
+        for (int j = 0; j < N; ++j) h[u][j] = fmaf(wrow[j], ok[u], h[u][j]);
     }
 #pragma unroll
-    for (int j = 0; j < N; ++j) h[j] = prelu(h[j] + b0[j], a0);
-    // second layer, one output row at a time (weights row-major [m][pad8(N)]): the hidden column stays in registers, the
-    // result goes straight to memory -- no second register array
+    for (int j = 0; j < N; ++j) {
+      const float bj = b0[j];
+#pragma unroll
+      for (int u = 0; u < CPL; ++u) h[u][j] = prelu(h[u][j] + bj, a0);
+    }
 #pragma unroll 1
     for (int m = 0; m < N; ++m) {
       float wrow[NPW];
@@ -119,11 +136,14 @@ CG_DEV void expansor_warp(const float* w0, const float* b0, float a0, const floa
         const float4 q = *reinterpret_cast<const float4*>(w4 + m * NPW + 4 * i);
         wrow[4 * i] = q.x; wrow[4 * i + 1] = q.y; wrow[4 * i + 2] = q.z; wrow[4 * i + 3] = q.w;
       }
-      float o0 = 0.f, o1 = 0.f;
 #pragma unroll
-      for (int k = 0; k + 1 < N; k += 2) { o0 = fmaf(wrow[k], h[k], o0); o1 = fmaf(wrow[k + 1], h[k + 1], o1); }
-      if (N & 1) o0 = fmaf(wrow[N - 1], h[N - 1], o0);
-      if (active) store(m, col, o0 + o1);
+      for (int u = 0; u < CPL; ++u) {
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int k = 0; k + 1 < N; k += 2) { o0 = fmaf(wrow[k], h[u][k], o0); o1 = fmaf(wrow[k + 1], h[u][k + 1], o1); }
+        if (N & 1) o0 = fmaf(wrow[N - 1], h[u][N - 1], o0);
+        if (active[u]) store(m, col[u], o0 + o1);
+      }
     }
   }
 }
@@ -248,7 +268,7 @@ __global__ void __launch_bounds__(32 * ADJ_MAX_WARPS, 1) dstd_adj_kernel(const A
         float* out = a.adj_s + (size_t)b * V * TT;
         const float* ds = dseq;
         const float* dp = dsp;
-        expansor_warp<V, TT>(P(CB_E0_WT_S), P(CB_E0_B_S), P(CB_E0_A_S)[0], P(CB_E4N_WT_S),
+        expansor_warp<V, TT, ADJ_CPL>(P(CB_E0_WT_S), P(CB_E0_B_S), P(CB_E0_A_S)[0], P(CB_E4N_WT_S),
           [&](int k, int col) { const int t = col / T, q = col - t * T; return dp[k * T + t] * ds[q * V + k]; },
           [&](int m, int col, float val) { out[m * TT + col] = val; });
       }
@@ -257,7 +277,7 @@ __global__ void __launch_bounds__(32 * ADJ_MAX_WARPS, 1) dstd_adj_kernel(const A
         float* out = a.adj_t + (size_t)b * T * VV;
         const float* ds = dseq + rpad4(TV);
         const float* dp = dsp + rpad4(TV);
-        expansor_warp<T, VV>(P(CB_E0_WT_T), P(CB_E0_B_T), P(CB_E0_A_T)[0], P(CB_E4N_WT_T),
+        expansor_warp<T, VV, ADJ_CPL>(P(CB_E0_WT_T), P(CB_E0_B_T), P(CB_E0_A_T)[0], P(CB_E4N_WT_T),
           [&](int k, int col) { const int v = col / V, w = col - v * V; return dp[v * T + k] * ds[k * V + w]; },
           [&](int m, int col, float val) { out[m * VV + col] = val; });
       }

@@ -16,14 +16,33 @@ namespace cgt {
 
 int fail_train(int code, const char* fmt, ...);     // records the message for cistgcn_last_error() (cistgcn_api.cu)
 
+#ifdef CISTGCN_EMU
+constexpr int NT = 32;      // SIMT emulator (tests/emu): one OS thread per CUDA thread, keep the CTAs small
+#else
 constexpr int NT = 256;
+#endif
 
 inline int grid_1d(long long n, int per_thread = 1) {
   long long g = (n + (long long)NT * per_thread - 1) / ((long long)NT * per_thread);
+#ifdef CISTGCN_EMU
+  const long long cap = 2;                                   // the SIMT emulator spawns one OS thread per CUDA thread
+#else
   const long long cap = (long long)cg::cached_sm_count() * 16;
+#endif
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;
+}
+
+// CTAs of the one-CTA-per-item kernels (every kernel loops, so any grid size is correct)
+inline int grid_items(long long items, int per_sm) {
+#ifdef CISTGCN_EMU
+  const long long cap = 2;
+#else
+  const long long cap = (long long)cg::cached_sm_count() * per_sm;
+#endif
+  const long long g = items < cap ? items : cap;
+  return (int)(g < 1 ? 1 : g);
 }
 
 CG_DEV float block_sum(float v, float* sh) {         // sum over the CTA (NT threads); result in every thread
@@ -202,7 +221,9 @@ __global__ void prelu_bwd_dx_kernel(const float* __restrict__ x, const float* __
 __global__ void prelu_bwd_ds_partial_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ part,
                                             long long B, int C, int HW, int ns) {
   __shared__ float sh[NT / 32];
-  const int s = blockIdx.x, chunk = blockIdx.y, nchunk = gridDim.y;
+  const int nchunk = CISTGCN_PRELU_SCRATCH_PER_SLOPE;
+  for (int item = blockIdx.x; item < ns * nchunk; item += gridDim.x) {
+  const int s = item / nchunk, chunk = item % nchunk;
   float acc = 0.f;
   if (ns == 1) {
     const long long n = B * C * HW;
@@ -217,6 +238,7 @@ __global__ void prelu_bwd_ds_partial_kernel(const float* __restrict__ x, const f
   }
   acc = block_sum(acc, sh);
   if (threadIdx.x == 0) part[(long long)s * nchunk + chunk] = acc;
+  }
 }
 __global__ void sum_rows_kernel(const float* __restrict__ part, float* __restrict__ out, int rows, int cols) {
   for (int r = blockIdx.x * NT + threadIdx.x; r < rows; r += gridDim.x * NT) {
@@ -680,8 +702,7 @@ int cistgcn_conv2d_bwd_weight(const cistgcn_conv_shape* s, const float* x, const
   ConvP p;
   if (!conv_params(s, p) || !x || !dy || !dw) return fail_train(-1, "conv2d_bwd_weight: bad arguments");
   const long long items = (long long)p.Co * p.Ci * p.kh * p.kw + (dbias ? p.Co : 0);
-  const long long cap = (long long)cg::cached_sm_count() * 32;
-  CG_LAUNCH(conv_bwd_weight_kernel, (int)(items < cap ? items : cap), NT, 0, stream, p, x, dy, dw, dbias);
+  CG_LAUNCH(conv_bwd_weight_kernel, grid_items(items, 32), NT, 0, stream, p, x, dy, dw, dbias);
   return launched("conv_bwd_weight_kernel");
 }
 
@@ -690,7 +711,7 @@ int cistgcn_bn_fwd(const float* x, const float* gamma, const float* beta, float*
                    float eps, void* stream) {
   if (!x || !gamma || !beta || !running_mean || !running_var || !y || !save_mean || !save_invstd || B < 1 || C < 1 || HW < 1)
     return fail_train(-1, "bn_fwd: bad arguments");
-  CG_LAUNCH(bn_fwd_kernel, C, NT, 0, stream, x, gamma, beta, running_mean, running_var, y, save_mean, save_invstd, (long long)B, C, HW,
+  CG_LAUNCH(bn_fwd_kernel, grid_items(C, 8), NT, 0, stream, x, gamma, beta, running_mean, running_var, y, save_mean, save_invstd, (long long)B, C, HW,
             training, momentum, eps);
   return launched("bn_fwd_kernel");
 }
@@ -698,7 +719,7 @@ int cistgcn_bn_bwd(const float* x, const float* dy, const float* gamma, const fl
                    float* dx, float* dgamma, float* dbeta, int64_t B, int32_t C, int32_t HW, int32_t training, void* stream) {
   if (!x || !dy || !gamma || !save_mean || !save_invstd || !dx || B < 1 || C < 1 || HW < 1 || ((dgamma == nullptr) != (dbeta == nullptr)))
     return fail_train(-1, "bn_bwd: bad arguments");
-  CG_LAUNCH(bn_bwd_kernel, C, NT, 0, stream, x, dy, gamma, save_mean, save_invstd, dx, dgamma, dbeta, (long long)B, C, HW, training);
+  CG_LAUNCH(bn_bwd_kernel, grid_items(C, 8), NT, 0, stream, x, dy, gamma, save_mean, save_invstd, dx, dgamma, dbeta, (long long)B, C, HW, training);
   return launched("bn_bwd_kernel");
 }
 
@@ -719,7 +740,7 @@ int cistgcn_prelu_bwd(const float* x, const float* dy, const float* slope, float
   if (dslope) {
     constexpr int NCHUNK = CISTGCN_PRELU_SCRATCH_PER_SLOPE;       // partial sums per slope, added in a fixed order
     float* part = scratch;
-    CG_LAUNCH(prelu_bwd_ds_partial_kernel, dim3(n_slopes, NCHUNK), NT, 0, stream, x, dy, part, (long long)B, C, HW, n_slopes);
+    CG_LAUNCH(prelu_bwd_ds_partial_kernel, grid_items((long long)n_slopes * NCHUNK, 64), NT, 0, stream, x, dy, part, (long long)B, C, HW, n_slopes);
     if (int rc = launched("prelu_bwd_ds_partial_kernel")) return rc;
     CG_LAUNCH(sum_rows_kernel, grid_1d(n_slopes), NT, 0, stream, (const float*)part, dslope, n_slopes, NCHUNK);
     return launched("sum_rows_kernel");
@@ -783,8 +804,7 @@ int cistgcn_gcn_bwd(const float* x, const float* A, const float* dy, float* dx, 
       CG_LAUNCH(gcn_bwd_a_kernel, grid_1d((long long)B * per), NT, 0, stream, x, dy, dA, (long long)B, C, T, V, domain);
       return launched("gcn_bwd_a_kernel");
     }
-    const long long cap = (long long)cg::cached_sm_count() * 32;
-    CG_LAUNCH(gcn_bwd_a_static_kernel, (int)(per < cap ? per : cap), NT, 0, stream, x, dy, dA, (long long)B, C, T, V, domain);
+    CG_LAUNCH(gcn_bwd_a_static_kernel, grid_items(per, 32), NT, 0, stream, x, dy, dA, (long long)B, C, T, V, domain);
     return launched("gcn_bwd_a_static_kernel");
   }
   return 0;
@@ -809,16 +829,14 @@ int cistgcn_stats_fwd(const float* x, float* stats, int64_t B, int32_t C, int32_
   if (!x || !stats || B < 0 || C < 2 || T < 1 || V < 2) return fail_train(-1, "stats_fwd: bad arguments (needs C >= 2, V >= 2)");
   if (B == 0) return 0;
   const size_t smem = (size_t)(2 * C + 2 * C * T) * sizeof(float);
-  const long long cap = (long long)cg::cached_sm_count() * 8;
-  CG_LAUNCH(stats_fwd_kernel, (int)(B < cap ? B : cap), NT, smem, stream, x, stats, (long long)B, C, T, V);
+  CG_LAUNCH(stats_fwd_kernel, grid_items(B, 8), NT, smem, stream, x, stats, (long long)B, C, T, V);
   return launched("stats_fwd_kernel");
 }
 int cistgcn_stats_bwd(const float* x, const float* stats, const float* dstats, float* dx, int64_t B, int32_t C, int32_t T,
                       int32_t V, void* stream) {
   if (!x || !stats || !dstats || !dx || B < 1 || C < 2 || T < 1 || V < 2) return fail_train(-1, "stats_bwd: bad arguments");
   const size_t smem = (size_t)(3 * C + 3 * C * T) * sizeof(float);
-  const long long cap = (long long)cg::cached_sm_count() * 8;
-  CG_LAUNCH(stats_bwd_kernel, (int)(B < cap ? B : cap), NT, smem, stream, x, stats, dstats, dx, (long long)B, C, T, V);
+  CG_LAUNCH(stats_bwd_kernel, grid_items(B, 8), NT, smem, stream, x, stats, dstats, dx, (long long)B, C, T, V);
   return launched("stats_bwd_kernel");
 }
 

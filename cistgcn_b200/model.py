@@ -14,6 +14,7 @@ under the same seed (checked in tests/test_module_contract.py when /root/referen
 from __future__ import annotations
 
 import copy
+import ctypes
 import time
 import warnings
 from typing import Dict, List, Optional, Tuple
@@ -398,12 +399,8 @@ class CISTGCN(nn.Module):
 
     def _run(self, x, target):
         self._check_input(x)
-        if torch.is_grad_enabled() and x.requires_grad and not self.training:
+        if self.training or (torch.is_grad_enabled() and x.requires_grad):
             return self._run_differentiable(x, target)
-        if self.training:
-            raise NotImplementedError(
-                "cistgcn_b200: train-mode forward (batch-statistics BatchNorm + dropout) is not built yet; "
-                "call .eval().  See DESIGN.md 'out of scope this round'.")
         lib = _cabi.lib()                                    # raises loudly if the extension is missing
         x = x.contiguous()
         B = x.shape[0]
@@ -436,12 +433,33 @@ class CISTGCN(nn.Module):
             self._publish_taps(holders)
         return pred, sums
 
+    # ------------------------------------------------------------------ differentiable path (train mode / input gradients)
+    def _diff_state(self):
+        """(FlatParams, DiffGraph) of the layer-by-layer differentiable path (cistgcn_b200/train.py), rebuilt when the
+        parameters were moved (.to / .cuda replaces their storage)."""
+        from .train import DiffGraph, FlatParams
+        st = getattr(self, "_diff", None)
+        first = next(self.parameters())
+        if st is None or st[0].flat.device != first.device or first.data_ptr() != st[0].flat.data_ptr():
+            flat = FlatParams(self)
+            st = (flat, DiffGraph(self, flat), torch.zeros(flat.numel, device=flat.device),
+                  torch.zeros(1, device=flat.device, requires_grad=True))
+            object.__setattr__(self, "_diff", st)
+        return st
+
     def _run_differentiable(self, x, target):
-        """Eval-mode forward with autograd w.r.t. the input (environment/adversarial_attacks.py:184, 422, 495-511)."""
-        raise NotImplementedError(
-            "cistgcn_b200: x.requires_grad is set, but the input-gradient path (SURVEY.md 8 f3) is not built; "
-            "the fused eval-mode forward returns tensors detached from autograd.  Wrap the call in "
-            "torch.no_grad() or pass x.detach() if no gradient is wanted.")
+        """Train-mode forward (environment/train.py:59: batch-statistics BatchNorm, dropout, parameter gradients through
+        autograd) and eval-mode forward with gradients w.r.t. the input (environment/adversarial_attacks.py:184, 422,
+        495-511).  Runs the hand-written layer kernels of csrc/train_ops.cu behind a torch.autograd.Function."""
+        flat, graph, fresh, anchor = self._diff_state()
+        pred = _DiffForward.apply(self, x, anchor)
+        if target is None:
+            return pred, None
+        from .losses import mpjpe
+        with torch.no_grad():
+            B, V = x.shape[0], self.n_joints
+            sums = mpjpe(pred.detach(), target, reduce_axis=(0, 2)).double() * (B * V)
+        return pred, sums
 
     def _publish_taps(self, taps: Dict[str, torch.Tensor]):
         """Expose the interpretability outputs as attributes on the same dotted paths the reference sets
@@ -467,6 +485,55 @@ class CISTGCN(nn.Module):
                     object.__setattr__(node, "gcn", gcn)     # plain attribute: keeps state_dict / module tree unchanged
                 if "A" not in gcn._parameters:
                     object.__setattr__(gcn, "A", value)
+
+
+class _DiffForward(torch.autograd.Function):
+    """autograd bridge of the differentiable path.  Parameter gradients do not travel through autograd's return values
+    (1 018 tensors): the backward kernels write them into one flat buffer and ``.grad`` of every Parameter is a view of
+    the flat accumulator, so `loss.backward(); optimizer.step()` of environment/train.py:80-106 works unchanged."""
+
+    @staticmethod
+    def forward(ctx, model, x, anchor):
+        flat, graph, fresh, _ = model._diff_state()
+        training = model.training
+        want_dx = bool(x.requires_grad) and torch.is_grad_enabled()
+        with torch.no_grad():
+            pred = graph.forward(x.detach(), training=training, input_grad=want_dx, param_grads=training)
+        ctx.model, ctx.training, ctx.want_dx = model, training, want_dx
+        if model._taps_enabled:
+            model.last_taps = dict(graph.taps)
+            model._publish_taps(model.last_taps)
+        return pred
+
+    @staticmethod
+    def backward(ctx, dpred):
+        model = ctx.model
+        flat, graph, fresh, _ = model._diff_state()
+        lib = graph.lib
+        with torch.no_grad():
+            graph.grad_target = fresh if ctx.training else None
+            dx = graph.backward(dpred.contiguous())
+            if ctx.training:
+                params = list(model.parameters())
+                have = [p.grad is not None for p in params]
+                stream = torch.cuda.current_stream(flat.device).cuda_stream if flat.flat.is_cuda else None
+                ours = all(p.grad is None or p.grad.data_ptr() == flat.grad.data_ptr() + 4 * flat.offsets[n][0]
+                           for (n, _), p in zip(model.named_parameters(), params))
+                if ours:
+                    # accumulate (or set, after zero_grad(set_to_none=True)) in ONE flat launch
+                    beta = 1.0 if any(have) else 0.0
+                    _cabi.check(lib.cistgcn_axpby(ctypes.c_float(1.0), fresh.data_ptr(), ctypes.c_float(beta), flat.grad.data_ptr(),
+                                                  flat.numel, stream), "axpby", lib)
+                    for (n, _), p in zip(model.named_parameters(), params):
+                        if p.grad is None:
+                            p.grad = flat.grad_view(n)
+                else:                                                    # foreign .grad tensors: per-parameter accumulation
+                    for (n, _), p in zip(model.named_parameters(), params):
+                        off, k, shape = flat.offsets[n]
+                        g = fresh[off: off + k].view(shape)
+                        p.grad = g.clone() if p.grad is None else p.grad + g
+                model._invalidate_pack()
+        return None, (dx if ctx.want_dx else None), None
 
 
 def choose_net(architecture: str, opt):

@@ -12,7 +12,10 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <functional>
+#include <map>
+#include <mutex>
 #include <memory>
 #include <thread>
 #include <vector>
@@ -107,32 +110,82 @@ static inline float atomicAdd(float* p, float v) {
 }
 
 namespace simt_emu {
-// Runs `body` for every (block, thread); blocks sequentially, threads of a block concurrently.
-inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body) {
-  const unsigned nt = block.x;
-  if (nt % 32 != 0) std::abort();
-  for (unsigned b = 0; b < grid.x; ++b) {
-    BlockCtx ctx;
+// A persistent team of `nt` OS threads per CTA size: a launch hands them the kernel body and they run the blocks one
+// after another (all threads of the team inside the same block, so barriers and shuffles behave).  Spawning threads per
+// launch made the layer-by-layer training path (thousands of launches) take minutes.
+struct Team {
+  unsigned nt;
+  std::vector<std::thread> threads;
+  std::mutex mu;
+  std::condition_variable cv_start, cv_done;
+  uint64_t generation = 0;
+  unsigned finished = 0;
+  const std::function<void()>* body = nullptr;
+  dim3 grid;
+  size_t smem_bytes = 0;
+  BlockCtx ctx;
+
+  explicit Team(unsigned n) : nt(n) {
     ctx.bar = std::make_unique<std::barrier<>>(nt);
     for (unsigned w = 0; w < nt / 32; ++w) ctx.warps.push_back(std::make_unique<WarpCtx>());
-    ctx.smem = std::aligned_alloc(128, ((smem_bytes + 127) / 128 + 1) * 128);
-    std::memset(ctx.smem, 0xCB, smem_bytes);  // poison: uninitialised shared memory shows up as NaN-ish junk
-    std::vector<std::thread> ts;
-    ts.reserve(nt);
-    for (unsigned t = 0; t < nt; ++t) {
-      ts.emplace_back([&, t]() {
-        tl_block = &ctx;
-        tl_warp = ctx.warps[t / 32].get();
-        tl_lane = int(t % 32);
-        threadIdx = {t, 0, 0};
-        blockIdx = {b, 0, 0};
-        blockDim = {nt, 1, 1};
-        gridDim = {grid.x, 1, 1};
-        body();
-      });
-    }
-    for (auto& th : ts) th.join();
-    std::free(ctx.smem);
+    for (unsigned t = 0; t < nt; ++t) threads.emplace_back([this, t]() { worker(t); });
+    for (auto& th : threads) th.detach();                     // the team lives until the process exits
   }
+
+  void worker(unsigned t) {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lock(mu);
+        cv_start.wait(lock, [&] { return generation != seen; });
+        seen = generation;
+      }
+      tl_block = &ctx;
+      tl_warp = ctx.warps[t / 32].get();
+      tl_lane = int(t % 32);
+      threadIdx = {t, 0, 0};
+      blockDim = {nt, 1, 1};
+      gridDim = {grid.x, 1, 1};
+      for (unsigned b = 0; b < grid.x; ++b) {
+        if (t == 0) std::memset(ctx.smem, 0xCB, smem_bytes);  // poison: uninitialised shared memory shows up as NaN-ish junk
+        ctx.bar->arrive_and_wait();
+        blockIdx = {b, 0, 0};
+        (*body)();
+        ctx.bar->arrive_and_wait();                           // the block is done before its shared memory is reused
+      }
+      {
+        std::lock_guard<std::mutex> lock(mu);
+        if (++finished == nt) cv_done.notify_one();
+      }
+    }
+  }
+
+  void run(dim3 g, size_t smem, const std::function<void()>& fn) {
+    ctx.smem = std::aligned_alloc(128, ((smem + 127) / 128 + 1) * 128);
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      body = &fn; grid = g; smem_bytes = smem; finished = 0;
+      ++generation;
+    }
+    cv_start.notify_all();
+    {
+      std::unique_lock<std::mutex> lock(mu);
+      cv_done.wait(lock, [&] { return finished == nt; });
+    }
+    std::free(ctx.smem);
+    ctx.smem = nullptr;
+  }
+};
+
+// Runs `body` for every (block, thread); blocks sequentially, threads of a block concurrently.  One launch at a time.
+inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body) {
+  const unsigned nt = block.x;
+  if (nt % 32 != 0 || grid.y != 1 || grid.z != 1) std::abort();
+  static std::mutex launch_mu;
+  static std::map<unsigned, Team*> teams;                     // leaked on purpose (detached worker threads)
+  std::lock_guard<std::mutex> lock(launch_mu);
+  Team*& team = teams[nt];
+  if (!team) team = new Team(nt);
+  team->run(grid, smem_bytes, body);
 }
 }  // namespace simt_emu

@@ -90,9 +90,9 @@ def test_empty_batch_and_errors():
         model(torch.zeros(2, 10, 22, 3))                           # host tensor: no CPU fallback
     with pytest.raises(ValueError):
         model(torch.zeros(2, 10, 18, 3, device=DEV))
-    model.train()
-    with pytest.raises(NotImplementedError):
-        model(torch.zeros(2, 10, 22, 3, device=DEV))
+    model.train()                                                  # train mode: the differentiable layer-by-layer path
+    out = model(torch.randn(4, 10, 22, 3, device=DEV))
+    assert isinstance(out, tuple) and out[0].shape == (4, 25, 22, 3) and out[0].requires_grad
 
 
 def test_batch_independence_across_chunks():

@@ -1,0 +1,204 @@
+"""The differentiable path (cistgcn_b200/train.py over csrc/train_ops.cu) against the reference's own autograd:
+train-mode forward (batch-statistics BatchNorm, running-stat updates), losses.mpjpe with reduce_axis=[], backward
+(every parameter's gradient), Adam; and the eval-mode input gradient.
+
+CPU: the kernels run on the SIMT emulator (tests/emu) and are compared with the UNMODIFIED reference module run by
+PyTorch (needs /root/reference or the vendored oracle/_ref).  GPU (-m gpu): the same comparison through the nvcc-built
+library on larger shapes."""
+import pytest
+import torch
+
+import _models as M
+import _reference as R
+from cistgcn_b200.train import DiffGraph, FlatParams, Trainer
+from oracle import cistgcn_oracle as O
+
+
+def _reference_step(E, V, sd, x, tgt, train=True, input_grad=False, interp=True):
+    ref = R.build(E, V, interpretable=interp, dropout=0.0)
+    ref.load_state_dict(sd)
+    ref.train(train)
+    xr = x.clone().requires_grad_(input_grad)
+    pred = ref(xr)[0]
+    loss = torch.mean(torch.norm(pred - tgt, 2, dim=-1))           # losses.mpjpe, reduce_axis=[]  (losses.py:57-60)
+    loss.backward()
+    grads = {n: p.grad.clone() for n, p in ref.named_parameters() if p.grad is not None}
+    return pred.detach(), loss.detach(), grads, {k: v.clone() for k, v in ref.state_dict().items()}, (xr.grad if input_grad else None)
+
+
+def _ours(E, V, sd, x, tgt, lib, device="cpu", train=True, input_grad=False, interp=True):
+    opt = M.make_opt(E, V, interp)
+    opt.learning_config.dropout = 0.0
+    from cistgcn_b200 import CISTGCN
+    model = CISTGCN(opt.architecture_config, opt.learning_config)
+    model.load_state_dict(sd)
+    model = model.to(device)
+    flat = FlatParams(model)
+    g = DiffGraph(model, flat, lib)
+    pred = g.forward(x.to(device), training=train, input_grad=input_grad, param_grads=True)
+    sums, dpred = g.mpjpe_loss(pred, tgt.to(device))
+    dx = g.backward(dpred)
+    loss = sums.sum() / (pred.shape[0] * pred.shape[1] * pred.shape[2])
+    return pred, loss, g, model, dx
+
+
+def _compare(E, V, B, lib, device, interp=True, train=True, input_grad=False):
+    model0, sd, cfg = M.build(E, V, "W2", interp=interp)
+    x, tgt = O.synth_inputs(B, cfg)
+    rp, rl, rg, rsd, rdx = _reference_step(E, V, sd, x, tgt, train, input_grad, interp)
+    pred, loss, g, model, dx = _ours(E, V, sd, x, tgt, lib, device, train, input_grad, interp)
+    scale = max(1.0, rp.abs().max().item())
+    assert (pred.cpu() - rp).abs().max().item() <= 2e-4 * scale
+    assert abs(loss.item() - rl.item()) <= 1e-4 * max(1.0, abs(rl.item()))
+    worst = ("", 0.0)
+    gmax = max(gr.abs().max().item() for gr in rg.values())          # some gradients are exactly 0 in exact arithmetic
+    for n, gr in rg.items():                                        # (biases in front of a train-mode BatchNorm): absolute floor
+        assert n in g.grads, f"no gradient for {n}"
+        got = g.grads[n].cpu()
+        den = max(gr.abs().max().item(), 1e-6)
+        rel = (got - gr).abs().max().item() / den
+        if rel > worst[1]:
+            worst = (n, rel)
+        # relative to the tensor's largest gradient entry; tiny-gradient tensors get an absolute floor
+        assert (got - gr).abs().max().item() <= 2e-3 * den + 1e-5 * gmax, (n, rel)
+    if train:                                                       # running statistics updated like torch (momentum 0.1)
+        osd = model.state_dict()
+        for k, v in rsd.items():
+            if k.endswith("running_mean") or k.endswith("running_var"):
+                assert torch.allclose(osd[k].cpu(), v, rtol=1e-4, atol=1e-5), k
+            if k.endswith("num_batches_tracked"):
+                assert int(osd[k]) == int(v), k
+    if input_grad:
+        den = max(rdx.abs().max().item(), 1e-6)
+        assert (dx.cpu() - rdx).abs().max().item() <= 2e-3 * den
+    return worst
+
+
+@pytest.mark.skipif(not R.available(), reason="reference module not available")
+def test_train_step_gradients_match_reference_autograd_emulated():
+    import _emu
+    worst = _compare(8, 22, 3, _emu.lib(), "cpu")
+    print("worst relative gradient error", worst)
+
+
+@pytest.mark.skipif(not R.available(), reason="reference module not available")
+def test_eval_mode_input_gradient_matches_reference_emulated():
+    import _emu
+    _compare(8, 18, 2, _emu.lib(), "cpu", train=False, input_grad=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not R.available(), reason="reference module not available")
+@pytest.mark.parametrize("E,V,B,interp", [(8, 22, 16, True), (32, 22, 24, True), (16, 18, 8, True), (8, 22, 6, False)])
+def test_train_step_gradients_match_reference_autograd_gpu(E, V, B, interp):
+    from cistgcn_b200 import _cabi
+    _compare(E, V, B, _cabi.lib(), "cuda:0", interp=interp)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not R.available(), reason="reference module not available")
+def test_eval_mode_input_gradient_gpu():
+    from cistgcn_b200 import _cabi
+    _compare(32, 22, 8, _cabi.lib(), "cuda:0", train=False, input_grad=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not R.available(), reason="reference module not available")
+def test_adam_steps_track_torch_optim_adam():
+    """Three full steps (forward, loss, backward, fused Adam with L2-in-gradient weight decay) against the reference
+    module + torch.optim.Adam (environment/utils.py:53-57): losses and parameters stay together."""
+    from cistgcn_b200 import CISTGCN
+    E, V, B = 16, 22, 32
+    model0, sd, cfg = M.build(E, V, "W2")
+    x, tgt = O.synth_inputs(B, cfg)
+    ref = R.build(E, V, dropout=0.0)
+    ref.load_state_dict(sd)
+    ref.train()
+    opt_ref = torch.optim.Adam(ref.parameters(), lr=0.01, weight_decay=1e-4)
+    opt = M.make_opt(E, V)
+    opt.learning_config.dropout = 0.0
+    model = CISTGCN(opt.architecture_config, opt.learning_config)
+    model.load_state_dict(sd)
+    model = model.to("cuda:0")
+    tr = Trainer(model, lr=0.01, weight_decay=1e-4)
+    xd, td = x.to("cuda:0"), tgt.to("cuda:0")
+    for step in range(3):
+        opt_ref.zero_grad()
+        lr_ = torch.mean(torch.norm(ref(x)[0] - tgt, 2, dim=-1))
+        lr_.backward()
+        opt_ref.step()
+        sums = tr.step(xd, td)
+        loss = (sums.sum() / (B * 25 * V)).item()
+        assert abs(loss - lr_.item()) <= 2e-3 * max(1.0, abs(lr_.item())), (step, loss, lr_.item())
+    worst = 0.0
+    for n, p in ref.named_parameters():
+        got = dict(model.named_parameters())[n].detach().cpu()
+        worst = max(worst, (got - p.detach()).abs().max().item())
+    # Adam's first steps move every parameter by ~lr regardless of gradient scale; sign flips of ~0 gradients are the
+    # only place the two trajectories can part, so compare in units of lr
+    assert worst <= 3 * 0.01, worst
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not R.available(), reason="reference module not available")
+def test_reference_style_training_loop_through_autograd():
+    """environment/train.py:54-107 verbatim against the drop-in module: model.train(); outputs = model(inputs);
+    loss = mpjpe(target, outputs[0]); optimizer.zero_grad(); loss.backward(); optimizer.step() with torch.optim.Adam."""
+    from cistgcn_b200 import CISTGCN, mpjpe
+    E, V, B = 16, 22, 16
+    model0, sd, cfg = M.build(E, V, "W2")
+    x, tgt = O.synth_inputs(B, cfg)
+    ref = R.build(E, V, dropout=0.0)
+    ref.load_state_dict(sd)
+    ref.train()
+    opt_ref = torch.optim.Adam(ref.parameters(), lr=0.01, weight_decay=1e-4)
+    opt = M.make_opt(E, V)
+    opt.learning_config.dropout = 0.0
+    model = CISTGCN(opt.architecture_config, opt.learning_config)
+    model.load_state_dict(sd)
+    model = model.to("cuda:0").train()
+    optim = torch.optim.Adam(model.parameters(), lr=0.01, weight_decay=1e-4)
+    xd, td = x.to("cuda:0"), tgt.to("cuda:0")
+    for step in range(2):
+        opt_ref.zero_grad()
+        lr_ = torch.mean(torch.norm(ref(x)[0] - tgt, 2, dim=-1))
+        lr_.backward()
+        outputs = model(xd)
+        assert isinstance(outputs, tuple) and len(outputs) == 1
+        loss = mpjpe(td, outputs[0])
+        optim.zero_grad()
+        loss.backward()
+        if step == 0:
+            gmax = max(p.grad.abs().max().item() for p in ref.parameters())
+            for (n, p), q in zip(ref.named_parameters(), model.parameters()):
+                assert q.grad is not None, n
+                assert (q.grad.cpu() - p.grad).abs().max().item() <= 2e-3 * p.grad.abs().max().item() + 1e-5 * gmax, n
+        opt_ref.step()
+        optim.step()
+        assert abs(loss.item() - lr_.item()) <= 2e-3 * max(1.0, abs(lr_.item()))
+    # eval after training: the fused inference kernels see the updated weights and running statistics
+    model.eval()
+    ref.eval()
+    with torch.no_grad():
+        pe, pr = model(xd)[0].cpu(), ref(x)[0]
+    assert (pe - pr).abs().max().item() <= 5e-2 * max(1.0, pr.abs().max().item())
+
+
+@pytest.mark.gpu
+def test_train_mode_dropout_is_active_and_unbiased():
+    """learning_config.dropout > 0: two train-mode forwards differ (fresh masks), eval-mode ones do not."""
+    from cistgcn_b200 import CISTGCN
+    opt = M.make_opt(8, 22)
+    opt.learning_config.dropout = 0.1
+    torch.manual_seed(0)
+    model = CISTGCN(opt.architecture_config, opt.learning_config).to("cuda:0")
+    x, _ = O.synth_inputs(8, O.OracleConfig(joints=22, input_gcn=[8] * 4))
+    xd = x.to("cuda:0")
+    model.train()
+    a = model(xd)[0].detach().clone()
+    b = model(xd)[0].detach().clone()
+    assert torch.isfinite(a).all() and not torch.equal(a, b)
+    model.eval()
+    with torch.no_grad():
+        c, d = model(xd)[0], model(xd)[0]
+    assert torch.equal(c, d)
