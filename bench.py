@@ -4,6 +4,7 @@
     python bench.py [--gpus N --steps K --warmup W]                      # configs[1]: E=32, V=22, batch 65536 / GPU, fp32
     python bench.py --embed 16 | --embed 8 --batch 256                   # configs[1] (E=16) / configs[0] shape on the GPU
     python bench.py --mode mpjpe --embed 64 --joints 18 --batch 262144 --scaling strong --gpus N      # configs[2]
+    python bench.py --mode train --batch 128 --gpus 8                    # configs[4]: data-parallel training step
     python bench.py --impl reference ...                                 # the reference's own CPU implementation
 
 A "step" is one pass of the path over one batch of synthetic sequences.  --mode forward: CISTGCN.forward;
@@ -34,7 +35,7 @@ FPN_FLOPS_PER_SEQ = {22: 29.5e6, 18: 29.5e6 * 18 / 22}
 
 
 def metric_name(V, mode):
-    what = {"forward": "forward", "mpjpe": "forward + MPJPE eval"}[mode]
+    what = {"forward": "forward", "mpjpe": "forward + MPJPE eval", "train": "training step (fwd + bwd + grad all-reduce + Adam)"}[mode]
     shape = "H36M 10->25 frames, 22 joints" if V == 22 else f"AMASS 10->25 frames, {V} joints"
     return f"sequences/sec CIST-GCN {what} ({shape})"
 
@@ -130,9 +131,21 @@ class ClockSampler(threading.Thread):
 # otherwise the oracle port (kind "port").  The only places bench.py touches oracle/.
 # ---------------------------------------------------------------------------------------------------------------
 def _cpu_forward_fn(E, V, mode):
-    """(callable(x, target) -> None, kind, description).  Reference module in eval mode under no_grad, fp32."""
+    """(callable(x, target) -> None, kind, description).  Reference module in eval mode under no_grad, fp32
+    (train mode: environment/train.py:54-107 -- forward, losses.mpjpe, backward, torch.optim.Adam step)."""
     import torch
     from oracle import ref_loader
+    if mode == "train":
+        if not ref_loader.available():
+            raise SystemExit("bench --mode train needs the reference module for its CPU arm (oracle/_ref, built by build())")
+        ref = ref_loader.build(E, V).train()
+        optim = torch.optim.Adam(ref.parameters(), lr=0.01, weight_decay=1e-4)      # environment/utils.py:53-57
+        def fn(x, tgt):
+            optim.zero_grad()
+            loss = torch.mean(torch.norm(ref(x)[0] - tgt, 2, dim=-1))
+            loss.backward()
+            optim.step()
+        return fn, "reference", f"unmodified reference CISTGCN module ({ref_loader.which()} copy), train mode, fwd + bwd + torch.optim.Adam"
     if ref_loader.available():
         ref = ref_loader.build(E, V)                              # torch.manual_seed(0) + reference constructor
         def mpjpe(pred, target):                                  # losses.py:57-60 restated (SURVEY.md App. D)
@@ -188,7 +201,8 @@ def _make_model(E, V):
 def workload_name(args, world):
     E, V = args.embed, args.joints
     shape = f"{'H36M' if V == 22 else 'AMASS'} shape (10 in / 25 out frames, {V} joints x 3)"
-    what = "forward" if args.mode == "forward" else "forward + MPJPE eval"
+    what = {"forward": "forward", "mpjpe": "forward + MPJPE eval",
+            "train": "data-parallel training step (train-mode fwd + bwd + one NCCL gradient all-reduce + Adam)"}[args.mode]
     if args.scaling == "strong":
         bs = f"global batch {args.batch} sharded over {world} GPU(s)"
     else:
@@ -207,7 +221,7 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     fn, kind, what = _cpu_forward_fn(E, V, args.mode)
-    step_seqs, sub = 1024, 256                       # one step = a bounded 1024-sequence sample, eval batch 256
+    step_seqs, sub = (1024, 256) if args.mode != "train" else (256, 128)   # bounded sample per step; train batch 128 (train_h36m.yaml:91)
     x, tgt = synth_inputs(step_seqs, V)
     def step():
         for i in range(0, step_seqs, sub):
@@ -478,6 +492,117 @@ def run_native(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def run_train(args, rank, world, local_rank):
+    """configs[4]: the reference's training step (environment/train.py:54-107) data-parallel over the ranks: train-mode
+    forward with local batch-statistics BatchNorm (the reference has no SyncBN), losses.mpjpe (reduce_axis=[]), backward,
+    ONE NCCL all-reduce of the flat fp32 gradient buffer, fused Adam (lr .01, weight decay 1e-4 in the gradient)."""
+    import torch
+    import torch.distributed as dist
+    from cistgcn_b200 import CISTGCN, _cabi
+    from cistgcn_b200.synth import make_opt, synth_inputs
+    from cistgcn_b200.train import Trainer
+
+    E, V, B = args.embed, args.joints, args.batch
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    opt = make_opt(E, V, dropout=0.1)                        # learning_config.dropout of train_h36m.yaml
+    torch.manual_seed(0)
+    model = CISTGCN(opt.architecture_config, opt.learning_config).to(dev).train()
+    tr = Trainer(model, lr=0.01, weight_decay=1e-4)
+    x_host, t_host = synth_inputs(B, V, seed=123 + rank)
+    x_pin, t_pin = x_host.pin_memory(), t_host.pin_memory()
+    x, tgt = x_pin.to(dev), t_pin.to(dev)
+    res_pin = torch.empty(25, dtype=torch.float64).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    for _ in range(max(args.warmup, 3)):
+        tr.step(x, tgt)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ar = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for (e0, e1), (a0, a1) in zip(evs, ar):
+        flush.zero_()
+        e0.record()
+        sums = tr.step(x, tgt, timing=(a0, a1))
+        e1.record()
+    barrier()
+    ms = max_over_ranks(sum(e0.elapsed_time(e1) for e0, e1 in evs))
+    ar_ms = max_over_ranks(sum(a0.elapsed_time(a1) for a0, a1 in ar)) if world > 1 else 0.0
+    launches = tr.graph.launches + 1 + (1 if world > 1 else 0)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms / 1e3)
+    loss = float(sums.sum() / (B * 25 * V))
+
+    # end to end: inputs and targets from pinned host memory every step, the loss read back on the host
+    def e2e_step():
+        x.copy_(x_pin, non_blocking=True)
+        tgt.copy_(t_pin, non_blocking=True)
+        s = tr.step(x, tgt)
+        res_pin.copy_(s, non_blocking=True)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    ev1.record()
+    barrier()
+    ms_e2e = max_over_ranks(ev0.elapsed_time(ev1))
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    n_params = tr.flat.numel
+    line = {
+        "metric": metric_name(V, "train"), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args, world), "batch_per_gpu": B, "global_batch": B * world, "embed": E, "joints": V,
+                   "mode": "train", "dropout": 0.1, "optimizer": "Adam lr 0.01 wd 1e-4 (environment/utils.py:53-57)",
+                   "parallelism": f"data-parallel x{world}, local BatchNorm statistics, one all-reduce of {4 * n_params} bytes per step",
+                   "l2_policy": "L2 flushed between steps (192 MB memset, outside the events)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (x.numel() + tgt.numel()) * 4, "d2h_bytes_per_step": 25 * 8,
+                "ms_per_step": ms_e2e / args.steps, "api": "Trainer.step on pinned host inputs + loss read-back", "checksum": float(res_pin.sum())},
+        "gpu_launches": launches * world * args.steps,
+        "launches_per_step": launches,
+        "collective": {"kind": "ncclAllReduce(SUM) over the flat fp32 gradient buffer" if world > 1 else "none (1 rank)",
+                       "bytes": 4 * n_params, "ms_per_step": ar_ms / args.steps, "share_of_step": (ar_ms / ms) if ms else None},
+        "result": {"loss_last_step": loss},
+        "roofline": {"bound": "hbm", "kernel": "training step (about 2 600 layer kernels per step)", "achieved": None, "peak": measured_peaks()[0],
+                     "unit": "GB/s", "frac": None, "traffic": None,
+                     "note": "launch-bound: whole-batch BatchNorm statistics force layer-by-layer kernels; see DESIGN.md"},
+        "clocks": clocks,
+    }
+    if world == 1:
+        line["cpu_baseline"] = cpu_baseline(E, V, "train", args.cpu_budget, batch=B)
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -487,7 +612,7 @@ def main():
     ap.add_argument("--embed", type=int, default=32)
     ap.add_argument("--joints", type=int, default=22)
     ap.add_argument("--batch", type=int, default=65536, help="sequences per GPU per step (weak) / global batch (strong)")
-    ap.add_argument("--mode", default="forward", choices=["forward", "mpjpe"])
+    ap.add_argument("--mode", default="forward", choices=["forward", "mpjpe", "train"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline timing (N=1 only)")
     args = ap.parse_args()
@@ -503,6 +628,8 @@ def main():
         raise SystemExit(subprocess.call(cmd))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.mode == "train":
+        run_train(args, rank, world, local_rank)
     else:
         run_native(args, rank, world, local_rank)
 

@@ -702,7 +702,7 @@ class Trainer:
         self.step_count = 0
         self.allreduce_ms = None
 
-    def step(self, x: torch.Tensor, target: torch.Tensor, group=None):
+    def step(self, x: torch.Tensor, target: torch.Tensor, group=None, timing=None):
         """One step; returns the per-frame error sums of this rank's batch (float64 (output_n,), on the device):
         loss = sums.sum() / (B * T * V), read it lazily to avoid a sync per step."""
         import torch.distributed as dist
@@ -712,8 +712,12 @@ class Trainer:
         sums, dpred = g.mpjpe_loss(pred, target)
         g.backward(dpred)
         world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        if timing is not None:
+            timing[0].record()
         if world > 1:
             dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=group)     # the only collective: one flat buffer
+        if timing is not None:
+            timing[1].record()
         self.step_count += 1
         st = g._stream(self.flat.flat)
         _cabi.check(self.lib.cistgcn_adam_step(self.flat.flat.data_ptr(), self.flat.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
