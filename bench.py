@@ -45,23 +45,26 @@ def bytes_per_seq(V, E, s=4):
     return s * V * (80 * E + 2683)
 
 
-def stage_bytes_per_seq(E, V, T=10, To=25):
+def stage_bytes_per_seq(E, V, T=10, To=25, act_bytes=4):
     """Compulsory HBM bytes per sequence of every kernel kind of THIS partition: each kernel
-    reads its inputs once and writes its outputs once, weights amortised over the batch.  Keys = profile kind names."""
+    reads its inputs once and writes its outputs once, weights amortised over the batch.  Keys = profile kind names.
+    act_bytes: storage of the activation tensors between the input blocks and into the FPN (2 in the bf16 forward)."""
     blocks = [(10, E, T, V, True)] + [(E, E, T, V, False)] * 3 + [(E, 10, T, V, False), (3, 3, V, To, False)]
     red = adj = mix = fused = 0
-    for ci, co, t, v, raw in blocks:
+    for i, (ci, co, t, v, raw) in enumerate(blocks):
         ch, cg, tv = ci // 2, max(co // 2, 1), t * v
-        x_in = 3 * tv if raw else ci * tv
-        rec = (2 + 2 * t) + 2 * cg * v + 2 * ch * v + 2 * ch * t
-        aj = 2 * co + v * t * t + t * v * v
+        ab_in = 4 if (raw or i == 5) else act_bytes
+        ab_out = 4 if i == 5 else act_bytes
+        x_in = ab_in * (3 * tv if raw else ci * tv)
+        rec = 4 * ((2 + 2 * t) + 2 * cg * v + 2 * ch * v + 2 * ch * t)
+        aj = 4 * (2 * co + v * t * t + t * v * v)
         red += x_in + rec
         adj += rec + aj
-        mix += x_in + aj + co * tv
-        fused += x_in + co * tv
+        mix += x_in + aj + ab_out * co * tv
+        fused += x_in + ab_out * co * tv
     tv = T * V
-    return {"dstd_reduce_kernel": 4 * red, "dstd_adj_kernel": 4 * adj, "dstd_mix_kernel": 4 * mix,
-            "dstd_block_kernel": 4 * fused, "fpn_kernel": 4 * (10 * tv + 3 * To * V),
+    return {"dstd_reduce_kernel": red, "dstd_adj_kernel": adj, "dstd_mix_kernel": mix,
+            "dstd_block_kernel": fused, "fpn_kernel": act_bytes * 10 * tv + 4 * 3 * To * V,
             "tail_kernel": 4 * (3 * tv + 3 * 3 * To * V), "mpjpe_kernel": 4 * 2 * 3 * To * V}
 
 
@@ -207,7 +210,8 @@ def workload_name(args, world):
         bs = f"global batch {args.batch} sharded over {world} GPU(s)"
     else:
         bs = f"batch {args.batch} per GPU"
-    return f"CISTGCN embed={E} {what}, {shape}, {bs}, fp32, random-init weights"
+    prec = "fp32" if getattr(args, "dtype", "f32") == "f32" else "bf16 activation storage + bf16 FPN tensor-core operands, fp32 accumulate"
+    return f"CISTGCN embed={E} {what}, {shape}, {bs}, {prec}, random-init weights"
 
 
 def run_reference(args, rank, world):
@@ -264,6 +268,8 @@ def run_native(args, rank, world, local_rank):
     lib = _cabi.lib()                                   # fails loudly if the extension is missing
     model = _make_model(E, V).to(dev)
     model.kernel_flags = int(os.environ.get("CISTGCN_BENCH_FLAGS", "0"))
+    if args.dtype == "bf16":
+        model.act_dtype = torch.bfloat16
     # weak: every rank owns its own --batch sequences; strong: --batch is the global batch, sharded by rank
     if args.scaling == "strong":
         lo, hi = shard_bounds(args.batch, rank, world)
@@ -422,7 +428,7 @@ def run_native(args, rank, world, local_rank):
     total_kms = sum(kms)
     n_launch_dom = max(int(kln[dom]), 1)
     seqs = B * args.steps                                   # sequences pushed through every kernel kind on this rank
-    kb = stage_bytes_per_seq(E, V)
+    kb = stage_bytes_per_seq(E, V, act_bytes=2 if args.dtype == "bf16" else 4)
     fl_total = FLOPS_PER_SEQ.get((V, E), 0.0)
     dstd_flops = fl_total - FPN_FLOPS_PER_SEQ[V] - 0.7e6 * V / 22
     dur_s = kms[dom] / 1e3 / n_launch_dom                   # average launch duration, CUDA events on the launch stream
@@ -466,7 +472,7 @@ def run_native(args, rank, world, local_rank):
     line = {
         "metric": metric_name(V, mode), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": workload_name(args, world), "batch_per_gpu": B, "global_batch": global_B, "embed": E,
                    "joints": V, "mode": mode,
                    "parallelism": f"batch-sharded x{world}, no data-path collective" +
@@ -614,6 +620,8 @@ def main():
     ap.add_argument("--batch", type=int, default=65536, help="sequences per GPU per step (weak) / global batch (strong)")
     ap.add_argument("--mode", default="forward", choices=["forward", "mpjpe", "train"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"],
+                    help="bf16: cistgcn_forward_bf16 (bf16 activation storage + single-term bf16 FPN tensor-core operands)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline timing (N=1 only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -59,6 +59,8 @@ def bind(path: str) -> ctypes.CDLL:
     L.cistgcn_forward_f32.restype = ctypes.c_int
     L.cistgcn_forward_f32.argtypes = [_i32p, ctypes.c_int32, _p, _p, _p, _p, _p, _p, ctypes.c_size_t,
                                       ctypes.c_int64, ctypes.POINTER(Taps), _p]
+    L.cistgcn_forward_bf16.restype = ctypes.c_int
+    L.cistgcn_forward_bf16.argtypes = L.cistgcn_forward_f32.argtypes
     L.cistgcn_dstd_block_f32.restype = ctypes.c_int
     L.cistgcn_dstd_block_f32.argtypes = [_i32p, _p, _p, _p, ctypes.c_int64, ctypes.POINTER(BlockTaps), _p, ctypes.c_size_t,
                                          ctypes.c_uint32, _p]

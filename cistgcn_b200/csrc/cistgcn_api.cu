@@ -127,10 +127,12 @@ int check_block_desc(const int32_t* d) {
 
 // ---- round-1 fused kernel (one CTA per sample, csrc/dstd_block.cuh): E = 64 blocks and CISTGCN_FLAG_DSTD_FUSED
 int launch_dstd_fused(const int32_t* desc, const float* weights, const float* in, float* out, long long batch,
-                      const cistgcn_block_taps* taps, uint32_t flags, void* stream) {
+                      const cistgcn_block_taps* taps, uint32_t flags, int in_bf16, int out_bf16, void* stream) {
   cg::DstdArgs a;
   memcpy(a.d, desc, sizeof(a.d));
   a.w = weights; a.in = in; a.out = out; a.batch = (int)batch;
+  a.in_bf16 = in_bf16; a.out_bf16 = out_bf16;
+  if (in_bf16 || out_bf16) flags &= ~(uint32_t)CISTGCN_FLAG_DSTD_TC;      // the tcgen05 epilogues store fp32 only
   a.tap_adj_s = taps ? taps->adj_s : nullptr;
   a.tap_adj_t = taps ? taps->adj_t : nullptr;
   a.tap_w1 = taps ? taps->w1 : nullptr;
@@ -226,7 +228,7 @@ bool use_split(const int32_t* desc, uint32_t flags, SplitPlan& sp) {
 }
 
 int launch_dstd_split(SplitPlan& sp, const float* weights, const float* in, float* out, long long batch,
-                      const cistgcn_block_taps* taps, float* scratch, void* stream) {
+                      const cistgcn_block_taps* taps, float* scratch, int in_bf16, int out_bf16, void* stream) {
   const int* d = sp.r.d;
   const int T = d[CB_T], V = d[CB_V], Co = d[CB_CO];
   const bool interp = d[CB_INTERP] != 0;
@@ -238,6 +240,7 @@ int launch_dstd_split(SplitPlan& sp, const float* weights, const float* in, floa
   // the adjacency taps have exactly the layout stage 3 reads: write them once, in place
   if (interp && taps && taps->adj_s && taps->adj_t) { adj_s = taps->adj_s; adj_t = taps->adj_t; }
   sp.r.w = weights; sp.r.in = in; sp.r.red = red; sp.r.batch = (int)batch; sp.r.red_stride = (int)sp.red_floats;
+  sp.r.in_bf16 = in_bf16; sp.m.in_bf16 = in_bf16; sp.m.out_bf16 = out_bf16;
   sp.j.w = weights; sp.j.red = red; sp.j.red_stride = (int)sp.red_floats; sp.j.wg = wg;
   sp.j.adj_s = adj_s; sp.j.adj_t = adj_t; sp.j.batch = (int)batch;
   sp.j.tap_w1 = taps ? taps->w1 : nullptr; sp.j.tap_w2 = taps ? taps->w2 : nullptr;
@@ -271,17 +274,20 @@ size_t dstd_scratch_floats(const int32_t* desc, uint32_t flags, long long batch)
 }
 
 int launch_dstd(const int32_t* desc, const float* weights, const float* in, float* out, long long batch,
-                const cistgcn_block_taps* taps, float* scratch, size_t scratch_floats, uint32_t flags, void* stream) {
+                const cistgcn_block_taps* taps, float* scratch, size_t scratch_floats, uint32_t flags, void* stream,
+                int in_bf16 = 0, int out_bf16 = 0) {
   if (int rc = check_block_desc(desc)) return rc;
+  if (in_bf16 && (desc[CB_IN_MODE] == 1 || desc[CB_IN_SV] != 1 || (desc[CB_V] & 1)))
+    return fail(-2, "DSTD-GC block: bf16 input needs an activation tensor with contiguous, even-length joint rows");
   SplitPlan sp;
   if (use_split(desc, flags, sp)) {
     const bool taps_hold = desc[CB_INTERP] && taps && taps->adj_s && taps->adj_t;
     const size_t need = split_scratch_floats(sp, batch, !taps_hold);
     if (!scratch || scratch_floats < need)
       return fail(-1, "DSTD-GC block: scratch too small (%zu floats given, %zu needed)", scratch_floats, need);
-    return launch_dstd_split(sp, weights, in, out, batch, taps, scratch, stream);
+    return launch_dstd_split(sp, weights, in, out, batch, taps, scratch, in_bf16, out_bf16, stream);
   }
-  return launch_dstd_fused(desc, weights, in, out, batch, taps, flags, stream);
+  return launch_dstd_fused(desc, weights, in, out, batch, taps, flags, in_bf16, out_bf16, stream);
 }
 
 #ifndef CISTGCN_EMU
@@ -298,7 +304,7 @@ bool fpn_tc_supported(const int32_t* fpn_descs, int n_fpn, const int32_t* tail_d
 }
 
 int launch_fpn_tc(const int32_t* fpn_descs, int n_fpn, const int32_t* tail_desc, const float* weights,
-                  const float* in, float* x7, long long batch, void* stream) {
+                  const float* in, float* x7, long long batch, void* stream, bool bf16 = false) {
   cg::FpnTcArgs a;
   memcpy(a.f, fpn_descs, sizeof(int32_t) * CF_COUNT * n_fpn);
   memcpy(a.t, tail_desc, sizeof(a.t));
@@ -307,7 +313,8 @@ int launch_fpn_tc(const int32_t* fpn_descs, int n_fpn, const int32_t* tail_desc,
   int e;
   {
     ProfScope prof(KIND_FPN, stream);
-    e = a.t[CT_V] == 22 ? cg::launch_fpn_tc_22(a, stream) : cg::launch_fpn_tc_18(a, stream);
+    if (bf16) e = a.t[CT_V] == 22 ? cg::launch_fpn_tc_22_bf16(a, stream) : cg::launch_fpn_tc_18_bf16(a, stream);
+    else e = a.t[CT_V] == 22 ? cg::launch_fpn_tc_22(a, stream) : cg::launch_fpn_tc_18(a, stream);
   }
   if (e) return fail(-4, "fpn_tc_kernel launch: %s", cg::launch_error_string(e));
   return 0;
@@ -315,7 +322,7 @@ int launch_fpn_tc(const int32_t* fpn_descs, int n_fpn, const int32_t* tail_desc,
 #endif
 
 int launch_fpn(const int32_t* fpn_descs, int n_fpn, const int32_t* tail_desc, const float* weights,
-               const float* in, float* x7, long long batch, uint32_t flags, void* stream) {
+               const float* in, float* x7, long long batch, uint32_t flags, void* stream, bool bf16 = false) {
   if (n_fpn < 1 || n_fpn > cg::FPN_MAX_LAYERS) return fail(-2, "FPN chain: %d layers unsupported", n_fpn);
   // descriptor consistency first: both kernels rely on it
   {
@@ -330,10 +337,17 @@ int launch_fpn(const int32_t* fpn_descs, int n_fpn, const int32_t* tail_desc, co
     }
   }
 #ifndef CISTGCN_EMU
+  if (bf16) {
+    bool ok = fpn_tc_supported(fpn_descs, n_fpn, tail_desc);
+    for (int l = 0; ok && l < n_fpn; ++l) ok = fpn_descs[l * CF_COUNT + CF_TC_W16] > 0;
+    if (!ok) return fail(-2, "bf16 forward: the FPN stack has no tcgen05 operand image for this shape / these weights");
+    return launch_fpn_tc(fpn_descs, n_fpn, tail_desc, weights, in, x7, batch, stream, true);
+  }
   if (!(flags & CISTGCN_FLAG_FPN_FP32) && fpn_tc_supported(fpn_descs, n_fpn, tail_desc))
     return launch_fpn_tc(fpn_descs, n_fpn, tail_desc, weights, in, x7, batch, stream);
 #else
   (void)flags;
+  if (bf16) return fail(-2, "bf16 forward needs the tensor-core FPN kernel (not available in the emulator build)");
 #endif
   cg::FpnArgs a;
   memcpy(a.f, fpn_descs, sizeof(int32_t) * CF_COUNT * n_fpn);
@@ -493,9 +507,9 @@ size_t cistgcn_workspace_bytes(const int32_t* plan, int64_t batch) {
   return (2 * act + 2 * xo + scratch) * sizeof(float) + 256;
 }
 
-int cistgcn_forward_f32(const int32_t* plan, int32_t plan_len, const float* weights, const float* x, float* pred,
+static int forward_impl(const int32_t* plan, int32_t plan_len, const float* weights, const float* x, float* pred,
                         const float* target, double* frame_sums, void* workspace, size_t workspace_bytes,
-                        int64_t batch, const cistgcn_taps* taps, void* stream) {
+                        int64_t batch, const cistgcn_taps* taps, void* stream, bool act_bf16) {
   PlanView pv;
   if (int rc = parse_plan(plan, plan_len, pv)) return rc;
   if (batch < 0) return fail(-1, "negative batch");
@@ -535,11 +549,14 @@ int cistgcn_forward_f32(const int32_t* plan, int32_t plan_len, const float* weig
       cistgcn_block_taps bt = {nullptr, nullptr, nullptr, nullptr};
       if (taps) bt = block_taps(taps->in_blocks[i], bd, s);
       float* dst = bufs[flip];
-      if (int rc = launch_dstd(bd, weights, cur, dst, n, taps ? &bt : nullptr, scratch, scratch_floats, flags, stream)) return rc;
+      // bf16 forward: every inter-block activation of the input stack (and the FPN's input) is stored as bf16
+      if (int rc = launch_dstd(bd, weights, cur, dst, n, taps ? &bt : nullptr, scratch, scratch_floats, flags, stream,
+                               act_bf16 && i > 0, act_bf16))
+        return rc;
       cur = dst;
       flip ^= 1;
     }
-    if (int rc = launch_fpn(pv.fpn, pv.n_fpn, pv.tail, weights, cur, x7, n, flags, stream)) return rc;
+    if (int rc = launch_fpn(pv.fpn, pv.n_fpn, pv.tail, weights, cur, x7, n, flags, stream, act_bf16)) return rc;
     cur = x7;
     for (int i = 0; i < pv.n_out; ++i) {
       const int32_t* bd = pv.out_blocks + i * CB_COUNT;
@@ -555,6 +572,18 @@ int cistgcn_forward_f32(const int32_t* plan, int32_t plan_len, const float* weig
       return rc;
   }
   return 0;
+}
+
+int cistgcn_forward_f32(const int32_t* plan, int32_t plan_len, const float* weights, const float* x, float* pred,
+                        const float* target, double* frame_sums, void* workspace, size_t workspace_bytes,
+                        int64_t batch, const cistgcn_taps* taps, void* stream) {
+  return forward_impl(plan, plan_len, weights, x, pred, target, frame_sums, workspace, workspace_bytes, batch, taps, stream, false);
+}
+
+int cistgcn_forward_bf16(const int32_t* plan, int32_t plan_len, const float* weights, const float* x, float* pred,
+                         const float* target, double* frame_sums, void* workspace, size_t workspace_bytes,
+                         int64_t batch, const cistgcn_taps* taps, void* stream) {
+  return forward_impl(plan, plan_len, weights, x, pred, target, frame_sums, workspace, workspace_bytes, batch, taps, stream, true);
 }
 
 size_t cistgcn_dstd_block_workspace_bytes(const int32_t* block_desc, int64_t batch) {

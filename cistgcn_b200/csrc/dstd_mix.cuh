@@ -29,6 +29,7 @@ struct MixArgs {
   const float* wg;         // (B, 2, Co) gates from stage 2
   const float* adj_s;      // (B, V, T, T) from stage 2 (ignored when the block carries static adjacencies)
   const float* adj_t;      // (B, T, V, V)
+  int in_bf16, out_bf16;   // activation tensors stored as bf16 (cistgcn_forward_bf16); strides stay in elements
   int batch;
   int o_xn, o_a, o_adj, o_sm, smem_floats;
 };
@@ -182,13 +183,13 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_mix_kernel(const M
         for (int c = 0; c < 10; ++c) XN[c * TV + n] = fmaf(gs[c], f[c], gb[c]);
       }
     } else {
-      const float* src = a.in + (size_t)b * d[CB_IN_SB];
+      const bool ibf = a.in_bf16 != 0;
+      const size_t sbase_ = (size_t)b * d[CB_IN_SB];
       const int sc = d[CB_IN_SC], st = d[CB_IN_ST], sv = d[CB_IN_SV];
-      if (sv == 1 && st == V && sc == TV && (TV % 4) == 0) {       // contiguous tile: 128-bit loads
-        const float4* s4 = reinterpret_cast<const float4*>(src);
+      if (sv == 1 && st == V && sc == TV && (TV % 4) == 0 && (d[CB_IN_SB] % 4) == 0) {       // contiguous tile: 128-bit (64-bit bf16) loads
         for (int i = tid; i < Ci * TV / 4; i += NT) {
           const int c = (i * 4) / TV;
-          float4 v4 = __ldg(s4 + i);
+          float4 v4 = ld_act4(a.in, sbase_ + (size_t)i * 4, ibf);
           const float g0 = gs[c], b0 = gb[c];
           v4.x = fmaf(g0, v4.x, b0); v4.y = fmaf(g0, v4.y, b0); v4.z = fmaf(g0, v4.z, b0); v4.w = fmaf(g0, v4.w, b0);
           reinterpret_cast<float4*>(XN)[i] = v4;
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_mix_kernel(const M
       } else {
         for (int i = tid; i < Ci * TV; i += NT) {
           const int c = i / TV, n = i - c * TV, t = n / V, v = n - t * V;
-          XN[i] = fmaf(gs[c], __ldg(src + c * sc + t * st + v * sv), gb[c]);
+          XN[i] = fmaf(gs[c], ld_act(a.in, sbase_ + (size_t)c * sc + t * st + v * sv, ibf), gb[c]);
         }
       }
     }
@@ -309,9 +310,10 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_mix_kernel(const M
     __syncthreads();
     // ---------------- out = c * gate + residual(xn)   (:390)
     {
-      float* dst = a.out + (size_t)b * d[CB_OUT_SB];
+      const bool obf = a.out_bf16 != 0;
+      const size_t obase = (size_t)b * d[CB_OUT_SB];
       const int sc = d[CB_OUT_SC], st = d[CB_OUT_ST], sv = d[CB_OUT_SV];
-      const bool contiguous = sv == 1 && st == V && sc == TV && (TV % 4) == 0;
+      const bool contiguous = sv == 1 && st == V && sc == TV && (TV % 4) == 0 && (d[CB_OUT_SB] % 4) == 0;
       if (has_res) {
         const float* rbias = P(CB_RS_B);
         const WideOp ops[1] = {{nullptr, P(CB_RS_WT), XN, nullptr}};
@@ -322,28 +324,30 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dstd_mix_kernel(const M
             lds_vec<TNW>(A + m * TV + n0, c);
 #pragma unroll
             for (int j = 0; j < TNW; ++j) v[j] = fmaf(c[j], gm, v[j] + bias);
-            if (contiguous) { store_vec<TNW>(dst + m * TV + n0, v); }
-            else {
+            if (contiguous) {
+              if constexpr (TNW == 4) st_act4(a.out, obase + (size_t)m * TV + n0, make_float4(v[0], v[1], v[2], v[3]), obf);
+              else { st_act(a.out, obase + (size_t)m * TV + n0, v[0], obf); st_act(a.out, obase + (size_t)m * TV + n0 + 1, v[1], obf); }
+            } else {
               int t = n0 / V, vv = n0 - t * V;
 #pragma unroll
               for (int j = 0; j < TNW; ++j) {
-                dst[m * sc + t * st + vv * sv] = v[j];
+                st_act(a.out, obase + (size_t)m * sc + t * st + vv * sv, v[j], obf);
                 if (++vv == V) { vv = 0; ++t; }
               }
             }
           });
       } else if (contiguous) {
-        float4* d4 = reinterpret_cast<float4*>(dst);
         for (int i = tid; i < Co * TV / 4; i += NT) {
           const float gm = gate[(i * 4) / TV];
           const float4 c4 = reinterpret_cast<const float4*>(A)[i];
           const float4 x4 = reinterpret_cast<const float4*>(XN)[i];
-          d4[i] = make_float4(fmaf(c4.x, gm, x4.x), fmaf(c4.y, gm, x4.y), fmaf(c4.z, gm, x4.z), fmaf(c4.w, gm, x4.w));
+          st_act4(a.out, obase + (size_t)i * 4,
+                  make_float4(fmaf(c4.x, gm, x4.x), fmaf(c4.y, gm, x4.y), fmaf(c4.z, gm, x4.z), fmaf(c4.w, gm, x4.w)), obf);
         }
       } else {
         for (int i = tid; i < Co * TV; i += NT) {
           const int m = i / TV, n = i - m * TV, t = n / V, v = n - t * V;
-          dst[m * sc + t * st + v * sv] = fmaf(A[i], gate[m], XN[i]);
+          st_act(a.out, obase + (size_t)m * sc + t * st + v * sv, fmaf(A[i], gate[m], XN[i]), obf);
         }
       }
     }

@@ -48,6 +48,7 @@ struct ReduceArgs {
   const float* in;
   float* red;
   int batch, red_stride;
+  int in_bf16;                      // the input activation tensor is stored as bf16 (cistgcn_forward_bf16; needs sv == 1, V even)
   int nwarps;                       // warps per CTA (= samples in flight per CTA)
   int o_a0, o_g0, o_tc3, o_jc3;     // resident matrices (shared-memory float offsets)
   int o_gn_s, o_gn_b, o_a0_b, o_a0_a, o_g0_b, o_g0_a, o_tc3_b, o_jc3_b;   // resident vectors
@@ -150,16 +151,24 @@ __global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(cons
     float* red = a.red + (size_t)b * a.red_stride;
     const float* src = a.in + (size_t)b * d[CB_IN_SB];
     const int sc = d[CB_IN_SC], st = d[CB_IN_ST], sv = d[CB_IN_SV];
-    auto gather_slab = [&](const float* sample, int tt) {  // lanes = joints: Ci coalesced row copies, no register staging
-      if (lane < V) {
-        const float* p = sample + tt * st + lane * sv;
+    const bool ibf = a.in_bf16 != 0;
+    auto gather_slab = [&](size_t sample_off, int tt) {    // lanes = joints: Ci coalesced row copies, no register staging
+      if (!ibf) {
+        if (lane < V) {
+          const float* p = a.in + sample_off + tt * st + lane * sv;
 #pragma unroll 8
-        for (int c = 0; c < Ci; ++c) cp_async4(xs + c * XS + lane, p + c * sc);
+          for (int c = 0; c < Ci; ++c) cp_async4(xs + c * XS + lane, p + c * sc);
+        }
+      } else if (lane < V / 2) {                           // bf16 rows: joint pairs as 4-byte copies into the row's first words
+        const unsigned short* p = reinterpret_cast<const unsigned short*>(a.in) + sample_off + tt * st + 2 * lane;
+#pragma unroll 8
+        for (int c = 0; c < Ci; ++c) cp_async4(xs + c * XS + lane, reinterpret_cast<const float*>(p + c * sc));
       }
       cp_async_commit();
     };
+    const size_t sample_off = (size_t)b * d[CB_IN_SB];
     const bool gathered = d[CB_IN_MODE] != 1;
-    if (gathered && first_sample) { gather_slab(src, 0); first_sample = false; }
+    if (gathered && first_sample) { gather_slab(sample_off, 0); first_sample = false; }
     float ch_mean = 0.f, ch_m2 = 0.f;                      // Chan accumulators over (t, v), lane = channel
     float acc_g[V], acc_tc[V];
 #pragma unroll
@@ -202,12 +211,32 @@ __global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(cons
         // flight at once and its latency hides behind the previous slab's collapse stage.  Normalise in place.
         cp_async_wait_all();
         __syncwarp();
-        if (lane < V) {
+        if (!ibf) {
+          if (lane < V) {
 #pragma unroll 8
-          for (int c = 0; c < Ci; ++c) {
-            const float val = fmaf(gs[c], xs[c * XS + lane], gb[c]);
-            xs[c * XS + lane] = val;
-            ag[c * XT + lane] = val;
+            for (int c = 0; c < Ci; ++c) {
+              const float val = fmaf(gs[c], xs[c * XS + lane], gb[c]);
+              xs[c * XS + lane] = val;
+              ag[c * XT + lane] = val;
+            }
+          }
+        } else {
+          // expand the packed bf16 pairs in place, eight rows at a time: every lane reads before any lane writes
+          const unsigned* xw = reinterpret_cast<const unsigned*>(xs);
+          for (int c0 = 0; c0 < Ci; c0 += 8) {
+            float val[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int c = rmin(c0 + k, Ci - 1);
+              const unsigned w = lane < V ? xw[c * XS + (lane >> 1)] : 0u;
+              val[k] = fmaf(gs[c], bits_f32((lane & 1) ? (w & 0xFFFF0000u) : (w << 16)), gb[c]);
+            }
+            __syncwarp();
+            if (lane < V) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                if (c0 + k < Ci) { xs[(c0 + k) * XS + lane] = val[k]; ag[(c0 + k) * XT + lane] = val[k]; }
+            }
           }
         }
       }
@@ -276,8 +305,8 @@ __global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(cons
       if (gathered) {
         __syncwarp();            // every lane is done reading the slab: gather the next one (or the next sample's first)
         const int bn = b + gridDim.x * a.nwarps;
-        if (t + 1 < T) gather_slab(src, t + 1);
-        else if (bn < a.batch) gather_slab(a.in + (size_t)bn * d[CB_IN_SB], 0);
+        if (t + 1 < T) gather_slab(sample_off, t + 1);
+        else if (bn < a.batch) gather_slab((size_t)bn * d[CB_IN_SB], 0);
       }
       if (interp) {
         // ---- BN + PReLU of the entry maps -> ag[m][v]  (:139-140, :147-148)

@@ -62,7 +62,7 @@ struct FpnTcArgs {
   int t[CT_COUNT];
   int n_layers;
   const float* w;
-  const float* in;     // (B, Tin, F, V)
+  const void* in;      // (B, Tin, F, V): fp32, or bf16 in the BF16 instantiation
   float* x7;           // (B, Tout, V, 3)
   int batch;
   long long* dbg;      // optional (cistgcn_debug_phase_clocks): CTA 0 writes its wait / total cycle counters, 16 x int64
@@ -99,10 +99,42 @@ CG_DEV void ftc_load_sum(uint32_t addr, float (&o)[16]) {
   for (int i = 0; i < 16; ++i) o[i] = (__uint_as_float(b1[i]) + __uint_as_float(b2[i])) + __uint_as_float(b0[i]);
 }
 
-CG_DEV void ftc_split_store8(const float* x, unsigned char* dst, int term_stride) { split_store8(x, dst, term_stride); }
+// BF16 = false: activation = bf16 term + fp16 remainder (fp32-accurate products); true: the bf16 term only
+template <bool BF16>
+CG_DEV void ftc_split_store8(const float* x, unsigned char* dst, int term_stride) {
+  if constexpr (!BF16) { split_store8(x, dst, term_stride); }
+  else {
+    uint32_t t1[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+      t1[e] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(dst) = make_uint4(t1[0], t1[1], t1[2], t1[3]);
+  }
+}
 
+template <bool BF16>
+CG_DEV void ftc_load_acc(uint32_t addr, float (&o)[16]) {
+  if constexpr (!BF16) { ftc_load_sum(addr, o); }
+  else {
+    uint32_t b0[16];
+    tmem_ld16(addr, b0);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(b0[i]);
+  }
+}
+
+template <bool BF16>
 CG_DEV void ftc_add_terms8(const unsigned char* src, int term_stride, float* x) {
   const uint4 q = *reinterpret_cast<const uint4*>(src);
+  if constexpr (BF16) {
+    const uint32_t wq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { x[2 * e] += __uint_as_float(wq[e] << 16); x[2 * e + 1] += __uint_as_float(wq[e] & 0xFFFF0000u); }
+    return;
+  }
   const uint4 r = *reinterpret_cast<const uint4*>(src + term_stride);
   const uint32_t wq[4] = {q.x, q.y, q.z, q.w}, wr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
@@ -113,7 +145,9 @@ CG_DEV void ftc_add_terms8(const unsigned char* src, int term_stride, float* x) 
   }
 }
 
-template <int V>
+// BF16 = true (cistgcn_forward_bf16): single-term bf16 operands -- ONE N = 32 MMA per k-step instead of two (N = 96 + 32),
+// a quarter of the weight-ring traffic (the compact image CF_TC_W16), bf16 input activations.
+template <int V, bool BF16 = false>
 __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
   using G = FtcGeom<V>;
   extern __shared__ __align__(128) unsigned char ftc_smem[];
@@ -177,6 +211,7 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const float inv_fv = 1.f / (float)FV;
+  constexpr int BCH = BF16 ? 32 * 16 : FTC_BCHUNK;        // bytes of one k-chunk of a weight slice in the ring
 
   if (warp == 0) {
     // ===== weight producer =====
@@ -184,12 +219,12 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
       uint32_t u = 0;
       for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
         for (int l = 0; l < L; ++l) {
-          const uint32_t tap_bytes = (uint32_t)a.f[l][CF_TC_KC] * FTC_BCHUNK;
-          const unsigned char* src = reinterpret_cast<const unsigned char*>(a.w + a.f[l][CF_TC_W]);
+          const uint32_t tap_bytes = (uint32_t)a.f[l][CF_TC_KC] * BCH;
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(a.w + a.f[l][BF16 ? CF_TC_W16 : CF_TC_W]);
           for (int d = 0; d < 3; ++d, ++u) {
             for (int s = 0; s < FTC_SLOTS; ++s) {
               mbar_wait(bar(FB_EMPTY + s), (u & 1) ^ 1);
-              const uint32_t bytes = s < 9 ? tap_bytes : (uint32_t)FTC_SLOT_BYTES;
+              const uint32_t bytes = s < 9 ? tap_bytes : (uint32_t)(4 * BCH);
               mbar_expect_tx(bar(FB_FULL + s), bytes);
               bulk_g2s(sbase + G::O_RING + s * FTC_SLOT_BYTES, src, bytes, bar(FB_FULL + s));
               src += bytes;
@@ -202,11 +237,11 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
     // ===== MMA issuer: the whole warp walks the schedule (warp-uniform control flow keeps descriptors in
     // uniform registers), one elected lane issues =====
     {
-      constexpr uint32_t I96 = umma_idesc_bf16(96), I32H = umma_idesc_f16(32);
+      constexpr uint32_t I96 = umma_idesc_bf16(BF16 ? 32 : 96), I32H = umma_idesc_f16(32);
       constexpr uint64_t BH = (uint64_t)((96 * 16) >> 4);              // the fp16 rows of a weight slice
       const uint64_t dA0 = umma_desc(sbase + G::O_A, SA, 128);
       const uint64_t dI0 = umma_desc(sbase + G::O_IN, SA, 128);
-      const uint64_t dB0 = umma_desc(sbase + G::O_RING, FTC_BCHUNK, 128);
+      const uint64_t dB0 = umma_desc(sbase + G::O_RING, BCH, 128);
       const uint64_t dS0 = umma_desc(sbase + G::O_STAGE, FTC_STAGE_CHUNK, 128);
       const uint32_t acc0 = tmem, cacc0 = tmem + 192;
       uint32_t u0 = 0, ar = 0, it = 0;
@@ -232,9 +267,9 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
               if (elect_one()) {
                 for (int ks = 0; ks < nks; ++ks) {
                   const uint64_t da = da_tap + (uint64_t)((2 * ks * SA) >> 4);
-                  const uint64_t db = db_tap + (uint64_t)((2 * ks * FTC_BCHUNK) >> 4);
+                  const uint64_t db = db_tap + (uint64_t)((2 * ks * BCH) >> 4);
                   umma_bf16(acc, da, db, I96, (tap | ks) != 0);
-                  umma_bf16(acc, da + (uint64_t)(((l == 0 ? 2 : 4) * SA) >> 4), db + BH, I32H, 1);
+                  if constexpr (!BF16) umma_bf16(acc, da + (uint64_t)(((l == 0 ? 2 : 4) * SA) >> 4), db + BH, I32H, 1);
                 }
                 if (t == 1) umma_commit(bar(FB_EMPTY + tap));      // both tiles have read this tap: refill it
               }
@@ -256,9 +291,9 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks) {
                 const uint64_t da = dS0 + (uint64_t)((2 * ks * FTC_STAGE_CHUNK + t * 128 * 16) >> 4);
-                const uint64_t db = dB0 + (uint64_t)((9 * FTC_SLOT_BYTES + 2 * ks * FTC_BCHUNK) >> 4);
+                const uint64_t db = dB0 + (uint64_t)((9 * FTC_SLOT_BYTES + 2 * ks * BCH) >> 4);
                 umma_bf16(cacc, da, db, I96, (d | ks) != 0);
-                umma_bf16(cacc, da + (uint64_t)((4 * FTC_STAGE_CHUNK) >> 4), db + BH, I32H, 1);
+                if constexpr (!BF16) umma_bf16(cacc, da + (uint64_t)((4 * FTC_STAGE_CHUNK) >> 4), db + BH, I32H, 1);
               }
               umma_commit(bar(FB_STG_EMPTY + t));
               if (t == 1) umma_commit(bar(FB_EMPTY + 9));
@@ -286,13 +321,23 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
     uint32_t it = 0;
     const float* prm0 = a.w + a.f[0][CF_TC_PRM];
     for (int b = blockIdx.x; b < a.batch; b += gridDim.x, ++it) {
-      const float* src = a.in + (size_t)b * Tin * FV;
       float xin[4][16];
+      if constexpr (BF16) {
+        const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(a.in) + (size_t)b * Tin * FV;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int idx = lt + 64 * k;
+        for (int k = 0; k < 4; ++k) {
+          const int idx = lt + 64 * k;
 #pragma unroll
-        for (int c = 0; c < 16; ++c) xin[k][c] = (idx < FV && c < Tin) ? __ldg(src + c * FV + idx) : 0.f;
+          for (int c = 0; c < 16; ++c) xin[k][c] = (idx < FV && c < Tin) ? __bfloat162float(src[c * FV + idx]) : 0.f;
+        }
+      } else {
+        const float* src = reinterpret_cast<const float*>(a.in) + (size_t)b * Tin * FV;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int idx = lt + 64 * k;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) xin[k][c] = (idx < FV && c < Tin) ? __ldg(src + c * FV + idx) : 0.f;
+        }
       }
       if (it > 0) mbar_wait(bar(FB_IN_FREE), (it - 1) & 1); // the previous sample's first layer has read the buffer
 #pragma unroll
@@ -301,8 +346,8 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
         if (idx < FV) {
           const int h = idx / V, w = idx - h * V;
           unsigned char* dst = ftc_smem + G::O_IN + (size_t)(Q0 + h * WP + w) * 16;
-          ftc_split_store8(&xin[k][0], dst, 2 * SA);
-          ftc_split_store8(&xin[k][8], dst + SA, 2 * SA);
+          ftc_split_store8<BF16>(&xin[k][0], dst, 2 * SA);
+          ftc_split_store8<BF16>(&xin[k][8], dst + SA, 2 * SA);
         }
       }
       float* cs = chsum_in + (it & 1) * 64;
@@ -351,11 +396,11 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             float o[16];
-            { const long long tl = CG_CLOCK(); ftc_load_sum(acc + half * 16, o); c_ld += CG_CLOCK() - tl; }
+            { const long long tl = CG_CLOCK(); ftc_load_acc<BF16>(acc + half * 16, o); c_ld += CG_CLOCK() - tl; }
 #pragma unroll
             for (int i = 0; i < 16; ++i) o[i] = prelu(o[i] + prm[FTC_PRM_BIAS + d * 32 + half * 16 + i], slope);
-            ftc_split_store8(&o[0], stage_row + (2 * half) * FTC_STAGE_CHUNK, 4 * FTC_STAGE_CHUNK);
-            ftc_split_store8(&o[8], stage_row + (2 * half + 1) * FTC_STAGE_CHUNK, 4 * FTC_STAGE_CHUNK);
+            ftc_split_store8<BF16>(&o[0], stage_row + (2 * half) * FTC_STAGE_CHUNK, 4 * FTC_STAGE_CHUNK);
+            ftc_split_store8<BF16>(&o[8], stage_row + (2 * half + 1) * FTC_STAGE_CHUNK, 4 * FTC_STAGE_CHUNK);
           }
           tc_fence_before();
           mbar_arrive(bar(FB_ACC_EMPTY + t));
@@ -372,7 +417,7 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
         for (int i = 0; i < 32; ++i) xo[i] = 0.f;
         if (resid) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) ftc_add_terms8(a_row + c * SA, 4 * SA, &xo[8 * c]);
+          for (int c = 0; c < 4; ++c) ftc_add_terms8<BF16>(a_row + c * SA, 4 * SA, &xo[8 * c]);
         }
         mbar_wait_timed(bar(FB_CACC_FULL + t), lv & 1, w_cacc);
         ++lv;
@@ -384,15 +429,15 @@ __global__ void __launch_bounds__(FTC_NT, 1) fpn_tc_kernel(const FpnTcArgs a) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           float o[16];
-          ftc_load_sum(cacc + half * 16, o);
+          ftc_load_acc<BF16>(cacc + half * 16, o);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float val = prelu(o[i] + cst[half * 16 + i], oa) + xo[half * 16 + i];
             xo[half * 16 + i] = valid ? val : 0.f;          // xo now holds the layer's output at this position
           }
           if (!last) {
-            ftc_split_store8(&xo[half * 16], a_row + (2 * half) * SA, 4 * SA);
-            ftc_split_store8(&xo[half * 16 + 8], a_row + (2 * half + 1) * SA, 4 * SA);
+            ftc_split_store8<BF16>(&xo[half * 16], a_row + (2 * half) * SA, 4 * SA);
+            ftc_split_store8<BF16>(&xo[half * 16 + 8], a_row + (2 * half + 1) * SA, 4 * SA);
           }
         }
         tc_fence_before();

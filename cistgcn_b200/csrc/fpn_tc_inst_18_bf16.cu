@@ -1,0 +1,7 @@
+// Explicit instantiation of the tensor-core FPN kernel for V = 18 joints, single-term bf16 operands.
+#include "fpn_tc_launch.h"
+#ifndef CISTGCN_EMU
+namespace cg {
+int launch_fpn_tc_18_bf16(const FpnTcArgs& a, void* stream) { return launch_fpn_tc_impl<18, true>(a, stream); }
+}  // namespace cg
+#endif

@@ -2,6 +2,7 @@
 // sources are compiled by g++ against a SIMT emulator so kernel logic can be checked without a GPU.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #ifdef CISTGCN_EMU
 #include "simt_emu.h"
@@ -36,6 +37,39 @@ CG_DEV const T* opaque_ptr(const T* p) {
   asm volatile("" : "+l"(p));
 #endif
   return p;
+}
+
+// ---- bf16 storage of inter-kernel activations (cistgcn_forward_bf16): plain bit manipulation, no cuda_bf16.h, so the
+// same code runs under the SIMT emulator.  Round-to-nearest-even; NaN payloads are not preserved (activations are finite).
+CG_DEV unsigned f32_bits(float v) { unsigned u; memcpy(&u, &v, 4); return u; }
+CG_DEV float bits_f32(unsigned u) { float v; memcpy(&v, &u, 4); return v; }
+CG_DEV unsigned short f32_to_bf16(float v) {
+  unsigned u = f32_bits(v);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (unsigned short)(u >> 16);
+}
+CG_DEV float bf16_to_f32(unsigned short h) { return bits_f32((unsigned)h << 16); }
+CG_DEV unsigned pack_bf16x2(float lo, float hi) { return (unsigned)f32_to_bf16(lo) | ((unsigned)f32_to_bf16(hi) << 16); }
+// element i of an activation tensor stored as fp32 or bf16
+CG_DEV float ld_act(const float* base, size_t i, bool bf16) {
+  return bf16 ? bf16_to_f32(reinterpret_cast<const unsigned short*>(base)[i]) : __ldg(base + i);
+}
+CG_DEV void st_act(float* base, size_t i, float v, bool bf16) {
+  if (bf16) reinterpret_cast<unsigned short*>(base)[i] = f32_to_bf16(v);
+  else base[i] = v;
+}
+// four consecutive elements starting at element i (i % 4 == 0, base 16-byte aligned)
+CG_DEV float4 ld_act4(const float* base, size_t i, bool bf16) {
+  if (!bf16) return __ldg(reinterpret_cast<const float4*>(base + i));
+  const uint2 q = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(base) + i);
+  return make_float4(bits_f32(q.x << 16), bits_f32(q.x & 0xFFFF0000u), bits_f32(q.y << 16), bits_f32(q.y & 0xFFFF0000u));
+}
+CG_DEV void st_act4(float* base, size_t i, float4 v, bool bf16) {
+  if (!bf16) { *reinterpret_cast<float4*>(base + i) = v; return; }
+  uint2 q;
+  q.x = pack_bf16x2(v.x, v.y);
+  q.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(base) + i) = q;
 }
 
 CG_DEV float prelu(float v, float a) { return v >= 0.f ? v : a * v; }

@@ -34,10 +34,10 @@ CG_DEV void mbar_wait(uint32_t bar, uint32_t parity) {
     if ((spin & 0xFFF) == 0xFFF && clock64() - t0 > 8000000000LL) __trap();   // a lost arrival must not hang the GPU
   }
 }
-CG_DEV void mbar_wait_timed(uint32_t bar, uint32_t parity, long long& acc) {
-  const long long t0 = clock64();
+CG_DEV void mbar_wait_timed(uint32_t bar, uint32_t parity, long long& acc) {     // accounting only in -DCISTGCN_PROFILE builds
+  const long long t0 = CG_CLOCK();
   mbar_wait(bar, parity);
-  acc += clock64() - t0;
+  acc += CG_CLOCK() - t0;
 }
 CG_DEV void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 CG_DEV void mbar_expect_tx(uint32_t bar, uint32_t bytes) {

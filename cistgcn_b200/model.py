@@ -278,6 +278,7 @@ class CISTGCN(nn.Module):
         self._tree_epoch = -1
         self.check_weights = False      # True: checksum the state on the device before every forward (synchronises)
         self.kernel_flags = 0           # CISTGCN_FLAG_* kernel choices, travels with every call (CP_FLAGS of the plan)
+        self.act_dtype = torch.float32  # torch.bfloat16: cistgcn_forward_bf16 (bf16 activation storage + bf16 FPN tensor-core operands)
         self.pack_count = 0
         self.last_pack_ms = 0.0
         self._warned_fpn_fallback = False
@@ -421,13 +422,14 @@ class CISTGCN(nn.Module):
             taps_struct, holders = _cabi.make_taps(self.geometry(), B, x.device)
         stream = torch.cuda.current_stream(x.device).cuda_stream
         with torch.cuda.device(x.device):
-            rc = lib.cistgcn_forward_f32(packed.plan_c, len(packed.plan), packed.blob.data_ptr(),
+            entry = lib.cistgcn_forward_bf16 if self.act_dtype == torch.bfloat16 else lib.cistgcn_forward_f32
+            rc = entry(packed.plan_c, len(packed.plan), packed.blob.data_ptr(),
                                          x.data_ptr(), pred.data_ptr(),
                                          target.data_ptr() if target is not None else None,
                                          sums.data_ptr() if sums is not None else None,
                                          workspace.data_ptr(), workspace.numel(), B,
                                          taps_struct, stream)
-        _cabi.check(rc, "cistgcn_forward_f32")
+        _cabi.check(rc, "cistgcn_forward_bf16" if self.act_dtype == torch.bfloat16 else "cistgcn_forward_f32")
         if self._taps_enabled:
             self.last_taps = holders
             self._publish_taps(holders)

@@ -342,6 +342,16 @@ def tc_slice(Wm: torch.Tensor, kc: int) -> torch.Tensor:
     return img.contiguous().view(torch.int32).reshape(-1)
 
 
+def tc_slice_bf16(Wm: torch.Tensor, kc: int) -> torch.Tensor:
+    """(cout <= 32, cin <= 8*kc) matrix -> int32 words of the single-term image [kc k-chunks][32 rows][8 x bf16]."""
+    co, ci = Wm.shape
+    assert co <= 32 and ci <= 8 * kc
+    full = torch.zeros(32, kc * 8, dtype=torch.float64)
+    full[:co, :ci] = Wm
+    img = full.to(torch.float32).to(torch.bfloat16).view(torch.int16).reshape(32, kc, 8).permute(1, 0, 2)
+    return img.contiguous().view(torch.int32).reshape(-1)
+
+
 def tc_image(Wm: torch.Tensor, segs) -> torch.Tensor:
     """(M outputs, sum(segs) inputs) matrix -> int32 words of the tcgen05 B-operand image used by the DSTD-GC channel
     mixes: [K/8 chunks][4*Np rows][8 x 16 bit], Np = pad16(M); rows j*Np + m = bf16 term j (j < 3), rows 3*Np + m = fp16(w).
@@ -377,7 +387,7 @@ def _pack_fpn_tc(blob: _Blob, sd, p: str, prelu_key: str, cin: int, cout: int, d
     if max(float(t.abs().max()) for t in folded + [_w(sd, f"{p}.compress.weight")]) >= TC_FP16_MAX:
         return f"{p}: |weight| >= {TC_FP16_MAX:g} would overflow the fp16 operand copy"
     kc = pad_up(cin, 16) // 8
-    words, prm = [], torch.zeros(TC_PRM_FLOATS, dtype=torch.float64)
+    words, words16, prm = [], [], torch.zeros(TC_PRM_FLOATS, dtype=torch.float64)
     Wc = _w(sd, f"{p}.compress.weight").reshape(cout, 3 * cout + cin)
     for i in (1, 2, 3):
         s, b = _fold(sd, f"{p}.block{i}.1")
@@ -385,7 +395,9 @@ def _pack_fpn_tc(blob: _Blob, sd, p: str, prelu_key: str, cin: int, cout: int, d
         for kh in range(3):
             for kw in range(3):
                 words.append(tc_slice(W[:, :, kh, kw], kc))
+                words16.append(tc_slice_bf16(W[:, :, kh, kw], kc))
         words.append(tc_slice(Wc[:, (i - 1) * cout: i * cout], 4))
+        words16.append(tc_slice_bf16(Wc[:, (i - 1) * cout: i * cout], 4))
         prm[TC_PRM_BIAS + 32 * (i - 1): TC_PRM_BIAS + 32 * (i - 1) + cout] = s * _w(sd, f"{p}.block{i}.0.bias") + b
         prm[TC_PRM_SLOPE + i - 1] = _w(sd, f"{p}.block{i}.3.weight").reshape(-1)[0]
     prm[TC_PRM_OUT_A] = _w(sd, prelu_key + ".weight").reshape(-1)[0]
@@ -395,6 +407,7 @@ def _pack_fpn_tc(blob: _Blob, sd, p: str, prelu_key: str, cin: int, cout: int, d
     prm[TC_PRM_WAVG:] = wavg.reshape(-1)
     d[F["CF_TC_KC"]] = kc
     d[F["CF_TC_W"]] = blob.add_raw(f"{p}:tc_w", torch.cat(words))
+    d[F["CF_TC_W16"]] = blob.add_raw(f"{p}:tc_w16", torch.cat(words16))
     d[F["CF_TC_PRM"]] = blob.add(f"{p}:tc_prm", prm)
     return ""
 

@@ -13,7 +13,8 @@
  *
  * What each entry point replaces in the reference (QualityMinds/cistgcn, paths relative to
  * human_motion_prediction/):
- *   cistgcn_forward_f32      models/CISTGCN/CISTGCN.py:567-597  CISTGCN.forward, called from
+ *   cistgcn_forward_f32 /    models/CISTGCN/CISTGCN.py:567-597  CISTGCN.forward, called from
+ *   cistgcn_forward_bf16
  *                            environment/train.py:59 and environment/test.py:101,103
  *                            (+ losses/losses.py:50-61 mpjpe when `target` is given)
  *   cistgcn_dstd_block_f32   models/CISTGCN/CISTGCN.py:373-390  DSTD_GC.forward (one block)
@@ -124,6 +125,7 @@ enum cistgcn_fpn_field {
   CF_TC_KC,       /* 16-byte k-chunks (8 input channels each) per kernel tap: pad16(Cin) / 8 */
   CF_TC_W,        /* 3 branches x { 9 tap slices [KC][96][8 bf16], 1 compress slice [4][96][8 bf16] }; row = 32*term + cout */
   CF_TC_PRM,      /* fp32: bias[3][32], slope[3], out slope, compress bias[32], avg-branch weights [32 cin][32 cout] */
+  CF_TC_W16,      /* bf16-only image for cistgcn_forward_bf16: same slices, [KC][32][8 bf16] (row = cout), 4 chunks for compress */
   CF_COUNT
 };
 
@@ -200,6 +202,18 @@ int cistgcn_forward_f32(const int32_t* plan, int32_t plan_len, const float* weig
                         const float* x, float* pred, const float* target, double* frame_sums,
                         void* workspace, size_t workspace_bytes, int64_t batch,
                         const cistgcn_taps* taps, void* stream);
+
+/* Same call with bf16 STORAGE and bf16 tensor-core operands where the path is a dense GEMM (BASELINE.json configs[3]):
+ * every activation tensor between the kernels of the input block stack and the FPN stack's input are stored as bf16
+ * (half the HBM traffic of the widest tensors); the FPN stack's convolutions run as single-term bf16 tcgen05 MMAs with
+ * fp32 accumulation (one MMA per k-step instead of the two split-operand ones of the fp32 path); the per-sample vector
+ * math (statistics, gates, adjacency generation, squeeze-excitation) and x / pred / x7 / x8 stay fp32.
+ * Stated bound against the fp32 reference on unit-scale inputs: max-abs <= 3e-2 on the predicted coordinates, MPJPE
+ * agreement <= 5e-3 (tests/test_bf16_forward.py).  Needs the tcgen05 FPN kernel (joints 22 / 18). */
+int cistgcn_forward_bf16(const int32_t* plan, int32_t plan_len, const float* weights,
+                         const float* x, float* pred, const float* target, double* frame_sums,
+                         void* workspace, size_t workspace_bytes, int64_t batch,
+                         const cistgcn_taps* taps, void* stream);
 
 /* One DSTD-GC block on `batch` samples with the strides in the descriptor.  The three-stage path needs
  * cistgcn_dstd_block_workspace_bytes(desc, batch) bytes of scratch (stage records + gates + adjacencies). */
