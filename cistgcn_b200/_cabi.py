@@ -74,6 +74,9 @@ def bind(path: str) -> ctypes.CDLL:
     L.cistgcn_tail_f32.argtypes = [_i32p, _p, _p, _p, _p, _p, _p, _p, ctypes.c_int64, ctypes.POINTER(Taps), _p]
     L.cistgcn_mpjpe_f32.restype = ctypes.c_int
     L.cistgcn_mpjpe_f32.argtypes = [_p, _p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _p, _p, _p]
+    L.cistgcn_eval_metrics_f32.restype = ctypes.c_int
+    L.cistgcn_eval_metrics_f32.argtypes = [_p, _p, _p, _p, ctypes.c_int32, _p, _p, _p, _p, ctypes.c_int64, ctypes.c_int32,
+                                           ctypes.c_int32, ctypes.c_int32, _p]
     L.cistgcn_profile_enable.restype = ctypes.c_int
     L.cistgcn_profile_enable.argtypes = [ctypes.c_int]
     L.cistgcn_profile_read.restype = ctypes.c_int
@@ -106,9 +109,9 @@ def bind_train(L: ctypes.CDLL) -> ctypes.CDLL:
     protos = {
         "cistgcn_conv2d_fwd": [_p, _p, _p, _p, _p, _p],
         "cistgcn_conv2d_bwd_input": [_p, _p, _p, _p, _p],
-        "cistgcn_conv2d_bwd_weight": [_p, _p, _p, _p, _p, _p],
-        "cistgcn_bn_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, i64, i32, i32, i32, f32, f32, _p],
-        "cistgcn_bn_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, i64, i32, i32, i32, _p],
+        "cistgcn_conv2d_bwd_weight": [_p, _p, _p, _p, _p, _p, _p],
+        "cistgcn_bn_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, i64, i32, i32, i32, f32, f32, _p],
+        "cistgcn_bn_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, i64, i32, i32, i32, _p],
         "cistgcn_prelu_fwd": [_p, _p, _p, i64, i32, i32, i32, _p],
         "cistgcn_prelu_bwd": [_p, _p, _p, _p, _p, _p, i64, i32, i32, i32, _p],
         "cistgcn_act_fwd": [_p, _p, i64, i32, _p],
@@ -134,10 +137,15 @@ def bind_train(L: ctypes.CDLL) -> ctypes.CDLL:
         "cistgcn_mpjpe_bwd": [_p, _p, _p, i64, f32, _p],
         "cistgcn_adam_step": [_p, _p, _p, _p, i64, f32, f32, f32, f32, f32, i32, f32, _p],
     }
-    assert set(protos) == set(TRAIN_EXPORTS), sorted(set(protos) ^ set(TRAIN_EXPORTS))
+    sizes = {"cistgcn_conv2d_bwd_weight_scratch_floats": [_p], "cistgcn_bn_scratch_floats": [i32]}
+    assert set(protos) | set(sizes) == set(TRAIN_EXPORTS), sorted((set(protos) | set(sizes)) ^ set(TRAIN_EXPORTS))
     for name, args in protos.items():
         fn = getattr(L, name)
         fn.restype = ctypes.c_int
+        fn.argtypes = args
+    for name, args in sizes.items():
+        fn = getattr(L, name)
+        fn.restype = ctypes.c_size_t
         fn.argtypes = args
     L._cistgcn_train_bound = True
     return L

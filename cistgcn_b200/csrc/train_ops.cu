@@ -105,97 +105,151 @@ __global__ void conv_bwd_input_kernel(ConvP p, const float* __restrict__ dy, con
   }
 }
 
-// one CTA per weight element (co, ci, a, c): reduction over (b, ho, wo); blockIdx.x >= n_weights: bias of channel co
-__global__ void conv_bwd_weight_kernel(ConvP p, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
-                                       float* __restrict__ dbias) {
-  __shared__ float sh[NT / 32];
+// dW / dbias: the reduction range (b, ho, wo) is cut into CONV_BW_CHUNKS chunks; a CTA owns NT consecutive items (weights
+// first, then the Co bias entries) of ONE chunk: thread = item, so threads sharing an input channel / an output channel
+// read the same x / dy element (L1 broadcast) instead of every weight re-streaming its two columns from L2.  Partials go
+// to `part[item][chunk]`; conv_bw_finish adds them in a fixed order (bit-reproducible, no atomics).
+constexpr int CONV_BW_CHUNKS = 32;
+__global__ void conv_bwd_weight_partial_kernel(ConvP p, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ part,
+                                               int n_items, int with_bias) {
   const long long nw = (long long)p.Co * p.Ci * p.kh * p.kw;
   const long long red = p.B * p.Ho * p.Wo;
-  for (long long e = blockIdx.x; e < nw + (dbias ? p.Co : 0); e += gridDim.x) {
+  const int tiles = (n_items + NT - 1) / NT;
+  for (int job = blockIdx.x; job < tiles * CONV_BW_CHUNKS; job += gridDim.x) {
+    const int tile = job / CONV_BW_CHUNKS, chunk = job % CONV_BW_CHUNKS;
+    const long long e = (long long)tile * NT + threadIdx.x;
+    const long long r0 = red * chunk / CONV_BW_CHUNKS, r1 = red * (chunk + 1) / CONV_BW_CHUNKS;
+    if (e >= n_items) continue;
     float acc = 0.f;
     if (e < nw) {
       const int c = (int)(e % p.kw), a = (int)((e / p.kw) % p.kh), ci = (int)((e / (p.kw * p.kh)) % p.Ci);
       const int co = (int)(e / ((long long)p.kw * p.kh * p.Ci));
-      for (long long r = threadIdx.x; r < red; r += NT) {
+      const int oh = a * p.dh - p.ph, ow = c * p.dw - p.pw;
+      for (long long r = r0; r < r1; ++r) {
         const int wo = (int)(r % p.Wo), ho = (int)((r / p.Wo) % p.Ho);
         const long long b = r / ((long long)p.Wo * p.Ho);
-        const int hi = ho - p.ph + a * p.dh, wi = wo - p.pw + c * p.dw;
+        const int hi = ho + oh, wi = wo + ow;
         if (hi < 0 || hi >= p.H || wi < 0 || wi >= p.W) continue;
         acc = fmaf(dy[((b * p.Co + co) * p.Ho + ho) * p.Wo + wo], x[((b * p.Ci + ci) * p.H + hi) * p.W + wi], acc);
       }
-    } else {
+    } else if (with_bias) {
       const int co = (int)(e - nw);
-      for (long long r = threadIdx.x; r < red; r += NT) {
+      for (long long r = r0; r < r1; ++r) {
         const long long b = r / ((long long)p.Wo * p.Ho), hw = r % ((long long)p.Wo * p.Ho);
         acc += dy[(b * p.Co + co) * p.Ho * p.Wo + hw];
       }
     }
-    acc = block_sum(acc, sh);
-    if (threadIdx.x == 0) { if (e < nw) dw[e] = acc; else dbias[e - nw] = acc; }
+    part[e * CONV_BW_CHUNKS + chunk] = acc;
+  }
+}
+__global__ void conv_bw_finish_kernel(const float* __restrict__ part, float* __restrict__ dw, float* __restrict__ dbias, long long nw, int n_items) {
+  for (long long e = (long long)blockIdx.x * NT + threadIdx.x; e < n_items; e += (long long)gridDim.x * NT) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < CONV_BW_CHUNKS; ++c) s += part[e * CONV_BW_CHUNKS + c];
+    if (e < nw) dw[e] = s; else dbias[e - nw] = s;
   }
 }
 
 // ------------------------------------------------------------------------------------------------ batch norm
-// one CTA per channel
-__global__ void bn_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                              float* running_mean, float* running_var, float* __restrict__ y, float* save_mean, float* save_invstd,
-                              long long B, int C, int HW, int training, float momentum, float eps) {
+// Statistics over (B, HW) per channel are cut into BN_CHUNKS chunks so that C * BN_CHUNKS CTAs work at once (C alone is
+// 3 .. 64 CTAs on 148 SMs).  scratch layout (floats): part[C][BN_CHUNKS][2] then coef[C][2].
+constexpr int BN_CHUNKS = 16;
+// chunk statistics, two passes inside the chunk: (mean_k, M2_k = sum (x - mean_k)^2)
+__global__ void bn_stats_kernel(const float* __restrict__ x, float* __restrict__ part, long long B, int C, int HW) {
   __shared__ float sh[NT / 32];
   const long long n = B * HW;
-  for (int c = blockIdx.x; c < C; c += gridDim.x) {
+  for (int job = blockIdx.x; job < C * BN_CHUNKS; job += gridDim.x) {
+    const int c = job / BN_CHUNKS, k = job % BN_CHUNKS;
+    const long long r0 = n * k / BN_CHUNKS, r1 = n * (k + 1) / BN_CHUNKS;
+    float s = 0.f;
+    for (long long r = r0 + threadIdx.x; r < r1; r += NT) s += x[((r / HW) * C + c) * HW + r % HW];
+    const float cnt = (float)(r1 - r0);
+    const float mean = cnt > 0 ? block_sum(s, sh) / cnt : 0.f;
+    float q = 0.f;
+    for (long long r = r0 + threadIdx.x; r < r1; r += NT) { const float d = x[((r / HW) * C + c) * HW + r % HW] - mean; q = fmaf(d, d, q); }
+    q = block_sum(q, sh);
+    if (threadIdx.x == 0) { part[(c * BN_CHUNKS + k) * 2] = mean; part[(c * BN_CHUNKS + k) * 2 + 1] = q; }
+    __syncthreads();
+  }
+}
+// merge the chunks (Chan's update, fixed order), update the running statistics, emit save_mean / save_invstd
+__global__ void bn_finalize_kernel(const float* __restrict__ part, float* running_mean, float* running_var, float* save_mean,
+                                   float* save_invstd, long long B, int C, int HW, int training, float momentum, float eps) {
+  const long long n = B * HW;
+  for (int c = blockIdx.x * NT + threadIdx.x; c < C; c += gridDim.x * NT) {
     float mean, invstd;
     if (training) {
-      float s = 0.f;
-      for (long long r = threadIdx.x; r < n; r += NT) s += x[((r / HW) * C + c) * HW + r % HW];
-      mean = block_sum(s, sh) / (float)n;
-      float q = 0.f;
-      for (long long r = threadIdx.x; r < n; r += NT) { const float d = x[((r / HW) * C + c) * HW + r % HW] - mean; q = fmaf(d, d, q); }
-      q = block_sum(q, sh);
-      const float var = q / (float)n;
-      invstd = 1.f / sqrtf(var + eps);
-      if (threadIdx.x == 0) {
-        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
-        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (n > 1 ? q / (float)(n - 1) : var);
+      float na = 0.f, m = 0.f, M2 = 0.f;
+      for (int k = 0; k < BN_CHUNKS; ++k) {
+        const float nb = (float)(n * (k + 1) / BN_CHUNKS - n * k / BN_CHUNKS);
+        if (nb <= 0.f) continue;
+        const float mb = part[(c * BN_CHUNKS + k) * 2], qb = part[(c * BN_CHUNKS + k) * 2 + 1];
+        const float delta = mb - m;
+        m += delta * (nb / (na + nb));
+        M2 += qb + delta * delta * (na * nb / (na + nb));
+        na += nb;
       }
+      mean = m;
+      const float var = M2 / (float)n;
+      invstd = 1.f / sqrtf(var + eps);
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (n > 1 ? M2 / (float)(n - 1) : var);
     } else {
       mean = running_mean[c];
       invstd = 1.f / sqrtf(running_var[c] + eps);
     }
-    if (threadIdx.x == 0) { save_mean[c] = mean; save_invstd[c] = invstd; }
-    const float g = gamma[c] * invstd, bb = beta[c] - mean * g;
-    for (long long r = threadIdx.x; r < n; r += NT) {
+    save_mean[c] = mean; save_invstd[c] = invstd;
+  }
+}
+__global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ save_mean, const float* __restrict__ save_invstd, float* __restrict__ y,
+                                long long n, int C, int HW) {
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
+    const int c = (int)((i / HW) % C);
+    const float g = gamma[c] * save_invstd[c];
+    y[i] = fmaf(x[i], g, beta[c] - save_mean[c] * g);
+  }
+}
+// backward: chunk sums of dy and dy * xhat -> part[C][BN_CHUNKS][2]
+__global__ void bn_bwd_partial_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ save_mean,
+                                      const float* __restrict__ save_invstd, float* __restrict__ part, long long B, int C, int HW) {
+  __shared__ float sh[NT / 32];
+  const long long n = B * HW;
+  for (int job = blockIdx.x; job < C * BN_CHUNKS; job += gridDim.x) {
+    const int c = job / BN_CHUNKS, k = job % BN_CHUNKS;
+    const long long r0 = n * k / BN_CHUNKS, r1 = n * (k + 1) / BN_CHUNKS;
+    const float mean = save_mean[c], invstd = save_invstd[c];
+    float sdy = 0.f, sdyx = 0.f;
+    for (long long r = r0 + threadIdx.x; r < r1; r += NT) {
       const long long i = ((r / HW) * C + c) * HW + r % HW;
-      y[i] = fmaf(x[i], g, bb);
+      const float d = dy[i];
+      sdy += d;
+      sdyx = fmaf(d, (x[i] - mean) * invstd, sdyx);
     }
+    sdy = block_sum(sdy, sh);
+    sdyx = block_sum(sdyx, sh);
+    if (threadIdx.x == 0) { part[(c * BN_CHUNKS + k) * 2] = sdy; part[(c * BN_CHUNKS + k) * 2 + 1] = sdyx; }
     __syncthreads();
   }
 }
-
-__global__ void bn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
-                              const float* __restrict__ save_mean, const float* __restrict__ save_invstd, float* __restrict__ dx,
-                              float* dgamma, float* dbeta, long long B, int C, int HW, int training) {
-  __shared__ float sh[NT / 32];
-  const long long n = B * HW;
-  for (int c = blockIdx.x; c < C; c += gridDim.x) {
-    const float mean = save_mean[c], invstd = save_invstd[c], g = gamma[c];
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, float* __restrict__ coef, float* dgamma, float* dbeta, long long B,
+                                       int C, int HW) {
+  const float n = (float)(B * HW);
+  for (int c = blockIdx.x * NT + threadIdx.x; c < C; c += gridDim.x * NT) {
     float sdy = 0.f, sdyx = 0.f;
-    if (training || dgamma) {
-      for (long long r = threadIdx.x; r < n; r += NT) {
-        const long long i = ((r / HW) * C + c) * HW + r % HW;
-        const float d = dy[i];
-        sdy += d;
-        sdyx = fmaf(d, (x[i] - mean) * invstd, sdyx);
-      }
-      sdy = block_sum(sdy, sh);
-      sdyx = block_sum(sdyx, sh);
-      if (threadIdx.x == 0 && dgamma) { dgamma[c] = sdyx; dbeta[c] = sdy; }
-    }
-    const float k = g * invstd, m1 = sdy / (float)n, m2 = sdyx / (float)n;
-    for (long long r = threadIdx.x; r < n; r += NT) {
-      const long long i = ((r / HW) * C + c) * HW + r % HW;
-      dx[i] = training ? k * (dy[i] - m1 - (x[i] - mean) * invstd * m2) : k * dy[i];
-    }
-    __syncthreads();
+    for (int k = 0; k < BN_CHUNKS; ++k) { sdy += part[(c * BN_CHUNKS + k) * 2]; sdyx += part[(c * BN_CHUNKS + k) * 2 + 1]; }
+    if (dgamma) { dgamma[c] = sdyx; dbeta[c] = sdy; }
+    coef[2 * c] = sdy / n; coef[2 * c + 1] = sdyx / n;
+  }
+}
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
+                                    const float* __restrict__ save_mean, const float* __restrict__ save_invstd,
+                                    const float* __restrict__ coef, float* __restrict__ dx, long long n, int C, int HW, int training) {
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
+    const int c = (int)((i / HW) % C);
+    const float invstd = save_invstd[c], k = gamma[c] * invstd;
+    dx[i] = training ? k * (dy[i] - coef[2 * c] - (x[i] - save_mean[c]) * invstd * coef[2 * c + 1]) : k * dy[i];
   }
 }
 
@@ -698,29 +752,59 @@ int cistgcn_conv2d_bwd_input(const cistgcn_conv_shape* s, const float* dy, const
   CG_LAUNCH(conv_bwd_input_kernel, grid_1d(p.B * p.Ci * p.H * p.W), NT, 0, stream, p, dy, w, dx);
   return launched("conv_bwd_input_kernel");
 }
-int cistgcn_conv2d_bwd_weight(const cistgcn_conv_shape* s, const float* x, const float* dy, float* dw, float* dbias, void* stream) {
+size_t cistgcn_conv2d_bwd_weight_scratch_floats(const cistgcn_conv_shape* s) {
+  if (!s) return 0;
+  return ((size_t)s->Co * s->Ci * s->kh * s->kw + s->Co) * CONV_BW_CHUNKS;
+}
+int cistgcn_conv2d_bwd_weight(const cistgcn_conv_shape* s, const float* x, const float* dy, float* dw, float* dbias, float* scratch,
+                              void* stream) {
   ConvP p;
-  if (!conv_params(s, p) || !x || !dy || !dw) return fail_train(-1, "conv2d_bwd_weight: bad arguments");
-  const long long items = (long long)p.Co * p.Ci * p.kh * p.kw + (dbias ? p.Co : 0);
-  CG_LAUNCH(conv_bwd_weight_kernel, grid_items(items, 32), NT, 0, stream, p, x, dy, dw, dbias);
-  return launched("conv_bwd_weight_kernel");
+  if (!conv_params(s, p) || !x || !dy || !dw || !scratch) return fail_train(-1, "conv2d_bwd_weight: bad arguments");
+  const long long nw = (long long)p.Co * p.Ci * p.kh * p.kw;
+  const int items = (int)(nw + (dbias ? p.Co : 0));
+  const int tiles = (items + NT - 1) / NT;
+  CG_LAUNCH(conv_bwd_weight_partial_kernel, grid_items((long long)tiles * CONV_BW_CHUNKS, 16), NT, 0, stream, p, x, dy, scratch, items,
+            dbias ? 1 : 0);
+  if (int rc = launched("conv_bwd_weight_partial_kernel")) return rc;
+  CG_LAUNCH(conv_bw_finish_kernel, grid_1d(items), NT, 0, stream, (const float*)scratch, dw, dbias, nw, items);
+  return launched("conv_bw_finish_kernel");
 }
 
+size_t cistgcn_bn_scratch_floats(int32_t C) { return (size_t)C * (2 * BN_CHUNKS + 2); }
 int cistgcn_bn_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var, float* y,
-                   float* save_mean, float* save_invstd, int64_t B, int32_t C, int32_t HW, int32_t training, float momentum,
-                   float eps, void* stream) {
-  if (!x || !gamma || !beta || !running_mean || !running_var || !y || !save_mean || !save_invstd || B < 1 || C < 1 || HW < 1)
+                   float* save_mean, float* save_invstd, float* scratch, int64_t B, int32_t C, int32_t HW, int32_t training,
+                   float momentum, float eps, void* stream) {
+  if (!x || !gamma || !beta || !running_mean || !running_var || !y || !save_mean || !save_invstd || B < 1 || C < 1 || HW < 1 ||
+      (training && !scratch))
     return fail_train(-1, "bn_fwd: bad arguments");
-  CG_LAUNCH(bn_fwd_kernel, grid_items(C, 8), NT, 0, stream, x, gamma, beta, running_mean, running_var, y, save_mean, save_invstd, (long long)B, C, HW,
-            training, momentum, eps);
-  return launched("bn_fwd_kernel");
+  if (training) {
+    CG_LAUNCH(bn_stats_kernel, grid_items((long long)C * BN_CHUNKS, 16), NT, 0, stream, x, scratch, (long long)B, C, HW);
+    if (int rc = launched("bn_stats_kernel")) return rc;
+  }
+  CG_LAUNCH(bn_finalize_kernel, grid_1d(C), NT, 0, stream, (const float*)scratch, running_mean, running_var, save_mean, save_invstd,
+            (long long)B, C, HW, training, momentum, eps);
+  if (int rc = launched("bn_finalize_kernel")) return rc;
+  const long long n = (long long)B * C * HW;
+  CG_LAUNCH(bn_apply_kernel, grid_1d(n), NT, 0, stream, x, gamma, beta, (const float*)save_mean, (const float*)save_invstd, y, n, C, HW);
+  return launched("bn_apply_kernel");
 }
 int cistgcn_bn_bwd(const float* x, const float* dy, const float* gamma, const float* save_mean, const float* save_invstd,
-                   float* dx, float* dgamma, float* dbeta, int64_t B, int32_t C, int32_t HW, int32_t training, void* stream) {
-  if (!x || !dy || !gamma || !save_mean || !save_invstd || !dx || B < 1 || C < 1 || HW < 1 || ((dgamma == nullptr) != (dbeta == nullptr)))
+                   float* dx, float* dgamma, float* dbeta, float* scratch, int64_t B, int32_t C, int32_t HW, int32_t training,
+                   void* stream) {
+  if (!x || !dy || !gamma || !save_mean || !save_invstd || !dx || !scratch || B < 1 || C < 1 || HW < 1 ||
+      ((dgamma == nullptr) != (dbeta == nullptr)))
     return fail_train(-1, "bn_bwd: bad arguments");
-  CG_LAUNCH(bn_bwd_kernel, grid_items(C, 8), NT, 0, stream, x, dy, gamma, save_mean, save_invstd, dx, dgamma, dbeta, (long long)B, C, HW, training);
-  return launched("bn_bwd_kernel");
+  float* coef = scratch + (size_t)C * 2 * BN_CHUNKS;
+  if (training || dgamma) {
+    CG_LAUNCH(bn_bwd_partial_kernel, grid_items((long long)C * BN_CHUNKS, 16), NT, 0, stream, x, dy, save_mean, save_invstd, scratch,
+              (long long)B, C, HW);
+    if (int rc = launched("bn_bwd_partial_kernel")) return rc;
+    CG_LAUNCH(bn_bwd_finalize_kernel, grid_1d(C), NT, 0, stream, (const float*)scratch, coef, dgamma, dbeta, (long long)B, C, HW);
+    if (int rc = launched("bn_bwd_finalize_kernel")) return rc;
+  }
+  const long long n = (long long)B * C * HW;
+  CG_LAUNCH(bn_bwd_apply_kernel, grid_1d(n), NT, 0, stream, x, dy, gamma, save_mean, save_invstd, (const float*)coef, dx, n, C, HW, training);
+  return launched("bn_bwd_apply_kernel");
 }
 
 int cistgcn_prelu_fwd(const float* x, const float* slope, float* y, int64_t B, int32_t C, int32_t HW, int32_t n_slopes, void* stream) {

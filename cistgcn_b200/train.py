@@ -114,6 +114,7 @@ class DiffGraph:
         self.grads: Dict[str, torch.Tensor] = {}
         self.launches = 0
         self.grad_target: Optional[torch.Tensor] = None    # flat buffer the parameter gradients are written into (default: flat.grad)
+        self._scratch: Optional[torch.Tensor] = None       # partial sums of the reductions (one stream: reused by every launch)
 
     # ------------------------------------------------------------------------------------------ plumbing
     def _stream(self, t):
@@ -125,6 +126,11 @@ class DiffGraph:
 
     def new(self, *shape, like: torch.Tensor, dtype=torch.float32):
         return torch.empty(*shape, device=like.device, dtype=dtype)
+
+    def scratch(self, floats: int, like: torch.Tensor) -> torch.Tensor:
+        if self._scratch is None or self._scratch.device != like.device or self._scratch.numel() < floats:
+            self._scratch = torch.empty(max(int(floats), 1 << 20), device=like.device, dtype=torch.float32)
+        return self._scratch
 
     def _gview(self, name):
         """Where the gradient of parameter ``name`` is written (flat gradient buffer when there is one)."""
@@ -175,8 +181,9 @@ class DiffGraph:
             if self.param_grads:
                 gw = self._gview(wname)
                 gb = self._gview(bname) if bname else None
+                scr = self.scratch(self.lib.cistgcn_conv2d_bwd_weight_scratch_floats(ctypes.byref(sh)), x.t)
                 self._ck(self.lib.cistgcn_conv2d_bwd_weight(ctypes.byref(sh), x.t.data_ptr(), y.g.data_ptr(), gw.data_ptr(),
-                                                            gb.data_ptr() if gb is not None else None, st), "conv2d_bwd_weight")
+                                                            gb.data_ptr() if gb is not None else None, scr.data_ptr(), st), "conv2d_bwd_weight")
             if x.needs:
                 dx = torch.empty_like(x.t)
                 self._ck(self.lib.cistgcn_conv2d_bwd_input(ctypes.byref(sh), y.g.data_ptr(), w.data_ptr(), dx.data_ptr(), st), "conv2d_bwd_input")
@@ -197,8 +204,10 @@ class DiffGraph:
         sm, si = self.new(C, like=x.t), self.new(C, like=x.t)
         st = self._stream(x.t)
         tr = int(self.training)
+        scr = self.scratch(self.lib.cistgcn_bn_scratch_floats(C), x.t)
         self._ck(self.lib.cistgcn_bn_fwd(x.t.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr(), y.t.data_ptr(),
-                                         sm.data_ptr(), si.data_ptr(), B, C, HW, tr, _f(self.BN_MOMENTUM), _f(self.BN_EPS), st), "bn_fwd")
+                                         sm.data_ptr(), si.data_ptr(), scr.data_ptr(), B, C, HW, tr, _f(self.BN_MOMENTUM), _f(self.BN_EPS), st),
+                 "bn_fwd")
         if self.training:
             nbt = self.buffers.get(p + ".num_batches_tracked")
             if nbt is not None:
@@ -212,7 +221,7 @@ class DiffGraph:
             dx = torch.empty_like(x.t)
             self._ck(self.lib.cistgcn_bn_bwd(x.t.data_ptr(), y.g.data_ptr(), gamma.data_ptr(), sm.data_ptr(), si.data_ptr(), dx.data_ptr(),
                                              gg.data_ptr() if gg is not None else None, gb.data_ptr() if gb is not None else None,
-                                             B, C, HW, tr, st), "bn_bwd")
+                                             self.scratch(self.lib.cistgcn_bn_scratch_floats(C), x.t).data_ptr(), B, C, HW, tr, st), "bn_bwd")
             self.acc(x, dx)
         self.tape.append(bwd)
         return y
@@ -649,9 +658,8 @@ class DiffGraph:
         lastb = self.bcast_axis1(self.view(last, B, V * 3), To)
         pred = self.add(x9, self.view(lastb, B, To, V, 3))
         self._pred = pred
-        if self.training:
-            for nbt in self._nbt:
-                nbt += 1                                                           # num_batches_tracked (bookkeeping only)
+        if self.training and self._nbt:
+            torch._foreach_add_(self._nbt, 1)                                      # num_batches_tracked (bookkeeping only, one launch)
         return pred.t
 
     def backward(self, dpred: torch.Tensor) -> Optional[torch.Tensor]:

@@ -236,6 +236,26 @@ int cistgcn_tail_f32(const int32_t* tail_desc, const float* weights, const float
 int cistgcn_mpjpe_f32(const float* pred, const float* target, int64_t batch, int32_t T, int32_t V,
                       float* err, double* frame_sums, void* stream);
 
+/* Fused evaluation metrics (environment/test.py:65-94 Metrics.compute, :125-129 the scatter of the model's joints into the
+ * full skeleton).  pred (B, To, Vu, 3) = model output on the used joints; target (B, To, Vf, 3) = full skeleton;
+ * src_map[Vf]: index into pred's joints or -1 (keep the target's joint: dim_used / dim_repeat_32 <- dim_repeat_22 of
+ * loaders/h36m_motion_3d.py:55-59 folded into one table).  One kernel accumulates, for every output frame, the sum over
+ * samples and joints of each metric below into sums[metric][To] (double, ACCUMULATED into; divide by B*Vf -- bones: B*n_bones
+ * -- for the reference's reduce_axis=(0, 2) values); `assembled` (optional) receives the scattered prediction. */
+enum cistgcn_metric {
+  CISTGCN_METRIC_MPJPE = 0,     /* losses.mpjpe                 losses/losses.py:50-61   */
+  CISTGCN_METRIC_PA_MPJPE,      /* losses.pa_mpjpe (Procrustes) losses/losses.py:79-144  */
+  CISTGCN_METRIC_N_MPJPE,       /* losses.n_mpjpe               losses/losses.py:147-161 */
+  CISTGCN_METRIC_VELOCITY,      /* losses.mean_velocity_error   losses/losses.py:164-179 (frames 0 .. To-2) */
+  CISTGCN_METRIC_BONE_LENGTH,   /* losses.bone_length_error     losses/losses.py:200-215 */
+  CISTGCN_METRIC_WEIGHTED0,     /* losses.weighted_mpjpe with weights0 (B, To, Vf), losses/losses.py:64-77 */
+  CISTGCN_METRIC_WEIGHTED1,     /* ... with weights1 */
+  CISTGCN_METRIC_COUNT
+};
+int cistgcn_eval_metrics_f32(const float* pred, const float* target, const int32_t* src_map, const int32_t* bones,
+                             int32_t n_bones, const float* weights0, const float* weights1, float* assembled,
+                             double* sums, int64_t batch, int32_t To, int32_t Vu, int32_t Vf, void* stream);
+
 /* Optional per-kernel timing for benchmarks (no reference counterpart).  While enabled every launch
  * (of every host thread) is bracketed by CUDA events on its stream; cistgcn_profile_read synchronises
  * the device, sums the elapsed milliseconds and launch counts per kernel kind (arrays of

@@ -33,17 +33,24 @@ typedef struct cistgcn_conv_shape {
 } cistgcn_conv_shape;
 int cistgcn_conv2d_fwd(const cistgcn_conv_shape* s, const float* x, const float* w, const float* bias, float* y, void* stream);
 int cistgcn_conv2d_bwd_input(const cistgcn_conv_shape* s, const float* dy, const float* w, float* dx, void* stream);
-int cistgcn_conv2d_bwd_weight(const cistgcn_conv_shape* s, const float* x, const float* dy, float* dw, float* dbias, void* stream);
+/* dW (and dbias) from partial sums over chunks of the (b, ho, wo) range, added in a fixed order; `scratch` holds them:
+ * cistgcn_conv2d_bwd_weight_scratch_floats(s) floats. */
+size_t cistgcn_conv2d_bwd_weight_scratch_floats(const cistgcn_conv_shape* s);
+int cistgcn_conv2d_bwd_weight(const cistgcn_conv_shape* s, const float* x, const float* dy, float* dw, float* dbias, float* scratch,
+                              void* stream);
 
 /* nn.BatchNorm{1,2}d over x (B,C,HW).  training != 0: batch statistics (biased variance) normalise, running_mean / running_var
  * are updated in place with `momentum` (unbiased variance), save_mean / save_invstd [C] are written for the backward.
- * training == 0: running statistics normalise, nothing is updated (save_* are written with the running values). */
+ * training == 0: running statistics normalise, nothing is updated (save_* are written with the running values).
+ * `scratch`: cistgcn_bn_scratch_floats(C) floats (chunked batch statistics, merged with Chan's update in a fixed order). */
+size_t cistgcn_bn_scratch_floats(int32_t C);
 int cistgcn_bn_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var, float* y,
-                   float* save_mean, float* save_invstd, int64_t B, int32_t C, int32_t HW, int32_t training, float momentum,
-                   float eps, void* stream);
+                   float* save_mean, float* save_invstd, float* scratch, int64_t B, int32_t C, int32_t HW, int32_t training,
+                   float momentum, float eps, void* stream);
 /* dgamma / dbeta may be NULL (input-gradient path).  training == 0: dx = dy * gamma * invstd. */
 int cistgcn_bn_bwd(const float* x, const float* dy, const float* gamma, const float* save_mean, const float* save_invstd,
-                   float* dx, float* dgamma, float* dbeta, int64_t B, int32_t C, int32_t HW, int32_t training, void* stream);
+                   float* dx, float* dgamma, float* dbeta, float* scratch, int64_t B, int32_t C, int32_t HW, int32_t training,
+                   void* stream);
 
 /* nn.PReLU with n_slopes in {1, C} on x (B,C,HW).  dslope [n_slopes] may be NULL; otherwise `scratch` must hold
  * n_slopes * CISTGCN_PRELU_SCRATCH_PER_SLOPE floats (partial sums, added in a fixed order: bit-reproducible). */
