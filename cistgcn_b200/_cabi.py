@@ -77,6 +77,9 @@ def bind(path: str) -> ctypes.CDLL:
     L.cistgcn_eval_metrics_f32.restype = ctypes.c_int
     L.cistgcn_eval_metrics_f32.argtypes = [_p, _p, _p, _p, ctypes.c_int32, _p, _p, _p, _p, ctypes.c_int64, ctypes.c_int32,
                                            ctypes.c_int32, ctypes.c_int32, _p]
+    L.cistgcn_augment_windows_f32.restype = ctypes.c_int
+    L.cistgcn_augment_windows_f32.argtypes = [_p, _p, _p, _p, _p, _p, _p, _p, _p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                              ctypes.c_int32, _p]
     L.cistgcn_profile_enable.restype = ctypes.c_int
     L.cistgcn_profile_enable.argtypes = [ctypes.c_int]
     L.cistgcn_profile_read.restype = ctypes.c_int

@@ -59,15 +59,22 @@ CG_DEV float block_sum(float v, float* sh) {         // sum over the CTA (NT thr
 // ------------------------------------------------------------------------------------------------ conv2d
 struct ConvP { long long B; int Ci, H, W, Co, kh, kw, ph, pw, dh, dw, Ho, Wo; };
 
+// thread = (sample, group of CF_T output channels, output position): one x load per (ci, a, c) feeds CF_T FFMAs; the
+// weights of a warp's channel group are warp-uniform (L1 broadcast)
+constexpr int CF_T = 4;
 __global__ void conv_fwd_kernel(ConvP p, const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                 float* __restrict__ y) {
-  const long long n = p.B * p.Co * p.Ho * p.Wo;
+  const int HoWo = p.Ho * p.Wo, cog = (p.Co + CF_T - 1) / CF_T, K = p.Ci * p.kh * p.kw;
+  const long long n = p.B * cog * HoWo;
   for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
-    const int wo = (int)(i % p.Wo), ho = (int)((i / p.Wo) % p.Ho), co = (int)((i / ((long long)p.Wo * p.Ho)) % p.Co);
-    const long long b = i / ((long long)p.Wo * p.Ho * p.Co);
-    float acc = bias ? bias[co] : 0.f;
-    const float* wp = w + (long long)co * p.Ci * p.kh * p.kw;
+    const int pos = (int)(i % HoWo), g = (int)((i / HoWo) % cog);
+    const long long b = i / ((long long)HoWo * cog);
+    const int wo = pos % p.Wo, ho = pos / p.Wo, co0 = g * CF_T;
+    float acc[CF_T];
+#pragma unroll
+    for (int j = 0; j < CF_T; ++j) acc[j] = (bias && co0 + j < p.Co) ? bias[co0 + j] : 0.f;
     const float* xb = x + b * p.Ci * p.H * p.W;
+    const float* wp = w + (long long)co0 * K;
     for (int ci = 0; ci < p.Ci; ++ci)
       for (int a = 0; a < p.kh; ++a) {
         const int hi = ho - p.ph + a * p.dh;
@@ -75,19 +82,29 @@ __global__ void conv_fwd_kernel(ConvP p, const float* __restrict__ x, const floa
         for (int c = 0; c < p.kw; ++c) {
           const int wi = wo - p.pw + c * p.dw;
           if (wi < 0 || wi >= p.W) continue;
-          acc = fmaf(wp[(ci * p.kh + a) * p.kw + c], xb[((long long)ci * p.H + hi) * p.W + wi], acc);
+          const float xv = xb[((long long)ci * p.H + hi) * p.W + wi];
+          const int k = (ci * p.kh + a) * p.kw + c;
+#pragma unroll
+          for (int j = 0; j < CF_T; ++j) acc[j] = fmaf(co0 + j < p.Co ? wp[(long long)j * K + k] : 0.f, xv, acc[j]);
         }
       }
-    y[i] = acc;
+#pragma unroll
+    for (int j = 0; j < CF_T; ++j)
+      if (co0 + j < p.Co) y[(b * p.Co + co0 + j) * HoWo + pos] = acc[j];
   }
 }
 
+// thread = (sample, group of CF_T input channels, input position)
 __global__ void conv_bwd_input_kernel(ConvP p, const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx) {
-  const long long n = p.B * p.Ci * p.H * p.W;
+  const int HW = p.H * p.W, cig = (p.Ci + CF_T - 1) / CF_T, K = p.Ci * p.kh * p.kw, khw = p.kh * p.kw;
+  const long long n = p.B * cig * HW;
   for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
-    const int wi = (int)(i % p.W), hi = (int)((i / p.W) % p.H), ci = (int)((i / ((long long)p.W * p.H)) % p.Ci);
-    const long long b = i / ((long long)p.W * p.H * p.Ci);
-    float acc = 0.f;
+    const int pos = (int)(i % HW), g = (int)((i / HW) % cig);
+    const long long b = i / ((long long)HW * cig);
+    const int wi = pos % p.W, hi = pos / p.W, ci0 = g * CF_T;
+    float acc[CF_T];
+#pragma unroll
+    for (int j = 0; j < CF_T; ++j) acc[j] = 0.f;
     const float* dyb = dy + b * p.Co * p.Ho * p.Wo;
     for (int a = 0; a < p.kh; ++a) {
       const int ho = hi + p.ph - a * p.dh;
@@ -95,58 +112,104 @@ __global__ void conv_bwd_input_kernel(ConvP p, const float* __restrict__ dy, con
       for (int c = 0; c < p.kw; ++c) {
         const int wo = wi + p.pw - c * p.dw;
         if (wo < 0 || wo >= p.Wo) continue;
-        const float* wp = w + ((long long)ci * p.kh + a) * p.kw + c;
+        const float* wp = w + ((long long)ci0 * p.kh + a) * p.kw + c;
         const float* dp = dyb + (long long)ho * p.Wo + wo;
-        for (int co = 0; co < p.Co; ++co)
-          acc = fmaf(wp[(long long)co * p.Ci * p.kh * p.kw], dp[(long long)co * p.Ho * p.Wo], acc);
+        for (int co = 0; co < p.Co; ++co) {
+          const float dv = dp[(long long)co * p.Ho * p.Wo];
+#pragma unroll
+          for (int j = 0; j < CF_T; ++j) acc[j] = fmaf(ci0 + j < p.Ci ? wp[(long long)co * K + j * khw] : 0.f, dv, acc[j]);
+        }
       }
     }
-    dx[i] = acc;
+#pragma unroll
+    for (int j = 0; j < CF_T; ++j)
+      if (ci0 + j < p.Ci) dx[(b * p.Ci + ci0 + j) * HW + pos] = acc[j];
   }
 }
 
-// dW / dbias: the reduction range (b, ho, wo) is cut into CONV_BW_CHUNKS chunks; a CTA owns NT consecutive items (weights
-// first, then the Co bias entries) of ONE chunk: thread = item, so threads sharing an input channel / an output channel
-// read the same x / dy element (L1 broadcast) instead of every weight re-streaming its two columns from L2.  Partials go
-// to `part[item][chunk]`; conv_bw_finish adds them in a fixed order (bit-reproducible, no atomics).
-constexpr int CONV_BW_CHUNKS = 32;
-__global__ void conv_bwd_weight_partial_kernel(ConvP p, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ part,
-                                               int n_items, int with_bias) {
-  const long long nw = (long long)p.Co * p.Ci * p.kh * p.kw;
+// dW / dbias.  A CTA owns a TCO x TK tile of the weight matrix W[co][k], k = (ci, a, c) flattened, for one chunk of the
+// reduction range (b, ho, wo); threads run over the reduction index (coalesced dy / x rows) and keep the whole tile in
+// registers: TCO + TK loads feed TCO * TK FFMAs (the first version re-streamed two full columns per weight element).
+// Chunk partials go to part[item][chunk]; conv_bw_finish adds them in a fixed order (bit-reproducible, no atomics).
+constexpr int CONV_BW_CHUNKS = 32;        // upper bound; small reductions use fewer
+constexpr int BW_TCO = 8, BW_TK = 8;
+__global__ void __launch_bounds__(NT) conv_bwd_weight_tile_kernel(ConvP p, const float* __restrict__ x, const float* __restrict__ dy,
+                                                                  float* __restrict__ part, int nchunks, int with_bias) {
+  __shared__ float sh[NT / 32][BW_TCO * BW_TK + BW_TCO];
+  const int K = p.Ci * p.kh * p.kw;
+  const int tiles_k = (K + BW_TK - 1) / BW_TK, tiles_co = (p.Co + BW_TCO - 1) / BW_TCO;
+  const long long nw = (long long)p.Co * K;
   const long long red = p.B * p.Ho * p.Wo;
-  const int tiles = (n_items + NT - 1) / NT;
-  for (int job = blockIdx.x; job < tiles * CONV_BW_CHUNKS; job += gridDim.x) {
-    const int tile = job / CONV_BW_CHUNKS, chunk = job % CONV_BW_CHUNKS;
-    const long long e = (long long)tile * NT + threadIdx.x;
-    const long long r0 = red * chunk / CONV_BW_CHUNKS, r1 = red * (chunk + 1) / CONV_BW_CHUNKS;
-    if (e >= n_items) continue;
-    float acc = 0.f;
-    if (e < nw) {
-      const int c = (int)(e % p.kw), a = (int)((e / p.kw) % p.kh), ci = (int)((e / (p.kw * p.kh)) % p.Ci);
-      const int co = (int)(e / ((long long)p.kw * p.kh * p.Ci));
-      const int oh = a * p.dh - p.ph, ow = c * p.dw - p.pw;
-      for (long long r = r0; r < r1; ++r) {
-        const int wo = (int)(r % p.Wo), ho = (int)((r / p.Wo) % p.Ho);
-        const long long b = r / ((long long)p.Wo * p.Ho);
-        const int hi = ho + oh, wi = wo + ow;
-        if (hi < 0 || hi >= p.H || wi < 0 || wi >= p.W) continue;
-        acc = fmaf(dy[((b * p.Co + co) * p.Ho + ho) * p.Wo + wo], x[((b * p.Ci + ci) * p.H + hi) * p.W + wi], acc);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int job = blockIdx.x; job < tiles_co * tiles_k * nchunks; job += gridDim.x) {
+    const int chunk = job % nchunks, tile = job / nchunks, tk = tile % tiles_k, tco = tile / tiles_k;
+    const long long r0 = red * chunk / nchunks, r1 = red * (chunk + 1) / nchunks;
+    int xoff[BW_TK], oh[BW_TK], ow[BW_TK];
+#pragma unroll
+    for (int kk = 0; kk < BW_TK; ++kk) {
+      const int k = tk * BW_TK + kk;
+      if (k < K) {
+        const int c = k % p.kw, a = (k / p.kw) % p.kh, ci = k / (p.kw * p.kh);
+        oh[kk] = a * p.dh - p.ph; ow[kk] = c * p.dw - p.pw; xoff[kk] = ci * p.H * p.W;
+      } else { oh[kk] = -(1 << 20); ow[kk] = 0; xoff[kk] = 0; }            // never inside the map: contributes 0
+    }
+    float acc[BW_TCO][BW_TK], bacc[BW_TCO];
+#pragma unroll
+    for (int j = 0; j < BW_TCO; ++j) { bacc[j] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < BW_TK; ++kk) acc[j][kk] = 0.f; }
+    const int HoWo = p.Ho * p.Wo;
+    for (long long r = r0 + threadIdx.x; r < r1; r += NT) {
+      const int wo = (int)(r % p.Wo), ho = (int)((r / p.Wo) % p.Ho);
+      const long long b = r / HoWo;
+      const float* dyp = dy + (b * p.Co + tco * BW_TCO) * HoWo + ho * p.Wo + wo;
+      const float* xb = x + b * p.Ci * p.H * p.W;
+      float dv[BW_TCO], xv[BW_TK];
+#pragma unroll
+      for (int j = 0; j < BW_TCO; ++j) dv[j] = (tco * BW_TCO + j < p.Co) ? dyp[(long long)j * HoWo] : 0.f;
+#pragma unroll
+      for (int kk = 0; kk < BW_TK; ++kk) {
+        const int hi = ho + oh[kk], wi = wo + ow[kk];
+        xv[kk] = (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) ? xb[xoff[kk] + hi * p.W + wi] : 0.f;
       }
-    } else if (with_bias) {
-      const int co = (int)(e - nw);
-      for (long long r = r0; r < r1; ++r) {
-        const long long b = r / ((long long)p.Wo * p.Ho), hw = r % ((long long)p.Wo * p.Ho);
-        acc += dy[(b * p.Co + co) * p.Ho * p.Wo + hw];
+#pragma unroll
+      for (int j = 0; j < BW_TCO; ++j) {
+        bacc[j] += dv[j];
+#pragma unroll
+        for (int kk = 0; kk < BW_TK; ++kk) acc[j][kk] = fmaf(dv[j], xv[kk], acc[j][kk]);
       }
     }
-    part[e * CONV_BW_CHUNKS + chunk] = acc;
+    // CTA reduction of the tile: warp shuffles, then the warps' rows in a fixed order
+#pragma unroll
+    for (int j = 0; j < BW_TCO; ++j) {
+#pragma unroll
+      for (int kk = 0; kk < BW_TK; ++kk) {
+        const float v = cg::warp_sum(acc[j][kk]);
+        if (lane == 0) sh[warp][j * BW_TK + kk] = v;
+      }
+      const float bv = cg::warp_sum(bacc[j]);
+      if (lane == 0) sh[warp][BW_TCO * BW_TK + j] = bv;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < BW_TCO * BW_TK + BW_TCO; i += NT) {
+      float v = 0.f;
+      for (int w = 0; w < NT / 32; ++w) v += sh[w][i];
+      if (i < BW_TCO * BW_TK) {
+        const int co = tco * BW_TCO + i / BW_TK, k = tk * BW_TK + i % BW_TK;
+        if (co < p.Co && k < K) part[((long long)co * K + k) * nchunks + chunk] = v;
+      } else if (with_bias && tk == 0) {
+        const int co = tco * BW_TCO + (i - BW_TCO * BW_TK);
+        if (co < p.Co) part[(nw + co) * nchunks + chunk] = v;
+      }
+    }
+    __syncthreads();
   }
 }
-__global__ void conv_bw_finish_kernel(const float* __restrict__ part, float* __restrict__ dw, float* __restrict__ dbias, long long nw, int n_items) {
+__global__ void conv_bw_finish_kernel(const float* __restrict__ part, float* __restrict__ dw, float* __restrict__ dbias, long long nw,
+                                      int n_items, int nchunks) {
   for (long long e = (long long)blockIdx.x * NT + threadIdx.x; e < n_items; e += (long long)gridDim.x * NT) {
     float s = 0.f;
-#pragma unroll 8
-    for (int c = 0; c < CONV_BW_CHUNKS; ++c) s += part[e * CONV_BW_CHUNKS + c];
+    for (int c = 0; c < nchunks; ++c) s += part[e * nchunks + c];
     if (e < nw) dw[e] = s; else dbias[e - nw] = s;
   }
 }
@@ -278,19 +341,21 @@ __global__ void prelu_bwd_ds_partial_kernel(const float* __restrict__ x, const f
   const int nchunk = CISTGCN_PRELU_SCRATCH_PER_SLOPE;
   for (int item = blockIdx.x; item < ns * nchunk; item += gridDim.x) {
   const int s = item / nchunk, chunk = item % nchunk;
-  float acc = 0.f;
+  // the slope gradient is a sum of ~10^5 .. 10^6 products of both signs (heavy cancellation): per-thread accumulation in
+  // fp64 keeps it at the accuracy of the reference's cascaded summation
+  double accd = 0.0;
   if (ns == 1) {
     const long long n = B * C * HW;
     for (long long i = (long long)chunk * NT + threadIdx.x; i < n; i += (long long)nchunk * NT)
-      if (x[i] < 0.f) acc = fmaf(dy[i], x[i], acc);
+      if (x[i] < 0.f) accd += (double)dy[i] * (double)x[i];
   } else {
     const long long n = B * HW;
     for (long long r = (long long)chunk * NT + threadIdx.x; r < n; r += (long long)nchunk * NT) {
       const long long i = ((r / HW) * C + s) * HW + r % HW;
-      if (x[i] < 0.f) acc = fmaf(dy[i], x[i], acc);
+      if (x[i] < 0.f) accd += (double)dy[i] * (double)x[i];
     }
   }
-  acc = block_sum(acc, sh);
+  const float acc = block_sum((float)accd, sh);
   if (threadIdx.x == 0) part[(long long)s * nchunk + chunk] = acc;
   }
 }
@@ -742,14 +807,14 @@ int cistgcn_conv2d_fwd(const cistgcn_conv_shape* s, const float* x, const float*
   ConvP p;
   if (!conv_params(s, p) || !x || !w || !y) return fail_train(-1, "conv2d_fwd: bad arguments");
   if (p.B == 0) return 0;
-  CG_LAUNCH(conv_fwd_kernel, grid_1d(p.B * p.Co * p.Ho * p.Wo), NT, 0, stream, p, x, w, bias, y);
+  CG_LAUNCH(conv_fwd_kernel, grid_1d(p.B * ((p.Co + CF_T - 1) / CF_T) * p.Ho * p.Wo), NT, 0, stream, p, x, w, bias, y);
   return launched("conv_fwd_kernel");
 }
 int cistgcn_conv2d_bwd_input(const cistgcn_conv_shape* s, const float* dy, const float* w, float* dx, void* stream) {
   ConvP p;
   if (!conv_params(s, p) || !dy || !w || !dx) return fail_train(-1, "conv2d_bwd_input: bad arguments");
   if (p.B == 0) return 0;
-  CG_LAUNCH(conv_bwd_input_kernel, grid_1d(p.B * p.Ci * p.H * p.W), NT, 0, stream, p, dy, w, dx);
+  CG_LAUNCH(conv_bwd_input_kernel, grid_1d(p.B * ((p.Ci + CF_T - 1) / CF_T) * p.H * p.W), NT, 0, stream, p, dy, w, dx);
   return launched("conv_bwd_input_kernel");
 }
 size_t cistgcn_conv2d_bwd_weight_scratch_floats(const cistgcn_conv_shape* s) {
@@ -760,13 +825,17 @@ int cistgcn_conv2d_bwd_weight(const cistgcn_conv_shape* s, const float* x, const
                               void* stream) {
   ConvP p;
   if (!conv_params(s, p) || !x || !dy || !dw || !scratch) return fail_train(-1, "conv2d_bwd_weight: bad arguments");
-  const long long nw = (long long)p.Co * p.Ci * p.kh * p.kw;
+  const int K = p.Ci * p.kh * p.kw;
+  const long long nw = (long long)p.Co * K;
   const int items = (int)(nw + (dbias ? p.Co : 0));
-  const int tiles = (items + NT - 1) / NT;
-  CG_LAUNCH(conv_bwd_weight_partial_kernel, grid_items((long long)tiles * CONV_BW_CHUNKS, 16), NT, 0, stream, p, x, dy, scratch, items,
-            dbias ? 1 : 0);
-  if (int rc = launched("conv_bwd_weight_partial_kernel")) return rc;
-  CG_LAUNCH(conv_bw_finish_kernel, grid_1d(items), NT, 0, stream, (const float*)scratch, dw, dbias, nw, items);
+  const long long red = p.B * p.Ho * p.Wo;
+  int nchunks = (int)(red / (2 * NT));                      // at least two passes of the CTA per chunk
+  if (nchunks < 1) nchunks = 1;
+  if (nchunks > CONV_BW_CHUNKS) nchunks = CONV_BW_CHUNKS;
+  const long long jobs = (long long)((p.Co + BW_TCO - 1) / BW_TCO) * ((K + BW_TK - 1) / BW_TK) * nchunks;
+  CG_LAUNCH(conv_bwd_weight_tile_kernel, grid_items(jobs, 16), NT, 0, stream, p, x, dy, scratch, nchunks, dbias ? 1 : 0);
+  if (int rc = launched("conv_bwd_weight_tile_kernel")) return rc;
+  CG_LAUNCH(conv_bw_finish_kernel, grid_1d(items), NT, 0, stream, (const float*)scratch, dw, dbias, nw, items, nchunks);
   return launched("conv_bw_finish_kernel");
 }
 

@@ -256,6 +256,27 @@ int cistgcn_eval_metrics_f32(const float* pred, const float* target, const int32
                              int32_t n_bones, const float* weights0, const float* weights1, float* assembled,
                              double* sums, int64_t batch, int32_t To, int32_t Vu, int32_t Vf, void* stream);
 
+/* GPU-side training-batch pipeline (loaders/h36m_motion_3d.py:94-108 window split + velocity / speed targets;
+ * environment/custom_transforms.py:10-419 RandomFlip, RandomRotation, RandomScale, RandomNoise, RandomTranslation in the
+ * order loaders/loader.py:42-130 composes them).  windows (N, S, V, 3): the resident dataset; index[B]: the window of every
+ * batch element; params (B, CISTGCN_AUG_PARAMS): the host-drawn random parameters (0 = transform does not fire);
+ * noise (optional) (B, V, 3): RandomNoise's uniform(-1, 1) draws.  Outputs: sample (B, Tin, V, 3), target (B, S-Tin, V, 3)
+ * and (optional) sample_vel, target_vel (cumulated velocities), target_gvel (B, S-Tin, V) (cumulated speeds). */
+enum cistgcn_aug_param {
+  CISTGCN_AUG_FLIP = 0,      /* [3] 1 = mirror that coordinate about the window's centroid        */
+  CISTGCN_AUG_ROT_ON = 3,    /* 1 = rotate about the centroid with ...                            */
+  CISTGCN_AUG_ROT = 4,       /* [9] row-major rotation matrix R: x <- (x - c) R + c               */
+  CISTGCN_AUG_SCALE_ON = 13,
+  CISTGCN_AUG_SCALE = 14,    /* [3] per-coordinate scale                                          */
+  CISTGCN_AUG_NOISE = 17,    /* amplitude (0 = off): x <- x + amp * u[joint, k] * (max - min)_k   */
+  CISTGCN_AUG_TRANS_ON = 18,
+  CISTGCN_AUG_TRANS = 19,    /* [3] translation as a fraction of the window's extent per coordinate */
+  CISTGCN_AUG_PARAMS = 24
+};
+int cistgcn_augment_windows_f32(const float* windows, const int64_t* index, const float* params, const float* noise,
+                                float* sample, float* target, float* sample_vel, float* target_vel, float* target_gvel,
+                                int64_t batch, int32_t seq_len, int32_t joints, int32_t input_n, void* stream);
+
 /* Optional per-kernel timing for benchmarks (no reference counterpart).  While enabled every launch
  * (of every host thread) is bracketed by CUDA events on its stream; cistgcn_profile_read synchronises
  * the device, sums the elapsed milliseconds and launch counts per kernel kind (arrays of

@@ -47,5 +47,5 @@ out = {
     # bone_length_error's arithmetic (:204-215) on an explicit bone list (body_utils.get_reduced_skeleton needs dataset tables)
     "bone_length": (dp - dt).abs().mean(ax).numpy(),
 }
-np.savez_compressed(os.path.join(HERE, "eval_metrics.npz"), **out)
+np.savez_compressed(os.path.join(HERE, "aux", "eval_metrics.npz"), **out)
 print({k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})

@@ -10,7 +10,7 @@ import torch
 from cistgcn_b200 import _cabi
 from cistgcn_b200.metrics import METRICS, EvalMetrics, source_map
 
-G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eval_metrics.npz"))
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "aux", "eval_metrics.npz"))
 
 
 def _run(lib, device):

@@ -19,6 +19,38 @@ def _scale(ref):
     return max(1.0, ref.abs().max().item() / 4)
 
 
+NOISE_K = 16.0      # the CUDA path may be this many times less accurate than the reference's own fp32 arithmetic
+
+
+def _truth64(sd, cfg, x, **kw):
+    """The oracle in fp64 (pinned to the reference by tests/test_oracle_golden.py): the truth both fp32 results are measured on."""
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    taps = {}
+    with torch.no_grad():
+        pred = O.forward(sd64, cfg, x.double(), taps=taps, **kw)
+    return pred, taps
+
+
+def _log(line):
+    import os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_r2_forward.log"), "a") as f:
+            f.write(line + "\n")
+
+
+def _check_noise_anchored(tag, got, ref32, truth):
+    """|cuda - truth| <= NOISE_K * |reference fp32 - truth| + 1e-6 |truth|max : the bound SURVEY.md 8(c) states as 1e-4 on
+    unit-scale outputs, re-anchored on the reference's measured fp32-vs-fp64 error so it stays meaningful for the
+    stress-initialised / mm-scale cases whose outputs reach 10^2 .. 10^3 (VERDICT r1, weak #1)."""
+    tmax = truth.abs().max().item()
+    ours = (got.double() - truth).abs().max().item()
+    noise = (ref32.double() - truth).abs().max().item()
+    _log(f"{tag}: |truth|max {tmax:.4g}  cuda-vs-fp64 {ours:.3e} (rel {ours / max(tmax, 1e-30):.2e})  reference-fp32-vs-fp64 {noise:.3e}  ratio {ours / max(noise, 1e-30):.2f}")
+    assert ours <= NOISE_K * noise + 1e-6 * tmax, (tag, ours, noise, tmax)
+    return ours, noise
+
+
 @pytest.mark.parametrize("name", G.names())
 def test_forward_matches_golden(name):
     g = G.load(name)
@@ -30,9 +62,17 @@ def test_forward_matches_golden(name):
     assert isinstance(out, tuple) and len(out) == 1
     pred = out[0].cpu()
     assert (pred - g["pred"]).abs().max().item() <= G.tol(g["pred"])
+    itp = g["interpretable"]
+    truth, ttaps = _truth64(g["sd"], g["cfg"], g["x"], interpretable_in=[itp] * 5, interpretable_out=[itp])
+    _check_noise_anchored(f"golden {name} pred", pred, g["pred"], truth)
+    stress = "stress" in name
     for k, ref in g["taps"].items():
         got = model.last_taps[k].cpu().reshape(ref.shape)
         assert (got - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item()), k
+        if stress:
+            # stress-initialised fixtures carry the check of the intermediates (at default init |Adj| ~ 3e-10 and an absolute
+            # bound is vacuous): RELATIVE 1e-4 of the tap's own magnitude, as SURVEY.md 8(c) asks
+            assert (got - ref).abs().max().item() <= 1e-4 * ref.abs().max().item(), (k, ref.abs().max().item())
     _, sums = model.forward_mpjpe(g["x"].to(DEV), g["target"].to(DEV))
     B, To, V = pred.shape[:3]
     assert abs((sums.sum() / (B * To * V)).item() - g["mpjpe_all"].item()) <= 1e-3 * _scale(g["pred"])
@@ -54,6 +94,10 @@ def test_forward_matches_oracle(E, V, weights, scale):
     pred = pred.cpu()
     assert torch.isfinite(pred).all()
     assert (pred - ref).abs().max().item() <= G.tol(ref)
+    truth, _ = _truth64(sd, cfg, x)
+    ours, noise = _check_noise_anchored(f"oracle E={E} V={V} {weights} {scale}", pred, ref, truth)
+    if weights == "W1" and scale == "unit":
+        assert (pred - ref).abs().max().item() <= 1e-4              # the case north_star names: absolute 1e-4
     assert abs((sums.sum() / (48 * 25 * V)).item() - O.mpjpe(ref, tgt).item()) <= 1e-3 * _scale(ref)
     for k in ("st_gcnns.1.dsgn.Adj", "st_gcnns.3.tsgn.Adj", "st_gcnns.2.w1", "st_gcnns.4.w2",
               "st_gcnns_o.0.dsgn.Adj", "st_gcnns_o.0.tsgn.Adj", "context_layer.joints", "context_layer.displacements"):
@@ -133,6 +177,25 @@ def test_full_size_batch_64k_e32():
     assert (pred[sel.to(DEV)].cpu() - ref).abs().max().item() <= G.tol(ref)
 
 
+def test_full_size_batch_256k_e64_amass():
+    """BASELINE configs[2] size (E=64, AMASS shape, global batch 262144, forward + MPJPE): finite outputs, MPJPE
+    bookkeeping linear over the internal chunks, and a 64-sample spot check vs the oracle."""
+    model, sd, cfg = M.build(64, 18, "W1")
+    B = 262144
+    x, tgt = O.synth_inputs(B, cfg)
+    model = model.to(DEV)
+    xd, td = x.to(DEV), tgt.to(DEV)
+    pred, sums = model.forward_mpjpe(xd, td)
+    assert torch.isfinite(pred).all()
+    m_all = mpjpe(pred, td)
+    assert abs(m_all.item() - (sums.sum() / (B * 25 * 18)).item()) <= 1e-5
+    sel = torch.randperm(B, generator=torch.Generator().manual_seed(2))[:64]
+    with torch.no_grad():
+        ref = O.forward(sd, cfg, x[sel])
+    assert (pred[sel.to(DEV)].cpu() - ref).abs().max().item() <= 1e-4
+    assert abs((mpjpe(pred[sel.to(DEV)].contiguous(), td[sel.to(DEV)].contiguous()) .item()) - O.mpjpe(ref, tgt[sel]).item()) <= 1e-3
+
+
 def test_mpjpe_all_reductions():
     g = torch.Generator().manual_seed(5)
     p, t = torch.randn(257, 25, 22, 3, generator=g), torch.randn(257, 25, 22, 3, generator=g)
@@ -140,6 +203,8 @@ def test_mpjpe_all_reductions():
     assert torch.allclose(mpjpe(pd, td, reduce_axis=None).cpu(), O.mpjpe(p, t, None), rtol=1e-6, atol=1e-6)
     assert torch.allclose(mpjpe(pd, td).cpu(), O.mpjpe(p, t), rtol=1e-6, atol=1e-6)
     assert torch.allclose(mpjpe(pd, td, reduce_axis=(0, 2)).cpu(), O.mpjpe(p, t, (0, 2)), rtol=1e-6, atol=1e-6)
+    # per-sample MPJPE (environment/adversarial_attacks.py:193, 521)
+    assert torch.allclose(mpjpe(pd, td, reduce_axis=[1, 2]).cpu(), O.mpjpe(p, t, (1, 2)), rtol=1e-5, atol=1e-6)
     with pytest.raises(AssertionError):
         mpjpe(pd, td[:, :10])
 
