@@ -217,7 +217,11 @@ __global__ void conv_bw_finish_kernel(const float* __restrict__ part, float* __r
 // ------------------------------------------------------------------------------------------------ batch norm
 // Statistics over (B, HW) per channel are cut into BN_CHUNKS chunks so that C * BN_CHUNKS CTAs work at once (C alone is
 // 3 .. 64 CTAs on 148 SMs).  scratch layout (floats): part[C][BN_CHUNKS][2] then coef[C][2].
+#ifdef CISTGCN_EMU
+constexpr int BN_CHUNKS = 2;              // SIMT emulator: every chunk costs host-thread barriers
+#else
 constexpr int BN_CHUNKS = 16;
+#endif
 // chunk statistics, two passes inside the chunk: (mean_k, M2_k = sum (x - mean_k)^2)
 __global__ void bn_stats_kernel(const float* __restrict__ x, float* __restrict__ part, long long B, int C, int HW) {
   __shared__ float sh[NT / 32];
@@ -832,6 +836,9 @@ int cistgcn_conv2d_bwd_weight(const cistgcn_conv_shape* s, const float* x, const
   int nchunks = (int)(red / (2 * NT));                      // at least two passes of the CTA per chunk
   if (nchunks < 1) nchunks = 1;
   if (nchunks > CONV_BW_CHUNKS) nchunks = CONV_BW_CHUNKS;
+#ifdef CISTGCN_EMU
+  if (nchunks > 2) nchunks = 2;                              // SIMT emulator: every job costs host-thread barriers
+#endif
   const long long jobs = (long long)((p.Co + BW_TCO - 1) / BW_TCO) * ((K + BW_TK - 1) / BW_TK) * nchunks;
   CG_LAUNCH(conv_bwd_weight_tile_kernel, grid_items(jobs, 16), NT, 0, stream, p, x, dy, scratch, nchunks, dbias ? 1 : 0);
   if (int rc = launched("conv_bwd_weight_tile_kernel")) return rc;
