@@ -45,6 +45,18 @@ inline int grid_items(long long items, int per_sm) {
   return (int)(g < 1 ? 1 : g);
 }
 
+CG_DEV double block_sum_f64(double v, double* sh) {   // same in fp64 (heavily cancelling sums: PReLU slope gradients)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int i = 0; i < NT / 32; ++i) s += sh[i];
+  return s;
+}
+
 CG_DEV float block_sum(float v, float* sh) {         // sum over the CTA (NT threads); result in every thread
   v = cg::warp_sum(v);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -216,52 +228,55 @@ __global__ void conv_bw_finish_kernel(const float* __restrict__ part, float* __r
 
 // ------------------------------------------------------------------------------------------------ batch norm
 // Statistics over (B, HW) per channel are cut into BN_CHUNKS chunks so that C * BN_CHUNKS CTAs work at once (C alone is
-// 3 .. 64 CTAs on 148 SMs).  scratch layout (floats): part[C][BN_CHUNKS][2] then coef[C][2].
+// 3 .. 64 CTAs on 148 SMs).  scratch layout: DOUBLE part[C][BN_CHUNKS][2] then float coef[C][2].  Every reduction of
+// the BatchNorm pair runs in fp64, like ATen's CPU kernels (acc_type<float> = double there): the sums behind dbeta /
+// dgamma / mean(dy) cancel heavily on the 1 .. 4 channel maps of Map2Adj, and in fp32 their error fed 10 .. 40 x the
+// reference's own noise into the gradients upstream of them.
 #ifdef CISTGCN_EMU
 constexpr int BN_CHUNKS = 2;              // SIMT emulator: every chunk costs host-thread barriers
 #else
 constexpr int BN_CHUNKS = 16;
 #endif
 // chunk statistics, two passes inside the chunk: (mean_k, M2_k = sum (x - mean_k)^2)
-__global__ void bn_stats_kernel(const float* __restrict__ x, float* __restrict__ part, long long B, int C, int HW) {
-  __shared__ float sh[NT / 32];
+__global__ void bn_stats_kernel(const float* __restrict__ x, double* __restrict__ part, long long B, int C, int HW) {
+  __shared__ double sh[NT / 32];
   const long long n = B * HW;
   for (int job = blockIdx.x; job < C * BN_CHUNKS; job += gridDim.x) {
     const int c = job / BN_CHUNKS, k = job % BN_CHUNKS;
     const long long r0 = n * k / BN_CHUNKS, r1 = n * (k + 1) / BN_CHUNKS;
-    float s = 0.f;
-    for (long long r = r0 + threadIdx.x; r < r1; r += NT) s += x[((r / HW) * C + c) * HW + r % HW];
-    const float cnt = (float)(r1 - r0);
-    const float mean = cnt > 0 ? block_sum(s, sh) / cnt : 0.f;
-    float q = 0.f;
-    for (long long r = r0 + threadIdx.x; r < r1; r += NT) { const float d = x[((r / HW) * C + c) * HW + r % HW] - mean; q = fmaf(d, d, q); }
-    q = block_sum(q, sh);
+    double s = 0.0;
+    for (long long r = r0 + threadIdx.x; r < r1; r += NT) s += (double)x[((r / HW) * C + c) * HW + r % HW];
+    const double cnt = (double)(r1 - r0);
+    const double mean = cnt > 0 ? block_sum_f64(s, sh) / cnt : 0.0;
+    double q = 0.0;
+    for (long long r = r0 + threadIdx.x; r < r1; r += NT) { const double d = (double)x[((r / HW) * C + c) * HW + r % HW] - mean; q = fma(d, d, q); }
+    q = block_sum_f64(q, sh);
     if (threadIdx.x == 0) { part[(c * BN_CHUNKS + k) * 2] = mean; part[(c * BN_CHUNKS + k) * 2 + 1] = q; }
     __syncthreads();
   }
 }
 // merge the chunks (Chan's update, fixed order), update the running statistics, emit save_mean / save_invstd
-__global__ void bn_finalize_kernel(const float* __restrict__ part, float* running_mean, float* running_var, float* save_mean,
+__global__ void bn_finalize_kernel(const double* __restrict__ part, float* running_mean, float* running_var, float* save_mean,
                                    float* save_invstd, long long B, int C, int HW, int training, float momentum, float eps) {
   const long long n = B * HW;
   for (int c = blockIdx.x * NT + threadIdx.x; c < C; c += gridDim.x * NT) {
     float mean, invstd;
     if (training) {
-      float na = 0.f, m = 0.f, M2 = 0.f;
+      double na = 0.0, m = 0.0, M2 = 0.0;
       for (int k = 0; k < BN_CHUNKS; ++k) {
-        const float nb = (float)(n * (k + 1) / BN_CHUNKS - n * k / BN_CHUNKS);
-        if (nb <= 0.f) continue;
-        const float mb = part[(c * BN_CHUNKS + k) * 2], qb = part[(c * BN_CHUNKS + k) * 2 + 1];
-        const float delta = mb - m;
+        const double nb = (double)(n * (k + 1) / BN_CHUNKS - n * k / BN_CHUNKS);
+        if (nb <= 0.0) continue;
+        const double mb = part[(c * BN_CHUNKS + k) * 2], qb = part[(c * BN_CHUNKS + k) * 2 + 1];
+        const double delta = mb - m;
         m += delta * (nb / (na + nb));
         M2 += qb + delta * delta * (na * nb / (na + nb));
         na += nb;
       }
-      mean = m;
-      const float var = M2 / (float)n;
-      invstd = 1.f / sqrtf(var + eps);
+      mean = (float)m;
+      const double var = M2 / (double)n;
+      invstd = (float)(1.0 / sqrt(var + (double)eps));
       running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
-      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (n > 1 ? M2 / (float)(n - 1) : var);
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(n > 1 ? M2 / (double)(n - 1) : var);
     } else {
       mean = running_mean[c];
       invstd = 1.f / sqrtf(running_var[c] + eps);
@@ -280,34 +295,34 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __rest
 }
 // backward: chunk sums of dy and dy * xhat -> part[C][BN_CHUNKS][2]
 __global__ void bn_bwd_partial_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ save_mean,
-                                      const float* __restrict__ save_invstd, float* __restrict__ part, long long B, int C, int HW) {
-  __shared__ float sh[NT / 32];
+                                      const float* __restrict__ save_invstd, double* __restrict__ part, long long B, int C, int HW) {
+  __shared__ double sh[NT / 32];
   const long long n = B * HW;
   for (int job = blockIdx.x; job < C * BN_CHUNKS; job += gridDim.x) {
     const int c = job / BN_CHUNKS, k = job % BN_CHUNKS;
     const long long r0 = n * k / BN_CHUNKS, r1 = n * (k + 1) / BN_CHUNKS;
     const float mean = save_mean[c], invstd = save_invstd[c];
-    float sdy = 0.f, sdyx = 0.f;
+    double sdy = 0.0, sdyx = 0.0;
     for (long long r = r0 + threadIdx.x; r < r1; r += NT) {
       const long long i = ((r / HW) * C + c) * HW + r % HW;
-      const float d = dy[i];
+      const double d = (double)dy[i];
       sdy += d;
-      sdyx = fmaf(d, (x[i] - mean) * invstd, sdyx);
+      sdyx = fma(d, (double)((x[i] - mean) * invstd), sdyx);
     }
-    sdy = block_sum(sdy, sh);
-    sdyx = block_sum(sdyx, sh);
+    sdy = block_sum_f64(sdy, sh);
+    sdyx = block_sum_f64(sdyx, sh);
     if (threadIdx.x == 0) { part[(c * BN_CHUNKS + k) * 2] = sdy; part[(c * BN_CHUNKS + k) * 2 + 1] = sdyx; }
     __syncthreads();
   }
 }
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, float* __restrict__ coef, float* dgamma, float* dbeta, long long B,
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ part, float* __restrict__ coef, float* dgamma, float* dbeta, long long B,
                                        int C, int HW) {
-  const float n = (float)(B * HW);
+  const double n = (double)(B * HW);
   for (int c = blockIdx.x * NT + threadIdx.x; c < C; c += gridDim.x * NT) {
-    float sdy = 0.f, sdyx = 0.f;
+    double sdy = 0.0, sdyx = 0.0;
     for (int k = 0; k < BN_CHUNKS; ++k) { sdy += part[(c * BN_CHUNKS + k) * 2]; sdyx += part[(c * BN_CHUNKS + k) * 2 + 1]; }
-    if (dgamma) { dgamma[c] = sdyx; dbeta[c] = sdy; }
-    coef[2 * c] = sdy / n; coef[2 * c + 1] = sdyx / n;
+    if (dgamma) { dgamma[c] = (float)sdyx; dbeta[c] = (float)sdy; }
+    coef[2 * c] = (float)(sdy / n); coef[2 * c + 1] = (float)(sdyx / n);
   }
 }
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
@@ -339,14 +354,14 @@ __global__ void prelu_bwd_dx_kernel(const float* __restrict__ x, const float* __
   }
 }
 // partial sums per CTA -> part[slope][gridDim.y]; a second tiny kernel adds them in a fixed order (bit-reproducible)
-__global__ void prelu_bwd_ds_partial_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ part,
+__global__ void prelu_bwd_ds_partial_kernel(const float* __restrict__ x, const float* __restrict__ dy, double* __restrict__ part,
                                             long long B, int C, int HW, int ns) {
-  __shared__ float sh[NT / 32];
+  __shared__ double sh[NT / 32];
   const int nchunk = CISTGCN_PRELU_SCRATCH_PER_SLOPE;
   for (int item = blockIdx.x; item < ns * nchunk; item += gridDim.x) {
   const int s = item / nchunk, chunk = item % nchunk;
-  // the slope gradient is a sum of ~10^5 .. 10^6 products of both signs (heavy cancellation): per-thread accumulation in
-  // fp64 keeps it at the accuracy of the reference's cascaded summation
+  // the slope gradient is a sum of ~10^5 .. 10^6 products of both signs whose total is orders of magnitude below its
+  // terms (the reference's own fp32 result is only good to ~3e-4 on some of them): the whole reduction runs in fp64
   double accd = 0.0;
   if (ns == 1) {
     const long long n = B * C * HW;
@@ -359,15 +374,15 @@ __global__ void prelu_bwd_ds_partial_kernel(const float* __restrict__ x, const f
       if (x[i] < 0.f) accd += (double)dy[i] * (double)x[i];
     }
   }
-  const float acc = block_sum((float)accd, sh);
+  const double acc = block_sum_f64(accd, sh);
   if (threadIdx.x == 0) part[(long long)s * nchunk + chunk] = acc;
   }
 }
-__global__ void sum_rows_kernel(const float* __restrict__ part, float* __restrict__ out, int rows, int cols) {
+__global__ void sum_rows_kernel(const double* __restrict__ part, float* __restrict__ out, int rows, int cols) {
   for (int r = blockIdx.x * NT + threadIdx.x; r < rows; r += gridDim.x * NT) {
-    float s = 0.f;
+    double s = 0.0;
     for (int c = 0; c < cols; ++c) s += part[(long long)r * cols + c];
-    out[r] = s;
+    out[r] = (float)s;
   }
 }
 
@@ -846,7 +861,7 @@ int cistgcn_conv2d_bwd_weight(const cistgcn_conv_shape* s, const float* x, const
   return launched("conv_bw_finish_kernel");
 }
 
-size_t cistgcn_bn_scratch_floats(int32_t C) { return (size_t)C * (2 * BN_CHUNKS + 2); }
+size_t cistgcn_bn_scratch_floats(int32_t C) { return (size_t)C * (4 * BN_CHUNKS + 2); }   // fp64 partials + fp32 coefficients
 int cistgcn_bn_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var, float* y,
                    float* save_mean, float* save_invstd, float* scratch, int64_t B, int32_t C, int32_t HW, int32_t training,
                    float momentum, float eps, void* stream) {
@@ -854,10 +869,10 @@ int cistgcn_bn_fwd(const float* x, const float* gamma, const float* beta, float*
       (training && !scratch))
     return fail_train(-1, "bn_fwd: bad arguments");
   if (training) {
-    CG_LAUNCH(bn_stats_kernel, grid_items((long long)C * BN_CHUNKS, 16), NT, 0, stream, x, scratch, (long long)B, C, HW);
+    CG_LAUNCH(bn_stats_kernel, grid_items((long long)C * BN_CHUNKS, 16), NT, 0, stream, x, reinterpret_cast<double*>(scratch), (long long)B, C, HW);
     if (int rc = launched("bn_stats_kernel")) return rc;
   }
-  CG_LAUNCH(bn_finalize_kernel, grid_1d(C), NT, 0, stream, (const float*)scratch, running_mean, running_var, save_mean, save_invstd,
+  CG_LAUNCH(bn_finalize_kernel, grid_1d(C), NT, 0, stream, (const double*)reinterpret_cast<double*>(scratch), running_mean, running_var, save_mean, save_invstd,
             (long long)B, C, HW, training, momentum, eps);
   if (int rc = launched("bn_finalize_kernel")) return rc;
   const long long n = (long long)B * C * HW;
@@ -870,12 +885,12 @@ int cistgcn_bn_bwd(const float* x, const float* dy, const float* gamma, const fl
   if (!x || !dy || !gamma || !save_mean || !save_invstd || !dx || !scratch || B < 1 || C < 1 || HW < 1 ||
       ((dgamma == nullptr) != (dbeta == nullptr)))
     return fail_train(-1, "bn_bwd: bad arguments");
-  float* coef = scratch + (size_t)C * 2 * BN_CHUNKS;
+  float* coef = scratch + (size_t)C * 4 * BN_CHUNKS;          // behind the fp64 partials
   if (training || dgamma) {
-    CG_LAUNCH(bn_bwd_partial_kernel, grid_items((long long)C * BN_CHUNKS, 16), NT, 0, stream, x, dy, save_mean, save_invstd, scratch,
-              (long long)B, C, HW);
+    CG_LAUNCH(bn_bwd_partial_kernel, grid_items((long long)C * BN_CHUNKS, 16), NT, 0, stream, x, dy, save_mean, save_invstd,
+              reinterpret_cast<double*>(scratch), (long long)B, C, HW);
     if (int rc = launched("bn_bwd_partial_kernel")) return rc;
-    CG_LAUNCH(bn_bwd_finalize_kernel, grid_1d(C), NT, 0, stream, (const float*)scratch, coef, dgamma, dbeta, (long long)B, C, HW);
+    CG_LAUNCH(bn_bwd_finalize_kernel, grid_1d(C), NT, 0, stream, (const double*)reinterpret_cast<double*>(scratch), coef, dgamma, dbeta, (long long)B, C, HW);
     if (int rc = launched("bn_bwd_finalize_kernel")) return rc;
   }
   const long long n = (long long)B * C * HW;
@@ -899,10 +914,10 @@ int cistgcn_prelu_bwd(const float* x, const float* dy, const float* slope, float
   if (int rc = launched("prelu_bwd_dx_kernel")) return rc;
   if (dslope) {
     constexpr int NCHUNK = CISTGCN_PRELU_SCRATCH_PER_SLOPE;       // partial sums per slope, added in a fixed order
-    float* part = scratch;
+    double* part = reinterpret_cast<double*>(scratch);        // scratch is 8-byte aligned (caller: 2 floats per partial)
     CG_LAUNCH(prelu_bwd_ds_partial_kernel, grid_items((long long)n_slopes * NCHUNK, 64), NT, 0, stream, x, dy, part, (long long)B, C, HW, n_slopes);
     if (int rc = launched("prelu_bwd_ds_partial_kernel")) return rc;
-    CG_LAUNCH(sum_rows_kernel, grid_1d(n_slopes), NT, 0, stream, (const float*)part, dslope, n_slopes, NCHUNK);
+    CG_LAUNCH(sum_rows_kernel, grid_1d(n_slopes), NT, 0, stream, (const double*)part, dslope, n_slopes, NCHUNK);
     return launched("sum_rows_kernel");
   }
   return 0;

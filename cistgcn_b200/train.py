@@ -239,7 +239,7 @@ class DiffGraph:
             if y.g is None:
                 return
             ga = self._gview(p + ".weight")
-            scratch = self.new(ns * 64, like=x.t) if ga is not None else None
+            scratch = self.new(ns * 64, like=x.t, dtype=torch.float64) if ga is not None else None
             dx = torch.empty_like(x.t)
             self._ck(self.lib.cistgcn_prelu_bwd(x.t.data_ptr(), y.g.data_ptr(), a.data_ptr(), dx.data_ptr(),
                                                 ga.data_ptr() if ga is not None else None,

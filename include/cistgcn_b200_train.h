@@ -42,7 +42,8 @@ int cistgcn_conv2d_bwd_weight(const cistgcn_conv_shape* s, const float* x, const
 /* nn.BatchNorm{1,2}d over x (B,C,HW).  training != 0: batch statistics (biased variance) normalise, running_mean / running_var
  * are updated in place with `momentum` (unbiased variance), save_mean / save_invstd [C] are written for the backward.
  * training == 0: running statistics normalise, nothing is updated (save_* are written with the running values).
- * `scratch`: cistgcn_bn_scratch_floats(C) floats (chunked batch statistics, merged with Chan's update in a fixed order). */
+ * `scratch`: cistgcn_bn_scratch_floats(C) floats, 8-byte aligned (chunked batch statistics kept in fp64, merged with
+ * Chan's update in a fixed order; every BatchNorm reduction accumulates in fp64 like ATen's CPU kernels). */
 size_t cistgcn_bn_scratch_floats(int32_t C);
 int cistgcn_bn_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var, float* y,
                    float* save_mean, float* save_invstd, float* scratch, int64_t B, int32_t C, int32_t HW, int32_t training,
@@ -53,7 +54,8 @@ int cistgcn_bn_bwd(const float* x, const float* dy, const float* gamma, const fl
                    void* stream);
 
 /* nn.PReLU with n_slopes in {1, C} on x (B,C,HW).  dslope [n_slopes] may be NULL; otherwise `scratch` must hold
- * n_slopes * CISTGCN_PRELU_SCRATCH_PER_SLOPE floats (partial sums, added in a fixed order: bit-reproducible). */
+ * n_slopes * CISTGCN_PRELU_SCRATCH_PER_SLOPE DOUBLES, 8-byte aligned (fp64 partial sums, added in a fixed order:
+ * bit-reproducible; the slope gradients are heavily cancelling sums). */
 #define CISTGCN_PRELU_SCRATCH_PER_SLOPE 64
 int cistgcn_prelu_fwd(const float* x, const float* slope, float* y, int64_t B, int32_t C, int32_t HW, int32_t n_slopes, void* stream);
 int cistgcn_prelu_bwd(const float* x, const float* dy, const float* slope, float* dx, float* dslope, float* scratch, int64_t B,

@@ -57,28 +57,48 @@ def _ours(E, V, sd, x, tgt, lib, device="cpu", train=True, input_grad=False, int
     return pred, loss, g, model, dx
 
 
-def _compare(E, V, B, lib, device, interp=True, train=True, input_grad=False):
+def _ulp_perturbed(t, gen):
+    """t with every element moved by a random fraction of one fp32 ulp (|delta| <= 2^-24 |t|): the same problem to
+    working precision."""
+    if not torch.is_floating_point(t):
+        return t.clone()
+    return t * (1.0 + (torch.rand(t.shape, generator=gen, dtype=torch.float64) * 2 - 1).to(t.dtype) * 2.0 ** -24)
+
+
+def _compare(E, V, B, lib, device, interp=True, train=True, input_grad=False, draws=3):
     model0, sd, cfg = M.build(E, V, "W2", interp=interp)
     x, tgt = O.synth_inputs(B, cfg)
     rp, rl, rg, rsd, rdx = _reference_step(E, V, sd, x, tgt, train, input_grad, interp)
-    # the reference's own fp32 noise: the same step in fp64 is the truth both fp32 runs are measured against.  Gradients
-    # travel through ~160 train-mode BatchNorms (small batches make them touchy) and sums of ~10^5 cancelling terms, so a
-    # fixed relative bound is either vacuous or flaky; "no worse than a small multiple of the reference's own error" is not.
+    # Truth = the reference step in fp64.  The yardstick is the reference's OWN fp32 noise against that truth, sampled
+    # (1 + draws) times: the plain fp32 run and `draws` fp32 runs whose weights and inputs are moved by less than one ulp
+    # (the same problem to working precision; a backward-stable evaluation is allowed exactly the answers of such
+    # neighbours).  One sample is not a yardstick here: the ~130 scalar PReLU slope gradients are sums of 10^4 .. 10^6
+    # products of both signs whose total is orders of magnitude below the terms, and the gate MLPs normalise with
+    # BatchNorm1d over a 3 .. 24 sample batch, so the fp32 error of ONE slope varies by more than 10x between two
+    # summation orders (observed: 5e-4 in one run, 1e-2 in the next) while every convolution / linear / BatchNorm tensor
+    # sits at 1e-5 .. 1e-4.  The per-tensor maximum over the samples is the noise level the bound multiplies.
     tp, tl, tg, _, tdx = _reference_step(E, V, sd, x, tgt, train, input_grad, interp, dtype=torch.float64)
+    noise_l2 = {n: (gr.double() - tg[n]).norm().item() / max(tg[n].norm().item(), 1e-30) for n, gr in rg.items()}
+    noise_dx = (rdx.double() - tdx).norm().item() / tdx.norm().item() if input_grad else 0.0
+    gen = torch.Generator().manual_seed(99)
+    for _ in range(draws):
+        sdp = {k: _ulp_perturbed(v, gen) for k, v in sd.items()}
+        _, _, pg, _, pdx = _reference_step(E, V, sdp, _ulp_perturbed(x, gen), tgt, train, input_grad, interp)
+        for n, gr in pg.items():
+            noise_l2[n] = max(noise_l2[n], (gr.double() - tg[n]).norm().item() / max(tg[n].norm().item(), 1e-30))
+        if input_grad:
+            noise_dx = max(noise_dx, (pdx.double() - tdx).norm().item() / tdx.norm().item())
     pred, loss, g, model, dx = _ours(E, V, sd, x, tgt, lib, device, train, input_grad, interp)
     scale = max(1.0, rp.abs().max().item())
     assert (pred.cpu() - rp).abs().max().item() <= 2e-4 * scale
     assert abs(loss.item() - rl.item()) <= 1e-4 * max(1.0, abs(rl.item()))
     # Per parameter tensor, against the fp64 truth:
-    #   (1) relative L2 error <= max(20 x the reference's own fp32 relative L2 error, 5e-3);
+    #   (1) relative L2 error <= max(10 x the reference's fp32 noise level on that tensor (above), 2e-3);
     #   (2) max-abs error <= 5e-3 of the tensor's largest entry + 1e-4 of the largest gradient in the model.
-    # Why not a plain multiple of the reference's max-abs noise: the network has kinks -- the two max-poolings of the
-    # ContextLayer (CISTGCN.py:465-466) route a gradient to ONE arg-max element and ~130 PReLUs switch slope at 0.  Two
-    # fp32 evaluations with different summation orders resolve a handful of near-ties differently, which moves single
-    # gradient entries by O(1e-3) relative while leaving the tensor as a whole (L2) at fp32 noise level; and the gate MLPs
-    # normalise with BatchNorm1d over the BATCH axis only, which at the tiny test batches (3 .. 24 samples) amplifies
-    # rounding noise into the handful of scalar PReLU slopes behind them (observed: up to ~1e-2 relative on single slopes,
-    # 1e-5 .. 1e-4 on every convolution / linear / BatchNorm tensor; gpurun_out/parity_r2_train.log keeps the table).
+    # (2) is not a multiple of the reference's max-abs noise because the network has kinks -- the two max-poolings of the
+    # ContextLayer (CISTGCN.py:465-466) route a gradient to ONE arg-max element and ~130 PReLUs switch slope at 0; two fp32
+    # evaluations resolve a handful of near-ties differently, which moves single entries by O(1e-3) relative while the
+    # tensor as a whole (L2) stays at noise level.  gpurun_out/parity_r2_train.log keeps the observed table.
     worst = ("", 0.0)
     gmax = max(gr.abs().max().item() for gr in tg.values())
     rows = []
@@ -89,13 +109,13 @@ def _compare(E, V, B, lib, device, interp=True, train=True, input_grad=False):
         den = max(truth.abs().max().item(), 1e-30)
         l2 = max(truth.norm().item(), 1e-30)
         ours_abs, ref_abs = (got - truth).abs().max().item(), (gr.double() - truth).abs().max().item()
-        ours_l2, ref_l2 = (got - truth).norm().item() / l2, (gr.double() - truth).norm().item() / l2
+        ours_l2, ref_l2 = (got - truth).norm().item() / l2, noise_l2[n]
         if truth.abs().max().item() > 1e-4 * gmax:
             rows.append((n, ours_abs / den, ref_abs / den, ours_l2, ref_l2))
         if ours_abs / den > worst[1]:
             worst = (n, ours_abs / den)
         if truth.abs().max().item() > 1e-4 * gmax:                  # tensors whose gradient is 0 in exact arithmetic: (2) only
-            assert ours_l2 <= max(20 * ref_l2, 5e-3), (n, ours_l2, ref_l2)
+            assert ours_l2 <= max(10 * ref_l2, 2e-3), (n, ours_l2, ref_l2)
         assert ours_abs <= 5e-3 * den + 1e-4 * gmax, (n, ours_abs, ref_abs, den)
     _log_parity(f"train-grad E={E} V={V} B={B} interp={interp} device={device}", rows)
     if train:                                                       # running statistics updated like torch (momentum 0.1)
@@ -107,11 +127,11 @@ def _compare(E, V, B, lib, device, interp=True, train=True, input_grad=False):
                 assert int(osd[k]) == int(v), k
     if input_grad:
         l2 = tdx.norm().item()
-        ours_l2, ref_l2 = (dx.cpu().double() - tdx).norm().item() / l2, (rdx.double() - tdx).norm().item() / l2
+        ours_l2 = (dx.cpu().double() - tdx).norm().item() / l2
         ours_abs = (dx.cpu().double() - tdx).abs().max().item()
         _log_parity(f"input-grad E={E} V={V} B={B} device={device}", [("d loss / d x", ours_abs / tdx.abs().max().item(),
-                    (rdx.double() - tdx).abs().max().item() / tdx.abs().max().item(), ours_l2, ref_l2)])
-        assert ours_l2 <= max(20 * ref_l2, 5e-3), (ours_l2, ref_l2)
+                    (rdx.double() - tdx).abs().max().item() / tdx.abs().max().item(), ours_l2, noise_dx)])
+        assert ours_l2 <= max(10 * noise_dx, 2e-3), (ours_l2, noise_dx)
         assert ours_abs <= 5e-3 * tdx.abs().max().item(), ours_abs
     return worst
 
