@@ -519,7 +519,8 @@ def run_train(args, rank, world, local_rank):
     opt = make_opt(E, V, dropout=0.1)                        # learning_config.dropout of train_h36m.yaml
     torch.manual_seed(0)
     model = CISTGCN(opt.architecture_config, opt.learning_config).to(dev).train()
-    tr = Trainer(model, lr=0.01, weight_decay=1e-4)
+    tr = Trainer(model, lr=0.01, weight_decay=1e-4, cuda_graph=not args.no_graph)
+    tr.graph.seed += rank                                    # every replica draws its own dropout masks
     x_host, t_host = synth_inputs(B, V, seed=123 + rank)
     x_pin, t_pin = x_host.pin_memory(), t_host.pin_memory()
     x, tgt = x_pin.to(dev), t_pin.to(dev)
@@ -538,7 +539,7 @@ def run_train(args, rank, world, local_rank):
         return float(t.item())
 
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 3)):                     # (with --graph: step 1 eager, step 2 captures, step 3.. replay)
         tr.step(x, tgt)
     barrier()
     sampler = ClockSampler(local_rank)
@@ -589,7 +590,8 @@ def run_train(args, rank, world, local_rank):
         "config": {"workload": workload_name(args, world), "batch_per_gpu": B, "global_batch": B * world, "embed": E, "joints": V,
                    "mode": "train", "dropout": 0.1, "optimizer": "Adam lr 0.01 wd 1e-4 (environment/utils.py:53-57)",
                    "parallelism": f"data-parallel x{world}, local BatchNorm statistics, one all-reduce of {4 * n_params} bytes per step",
-                   "l2_policy": "L2 flushed between steps (192 MB memset, outside the events)"},
+                   "l2_policy": "L2 flushed between steps (192 MB memset, outside the events)",
+                   "cuda_graph": bool(tr.use_cuda_graph)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (x.numel() + tgt.numel()) * 4, "d2h_bytes_per_step": 25 * 8,
                 "ms_per_step": ms_e2e / args.steps, "api": "Trainer.step on pinned host inputs + loss read-back", "checksum": float(res_pin.sum())},
         "gpu_launches": launches * world * args.steps,
@@ -622,6 +624,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"],
                     help="bf16: cistgcn_forward_bf16 (bf16 activation storage + single-term bf16 FPN tensor-core operands)")
+    ap.add_argument("--no-graph", action="store_true", help="train mode: launch every layer kernel from the host instead of "
+                    "replaying the captured CUDA graph of forward + loss + backward")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline timing (N=1 only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

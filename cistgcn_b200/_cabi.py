@@ -119,7 +119,8 @@ def bind_train(L: ctypes.CDLL) -> ctypes.CDLL:
         "cistgcn_prelu_bwd": [_p, _p, _p, _p, _p, _p, i64, i32, i32, i32, _p],
         "cistgcn_act_fwd": [_p, _p, i64, i32, _p],
         "cistgcn_act_bwd": [_p, _p, _p, i64, i32, _p],
-        "cistgcn_dropout": [_p, _p, i64, f32, u64, _p],
+        "cistgcn_dropout": [_p, _p, i64, f32, u64, _p, _p],
+        "cistgcn_counter_bump": [_p, _p],
         "cistgcn_copy4d": [_p, ctypes.POINTER(i64), _p, ctypes.POINTER(i64), ctypes.POINTER(i64), i32, _p],
         "cistgcn_axpby": [f32, _p, f32, _p, i64, _p],
         "cistgcn_gcn_fwd": [_p, _p, _p, i64, i32, i32, i32, i32, i32, _p],

@@ -405,14 +405,20 @@ CG_DEV unsigned long long mix64(unsigned long long z) {       // splitmix64 fina
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);
 }
-__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float p, unsigned long long seed) {
+// `step` (optional, device memory): a per-step counter mixed into the seed, so that a captured CUDA graph of the training
+// step draws fresh masks on every replay without a host-side argument change
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float p, unsigned long long seed,
+                               const unsigned long long* __restrict__ step) {
   const float keep_scale = 1.f / (1.f - p);
+  if (step) seed ^= mix64(*step * 0xD1342543DE82EF95ull + 1ull);
   for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
     const unsigned long long h = mix64(seed ^ mix64((unsigned long long)i));
     const float u = (float)(h >> 40) * (1.f / 16777216.f);
     y[i] = u >= p ? x[i] * keep_scale : 0.f;
   }
 }
+
+__global__ void counter_bump_kernel(unsigned long long* c) { if (threadIdx.x == 0 && blockIdx.x == 0) *c += 1ull; }
 
 // ------------------------------------------------------------------------------------------------ strided copy / flat axpby
 struct Copy4 { long long ds[4], ss[4], sz[4]; };
@@ -935,11 +941,17 @@ int cistgcn_act_bwd(const float* y, const float* dy, float* dx, int64_t n, int32
   CG_LAUNCH(act_bwd_kernel, grid_1d(n), NT, 0, stream, y, dy, dx, (long long)n, kind);
   return launched("act_bwd_kernel");
 }
-int cistgcn_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, void* stream) {
+int cistgcn_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, const uint64_t* step, void* stream) {
   if (!x || !y || n < 0 || !(p >= 0.f && p < 1.f)) return fail_train(-1, "dropout: bad arguments");
   if (n == 0) return 0;
-  CG_LAUNCH(dropout_kernel, grid_1d(n), NT, 0, stream, x, y, (long long)n, p, (unsigned long long)seed);
+  CG_LAUNCH(dropout_kernel, grid_1d(n), NT, 0, stream, x, y, (long long)n, p, (unsigned long long)seed,
+            reinterpret_cast<const unsigned long long*>(step));
   return launched("dropout_kernel");
+}
+int cistgcn_counter_bump(uint64_t* counter, void* stream) {
+  if (!counter) return fail_train(-1, "counter_bump: bad arguments");
+  CG_LAUNCH(counter_bump_kernel, 1, 32, 0, stream, reinterpret_cast<unsigned long long*>(counter));
+  return launched("counter_bump_kernel");
 }
 
 int cistgcn_copy4d(float* dst, const int64_t dst_strides[4], const float* src, const int64_t src_strides[4],

@@ -113,6 +113,7 @@ class DiffGraph:
         self._drop_counter = 0
         self.grads: Dict[str, torch.Tensor] = {}
         self.launches = 0
+        self._step_dev: Optional[torch.Tensor] = None      # device-side step counter mixed into every dropout seed (graph replays)
         self.grad_target: Optional[torch.Tensor] = None    # flat buffer the parameter gradients are written into (default: flat.grad)
         self._scratch: Optional[torch.Tensor] = None       # partial sums of the reductions (one stream: reused by every launch)
 
@@ -267,16 +268,17 @@ class DiffGraph:
         if not self.training or p <= 0.0:
             return x
         self._drop_counter += 1
-        seed = (self.seed * 0x9E3779B1 + self._drop_counter) & 0xFFFFFFFFFFFFFFFF
+        seed = (self.seed * 0x9E3779B1 + self._drop_counter) & 0xFFFFFFFFFFFFFFFF      # per layer; the step enters on the device
         y = Var(torch.empty_like(x.t))
         st = self._stream(x.t)
-        self._ck(self.lib.cistgcn_dropout(x.t.data_ptr(), y.t.data_ptr(), x.t.numel(), _f(p), ctypes.c_uint64(seed), st), "dropout")
+        step = self._step_dev.data_ptr() if self._step_dev is not None else None
+        self._ck(self.lib.cistgcn_dropout(x.t.data_ptr(), y.t.data_ptr(), x.t.numel(), _f(p), ctypes.c_uint64(seed), step, st), "dropout")
 
         def bwd():
             if y.g is None:
                 return
             dx = torch.empty_like(x.t)
-            self._ck(self.lib.cistgcn_dropout(y.g.data_ptr(), dx.data_ptr(), x.t.numel(), _f(p), ctypes.c_uint64(seed), st), "dropout")
+            self._ck(self.lib.cistgcn_dropout(y.g.data_ptr(), dx.data_ptr(), x.t.numel(), _f(p), ctypes.c_uint64(seed), step, st), "dropout")
             self.acc(x, dx)
         self.tape.append(bwd)
         return y
@@ -630,8 +632,12 @@ class DiffGraph:
         self.training = bool(training)
         self.param_grads = bool(training) if param_grads is None else bool(param_grads)
         self._drop_counter = 0
-        self.seed = (self.seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
         self.launches = 0
+        if self.training and self.dropout_p > 0.0:
+            # fresh masks every forward: a device-side counter (bumped by a kernel, so a captured graph advances it too)
+            if self._step_dev is None or self._step_dev.device != x.device:
+                self._step_dev = torch.zeros(1, device=x.device, dtype=torch.int64)
+            self._ck(self.lib.cistgcn_counter_bump(self._step_dev.data_ptr(), self._stream(x)), "counter_bump")
         B, T, V, To = x.shape[0], m.n_input, m.n_joints, m.n_output
         xv = Var(x.contiguous(), needs=input_grad)
         self._x = xv
@@ -699,7 +705,8 @@ class Trainer:
     data-parallel over the ranks of ``torch.distributed`` (local BatchNorm statistics like the reference, ONE all-reduce of
     the flat gradient buffer per step, identical Adam on every replica)."""
 
-    def __init__(self, model, lr: float = 0.01, weight_decay: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, lib=None):
+    def __init__(self, model, lr: float = 0.01, weight_decay: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, lib=None,
+                 cuda_graph: bool = False):
         self.model = model
         self.flat = FlatParams(model)
         self.graph = DiffGraph(model, self.flat, lib)
@@ -709,6 +716,45 @@ class Trainer:
         self.v = torch.zeros_like(self.flat.flat)
         self.step_count = 0
         self.allreduce_ms = None
+        self.use_cuda_graph = bool(cuda_graph)
+        self._cg = None                                    # (torch.cuda.CUDAGraph, static x, static target, static sums, launches)
+        self._eager_steps = 0
+
+    def _fwd_bwd(self, x, target):
+        g = self.graph
+        pred = g.forward(x, training=True)
+        sums, dpred = g.mpjpe_loss(pred, target)
+        g.backward(dpred)
+        return sums
+
+    def _fwd_bwd_graphed(self, x, target):
+        """The ~1 900 launches of forward + loss + backward as ONE CUDA graph (train_h36m.yaml's batch of 128 is launch-bound:
+        19 us of host work per launch against 2-3 us of kernel).  The first step runs eagerly (it also serves as the warm-up
+        the capture needs), the second is captured and replayed, later ones are replays.  Inputs are copied into static
+        buffers; dropout masks change per replay through the device-side step counter; the gradient buffer, the running
+        statistics and num_batches_tracked are written in place by the graph's kernels."""
+        if self._cg is not None and (self._cg[1].shape != x.shape or self._cg[1].device != x.device):
+            self._cg, self._eager_steps = None, 0          # new batch shape: capture again
+        if self._cg is None:
+            if self._eager_steps < 1:
+                self._eager_steps += 1
+                return self._fwd_bwd(x, target)
+            sx, st = torch.empty_like(x), torch.empty_like(target)
+            sx.copy_(x)
+            st.copy_(target)
+            torch.cuda.synchronize(x.device)
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg):
+                ssums = self._fwd_bwd(sx, st)
+            self._cg = (cg, sx, st, ssums, self.graph.launches)
+            cg.replay()
+            return ssums.clone()
+        cg, sx, st, ssums, launches = self._cg
+        sx.copy_(x, non_blocking=True)
+        st.copy_(target, non_blocking=True)
+        cg.replay()
+        self.graph.launches = launches
+        return ssums.clone()
 
     def step(self, x: torch.Tensor, target: torch.Tensor, group=None, timing=None):
         """One step; returns the per-frame error sums of this rank's batch (float64 (output_n,), on the device):
@@ -716,9 +762,7 @@ class Trainer:
         import torch.distributed as dist
         g = self.graph
         self.model.train()
-        pred = g.forward(x, training=True)
-        sums, dpred = g.mpjpe_loss(pred, target)
-        g.backward(dpred)
+        sums = self._fwd_bwd_graphed(x, target) if (self.use_cuda_graph and x.is_cuda) else self._fwd_bwd(x, target)
         world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         if timing is not None:
             timing[0].record()

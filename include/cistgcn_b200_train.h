@@ -65,9 +65,11 @@ int cistgcn_prelu_bwd(const float* x, const float* dy, const float* slope, float
 int cistgcn_act_fwd(const float* x, float* y, int64_t n, int32_t kind, void* stream);
 int cistgcn_act_bwd(const float* y, const float* dy, float* dx, int64_t n, int32_t kind, void* stream);
 
-/* nn.Dropout(p): y = x * keep(seed, i) / (1 - p), keep from a counter-based hash of (seed, element index); the same call
- * with dy in place of x is the backward. */
-int cistgcn_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, void* stream);
+/* nn.Dropout(p): y = x * keep(seed, i) / (1 - p), keep from a counter-based hash of (seed, *step, element index); the same
+ * call with dy in place of x is the backward.  `step` (device memory, may be NULL) is a per-step counter read by the
+ * kernel: a captured CUDA graph of the training step draws fresh masks on every replay.  cistgcn_counter_bump adds 1. */
+int cistgcn_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, const uint64_t* step, void* stream);
+int cistgcn_counter_bump(uint64_t* counter, void* stream);
 
 /* dst[i0,i1,i2,i3] (=|+=) src[i0,i1,i2,i3] with arbitrary element strides on both sides: permute, cat / split (channel
  * slices), broadcast (source stride 0), residual adds. */
