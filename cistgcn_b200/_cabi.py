@@ -45,6 +45,7 @@ EXPORTS = _declared_exports()
 FLAG_FPN_FP32 = DEFINES["CISTGCN_FLAG_FPN_FP32"]
 FLAG_DSTD_FUSED = DEFINES["CISTGCN_FLAG_DSTD_FUSED"]
 FLAG_DSTD_TC = DEFINES["CISTGCN_FLAG_DSTD_TC"]
+FLAG_DSTD_MIX_FFMA = DEFINES["CISTGCN_FLAG_DSTD_MIX_FFMA"]
 PROFILE_KINDS = DEFINES["CISTGCN_PROFILE_KINDS"]
 
 

@@ -173,6 +173,7 @@ struct SplitPlan {
   cg::AdjArgs j;
   cg::MixArgs m;
   int mix_nt, mix_tm, ne;
+  bool mix_mma;                                               // stage 3 on 3xTF32 mma.sync (dstd_mix_mma.cuh)
   size_t red_floats, wg_floats, adjs_floats, adjt_floats;     // scratch per sample
 };
 
@@ -181,7 +182,7 @@ bool shape_has_split_kernels(int T, int V) {
 }
 
 // Fills the three argument blocks' plans; false if the shape / widths are outside what the split kernels tile.
-bool split_plan(const int32_t* desc, SplitPlan& sp) {
+bool split_plan(const int32_t* desc, SplitPlan& sp, uint32_t flags = 0) {
   const int T = desc[CB_T], V = desc[CB_V], Co = desc[CB_CO], Ch = desc[CB_CH], Cg = desc[CB_CG];
   const bool interp = desc[CB_INTERP] != 0;
   if (!shape_has_split_kernels(T, V)) return false;
@@ -199,7 +200,13 @@ bool split_plan(const int32_t* desc, SplitPlan& sp) {
   const int ng = ((TV / tn) + 31) / 32;
   auto fits = [&](int nt, int tm) { return ((Co + tm - 1) / tm) * ng <= (tm == 8 ? 1 : 2) * (nt / 32); };
   sp.mix_nt = 0;
-  if (cg::mix_plan(sp.m, 256, cg::DSTD_SMEM_NARROW_BYTES / 4)) {
+  sp.mix_mma = false;
+  // tensor-core channel mixes: the input blocks (T = 10) from 16 channels up -- below that a 16-row MMA tile is mostly
+  // padding and the FFMA loops are already short
+  if (!(flags & CISTGCN_FLAG_DSTD_MIX_FFMA) && T == 10 && (desc[CB_CI] >= 16 || Co >= 16) &&
+      cg::mix_mma_plan(sp.m, cg::DSTD_SMEM_NARROW_BYTES / 4)) {
+    sp.mix_mma = true; sp.mix_nt = 256; sp.mix_tm = 0;
+  } else if (cg::mix_plan(sp.m, 256, cg::DSTD_SMEM_NARROW_BYTES / 4)) {
     if (Co > 16 && fits(256, 8)) { sp.mix_nt = 256; sp.mix_tm = 8; }
     else if (fits(256, 4)) { sp.mix_nt = 256; sp.mix_tm = 4; }
   }
@@ -224,7 +231,13 @@ size_t split_scratch_floats(const SplitPlan& sp, long long batch, bool with_adj)
 
 bool use_split(const int32_t* desc, uint32_t flags, SplitPlan& sp) {
   if (flags & (CISTGCN_FLAG_DSTD_FUSED | CISTGCN_FLAG_DSTD_TC)) return false;
-  return split_plan(desc, sp);
+  return split_plan(desc, sp, flags);
+}
+
+int launch_mix_mma_shape(int T, int V, const cg::MixArgs& m, void* stream) {
+  if (T == 10 && V == 22) return cg::launch_mix_mma_10_22(m, stream);
+  if (T == 10 && V == 18) return cg::launch_mix_mma_10_18(m, stream);
+  return -1;
 }
 
 int launch_dstd_split(SplitPlan& sp, const float* weights, const float* in, float* out, long long batch,
@@ -254,7 +267,8 @@ int launch_dstd_split(SplitPlan& sp, const float* weights, const float* in, floa
     { ProfScope prof(KIND_ADJ, stream); e = cg::launch_adj_##TT##_##VV(sp.j, stream); } \
     if (e) return dstd_done(e, "dstd_adj_kernel"); \
     { ProfScope prof(KIND_MIX, stream); \
-      e = sp.mix_nt == 512 ? cg::launch_mix_##TT##_##VV##_512_8(sp.m, stream) \
+      e = sp.mix_mma ? launch_mix_mma_shape(TT, VV, sp.m, stream) \
+          : sp.mix_nt == 512 ? cg::launch_mix_##TT##_##VV##_512_8(sp.m, stream) \
           : (sp.mix_tm == 8 ? cg::launch_mix_##TT##_##VV##_256_8(sp.m, stream) : cg::launch_mix_##TT##_##VV##_256_4(sp.m, stream)); } \
     return dstd_done(e, "dstd_mix_kernel"); \
   }

@@ -4,6 +4,7 @@
 #pragma once
 #include "dstd_adj.cuh"
 #include "dstd_mix.cuh"
+#include "dstd_mix_mma.cuh"
 #include "dstd_reduce.cuh"
 #include "host_util.h"
 
@@ -21,5 +22,7 @@ CG_DECL_SPLIT(10, 18)
 CG_DECL_SPLIT(22, 25)
 CG_DECL_SPLIT(18, 25)
 #undef CG_DECL_SPLIT
+int launch_mix_mma_10_22(const MixArgs& a, void* stream);
+int launch_mix_mma_10_18(const MixArgs& a, void* stream);
 
 }  // namespace cg

@@ -48,6 +48,8 @@ extern "C" {
 #define CISTGCN_FLAG_DSTD_FUSED 2  /* DSTD-GC blocks on the round-1 fused one-CTA-per-sample kernel (csrc/dstd_block.cuh) instead
                                       of the three-stage reduce / adjacency / mix kernels */
 #define CISTGCN_FLAG_DSTD_TC    4  /* with DSTD_FUSED: channel mixes as tcgen05 MMAs where the shared-memory plan fits */
+#define CISTGCN_FLAG_DSTD_MIX_FFMA 8  /* three-stage path: channel mixes of stage 3 on the FP32-FMA tile loops (csrc/dstd_mix.cuh)
+                                        instead of 3xTF32 mma.sync (csrc/dstd_mix_mma.cuh, the default where Ci, Co <= 32) */
 
 /* ---- one DSTD-GC block (CISTGCN.py:273-390).  *_S/_T pairs: index +0 = dsgn ("space" domain,
  *      TxT adjacency per joint), +1 = tsgn ("time" domain, VxV adjacency per frame). ---------- */

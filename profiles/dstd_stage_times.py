@@ -36,10 +36,10 @@ for which, i in blocks:
     raw = d[F["CB_IN_MODE"]] == 1
     x = torch.randn(B, 10, V, 3, device=dev) if raw else torch.randn(B, ci * T * Vb, device=dev)
     out = torch.empty(B, co * T * Vb, device=dev)
-    for flags, label in ((0, "split"), (_cabi.FLAG_DSTD_FUSED, "fused")):
+    for flags, label in ((0, "split"), (_cabi.FLAG_DSTD_MIX_FFMA, "split, FFMA mix"), (_cabi.FLAG_DSTD_FUSED, "fused")):
         if only and flags:
             continue
-        nb = L.cistgcn_dstd_block_workspace_bytes(d, B) if flags == 0 else 0
+        nb = L.cistgcn_dstd_block_workspace_bytes(d, B) if not (flags & _cabi.FLAG_DSTD_FUSED) else 0
         ws = torch.empty(max(nb, 256), dtype=torch.uint8, device=dev)
         def run():
             rc = L.cistgcn_dstd_block_f32(d, pk.blob.data_ptr(), x.data_ptr(), out.data_ptr(), B, None,

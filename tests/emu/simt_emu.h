@@ -43,6 +43,7 @@ namespace simt_emu {
 struct WarpCtx {
   std::barrier<> bar{32};
   uint64_t slot[32];
+  float mma_a[32][4], mma_b[32][2];      // fragment exchange of the emulated mma.sync
 };
 struct BlockCtx {
   std::unique_ptr<std::barrier<>> bar;
@@ -53,6 +54,37 @@ inline thread_local BlockCtx* tl_block = nullptr;
 inline thread_local WarpCtx* tl_warp = nullptr;
 inline thread_local int tl_lane = 0;
 inline void* dyn_smem() { return tl_block->smem; }
+
+// mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 with the PTX fragment layouts: lane = 4 g + q holds
+//   a0 = A[g][q], a1 = A[g+8][q], a2 = A[g][q+4], a3 = A[g+8][q+4];  b0 = B[q][g], b1 = B[q+4][g];
+//   c0 = C[g][2q], c1 = C[g][2q+1], c2 = C[g+8][2q], c3 = C[g+8][2q+1].
+// Operands are truncated to TF32 (the tensor core ignores the 13 low mantissa bits); products and sums in fp32.
+inline float tf32_trunc(float x) {
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  u &= 0xFFFFE000u;
+  std::memcpy(&x, &u, 4);
+  return x;
+}
+inline void mma_m16n8k8(float (&c)[4], const float (&a)[4], const float (&b)[2]) {
+  WarpCtx* w = tl_warp;
+  const int lane = tl_lane, g = lane >> 2, q = lane & 3;
+  for (int i = 0; i < 4; ++i) w->mma_a[lane][i] = tf32_trunc(a[i]);
+  for (int i = 0; i < 2; ++i) w->mma_b[lane][i] = tf32_trunc(b[i]);
+  w->bar.arrive_and_wait();
+  for (int h = 0; h < 2; ++h)
+    for (int j = 0; j < 2; ++j) {
+      const int n = 2 * q + j;
+      float s = c[2 * h + j];
+      for (int k = 0; k < 8; ++k) {
+        const float av = w->mma_a[g * 4 + (k & 3)][h + ((k >> 2) << 1)];
+        const float bv = w->mma_b[n * 4 + (k & 3)][k >> 2];
+        s += av * bv;
+      }
+      c[2 * h + j] = s;
+    }
+  w->bar.arrive_and_wait();
+}
 }  // namespace simt_emu
 
 inline thread_local uint3_emu threadIdx{0, 0, 0};

@@ -163,3 +163,31 @@ def test_dstd_tensor_core_channel_mixes_match_oracle(E, V, weights, scale):
     assert not torch.equal(tc, fused)                    # the tensor-core path really ran
     assert (tc - fm).abs().max().item() <= 0.5 * G.tol(ref)
     assert (fused - fm).abs().max().item() <= 0.5 * G.tol(ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("E,V", [(32, 22), (32, 18), (16, 22), (16, 18)])
+@pytest.mark.parametrize("weights,scale", [("W1", "unit"), ("W2", "unit"), ("W1", "mm")])
+def test_dstd_mix_mma_channel_mixes_match_oracle(E, V, weights, scale):
+    """Default three-stage path: the channel mixes of stage 3 (tcn of both domains, domain residual conv, compressor,
+    block residual conv) run as 3xTF32 mma.sync (csrc/dstd_mix_mma.cuh).  The forward must stay inside the fp32
+    tolerance, agree with the FP32-FMA tile loops (CISTGCN_FLAG_DSTD_MIX_FFMA) to a fraction of it, and differ from them
+    in the last bits (i.e. the tensor-core kernel really ran)."""
+    import _golden as G
+    from cistgcn_b200 import _cabi
+    dev = "cuda:0"
+    model, sd, cfg = M.build(E, V, weights)
+    x, _ = O.synth_inputs(48, cfg, scale=scale)
+    with torch.no_grad():
+        ref = O.forward(sd, cfg, x)
+    model = model.to(dev)
+    model.kernel_flags = 0
+    mma = model(x.to(dev))[0].cpu()
+    model.kernel_flags = _cabi.FLAG_DSTD_MIX_FFMA
+    ffma = model(x.to(dev))[0].cpu()
+    model.kernel_flags = 0
+    assert torch.isfinite(mma).all()
+    assert (mma - ref).abs().max().item() <= G.tol(ref)
+    assert (ffma - ref).abs().max().item() <= G.tol(ref)
+    assert not torch.equal(mma, ffma)
+    assert (mma - ffma).abs().max().item() <= 0.5 * G.tol(ref)

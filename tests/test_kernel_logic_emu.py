@@ -38,3 +38,32 @@ def test_emulated_e32_block_widths():
     pred, sums, _ = _emu.forward(sd, model.geometry(), x, tgt, want_taps=False)
     assert (pred - ref).abs().max().item() <= G.tol(ref)
     assert abs((sums.sum() / (3 * 25 * 18)).item() - O.mpjpe(ref, tgt).item()) <= 1e-3 * max(1, ref.abs().max().item() / 4)
+
+
+@pytest.mark.parametrize("E,V", [(32, 22), (16, 18)])
+def test_emulated_mix_mma_matches_ffma_and_oracle(E, V):
+    """Stage 3 of the DSTD-GC path on 3xTF32 mma.sync (csrc/dstd_mix_mma.cuh; the emulator executes the PTX fragment
+    layouts of m16n8k8 with TF32-truncated operands) against the FP32-FMA tile loops and the oracle."""
+    from cistgcn_b200 import _cabi
+    from cistgcn_b200.pack import F, pack_state_dict
+    model, sd, cfg = M.build(E, V, "W2")
+    x, _ = O.synth_inputs(2, cfg)
+    with torch.no_grad():
+        ref = O.forward(sd, cfg, x)
+    L = _emu.lib()
+    geom = model.geometry()
+    outs = []
+    for flags in (0, _cabi.FLAG_DSTD_MIX_FFMA):
+        pk = pack_state_dict(sd, geom, "cpu")
+        pk.plan_c[F["CP_FLAGS"]] = flags
+        pred = torch.empty(2, geom.output_n, geom.joints, 3)
+        ws = torch.empty(L.cistgcn_workspace_bytes(pk.plan_c, 2), dtype=torch.uint8)
+        rc = L.cistgcn_forward_f32(pk.plan_c, len(pk.plan), pk.blob.data_ptr(), x.contiguous().data_ptr(), pred.data_ptr(),
+                                   None, None, ws.data_ptr(), ws.numel(), 2, None, None)
+        _cabi.check(rc, "cistgcn_forward_f32[emu]", L)
+        outs.append(pred)
+    mma, ffma = outs
+    assert (mma - ref).abs().max().item() <= G.tol(ref)
+    assert (ffma - ref).abs().max().item() <= G.tol(ref)
+    assert not torch.equal(mma, ffma)
+    assert (mma - ffma).abs().max().item() <= 0.5 * G.tol(ref)
