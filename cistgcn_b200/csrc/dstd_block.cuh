@@ -702,9 +702,9 @@ CG_DEV void gate_mlp_tail(int g, const float* m0w, const float* m0b, float m0a, 
 // adjacency products (ConvTemporalGraphical, CISTGCN.py:110,117,123)
 // ---------------------------------------------------------------------------------------------
 // "space" domain: g1[c][q][v] = sum_t XN[c][t][v] * Adj_s[v][t][q], Adj_s held as adjT[(t*T+q)*VP + v], VP = V|1.
-template <int T, int V, int TC, int NT>
+template <int T, int V, int TC, int NT, int LD = T * V>
 CG_DEV void gcn_space(const float* XN, const float* adjT, float* G, int C) {
-  constexpr int TV = T * V, VP = V | 1;
+  constexpr int TV = LD, VP = V | 1;                       // TV: row stride of the XN / G tiles
   const int nct = (C + TC - 1) / TC;
   for (int item = threadIdx.x; item < nct * V; item += NT) {
     const int v = item % V, c0 = (item / V) * TC;
@@ -735,9 +735,9 @@ CG_DEV void gcn_space(const float* XN, const float* adjT, float* G, int C) {
 }
 
 // "time" domain: g2[c][t][w] = sum_v XN[c][t][v] * Adj_t[t][v][w]  (natural layout).
-template <int T, int V, int TC, int NT>
+template <int T, int V, int TC, int NT, int LD = T * V>
 CG_DEV void gcn_time(const float* XN, const float* adj, float* G, int C) {
-  constexpr int TV = T * V, VVP = (V * V + 3) & ~3;        // padded row stride of the frame-axis adjacency
+  constexpr int TV = LD, VVP = (V * V + 3) & ~3;           // TV: row stride of the XN / G tiles; VVP: padded row stride of the frame-axis adjacency
   constexpr int TW = (V % 11 == 0) ? 11 : ((V % 9 == 0) ? 9 : ((V % 5 == 0) ? 5 : 1));
   constexpr int NWG = V / TW;
   const int nct = (C + TC - 1) / TC;

@@ -11,8 +11,8 @@
 // accumulator fragment is already in the registers of the lanes that run the epilogue, and every warp owns whole
 // columns (positions) of the tile, so the in-place epilogue and the compressor that consumes it need no block barrier.
 //
-// fp32 accuracy on the TF32 pipe (3xTF32): x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi) (x - hi is exact in
-// fp32); w likewise; x*w ~= lo*hi + hi*lo + hi*hi, accumulated in fp32, smallest terms first.  hi*hi is exact (11 x 11
+// fp32 accuracy on the TF32 pipe (3xTF32): x = hi + lo with hi = rna_tf32(x), lo = x - hi (exact in fp32, truncated to
+// TF32 by the MMA); w likewise; x*w ~= lo*hi + hi*lo + hi*hi, accumulated in fp32, smallest terms first.  hi*hi is exact (11 x 11
 // significant bits), the dropped lo*lo term is < 2^-22 |x w|: 3e-7 relative per product against 6e-8 for an FFMA.
 // mma.sync.m16n8k8.tf32 issues at 0.47 / clk / SM on B200 (profiles/mma_sync_r1.log) = 159 effective MAC / clk / SM
 // after the 3x, against the ~50 the FFMA tile loops of dstd_mix.cuh sustain (FMA pipe 39 % active, issue 60 %).
@@ -33,6 +33,10 @@ namespace cg {
 
 constexpr int MMA_NT = 256;                 // threads per CTA (two CTAs per SM)
 
+// Row stride of the two activation tiles: = 8 (mod 32), so that the B-fragment loads (lane = 4 g + q reads row q, column
+// g: bank 8 q + g) and the float2 accesses of the epilogues (rows g, columns 2 q) are bank-conflict free; with the
+// natural stride T*V = 220 = 28 (mod 32) both were 2-way conflicted (ncu: half of their wavefronts excessive).
+__host__ __device__ constexpr int mma_ld(int TV) { return ((TV + 31) / 32) * 32 + 8; }
 __host__ __device__ inline int mma_mt(int M) { return (M + 15) / 16; }
 __host__ __device__ inline int mma_ks(int K) { return (K + 7) / 8; }
 
@@ -57,14 +61,16 @@ inline bool mix_mma_plan(MixArgs& a, int max_smem_floats) {
   z[CB_SE1_WT] = Co * pad8i(Hs); z[CB_SE2_WT] = Hs * Cop;
   if (has_res) { z[CB_RS_WT] = 2 * MT * KSi * 128; z[CB_RS_B] = Co; }
   for (int f = 0; f < CB_COUNT; ++f) z[f] = pad4i(z[f]);
+  const int LD = mma_ld(TV);
   a.o_xn = 0;
-  a.o_a = pad4i(Ci * TV);
-  // the B fragments of the last (partial) column tile read up to 7 floats past a tile's last row: the region behind
-  // each tile is initialised shared memory (the next tile / the adjacency), and those columns are never stored
-  a.o_adj = a.o_a + pad4i(cmax * TV);
-  const int adj = imax(pad4i(T * T * (V | 1)), T * pad4i(V * V));
+  a.o_a = pad4i(Ci * LD);
+  // (the B fragments of the last, partial column tile read the row padding behind column T*V: column-local garbage in
+  // accumulator columns that are never stored)
+  a.o_adj = a.o_a + pad4i(cmax * LD);
+  // adjacency region; the squeeze partial sums [NW][32] alias its start (both adjacencies are dead by then)
+  const int adj = imax(imax(pad4i(T * T * (V | 1)), T * pad4i(V * V)), (MMA_NT / 32) * 32);
   a.o_sm = a.o_adj + adj;
-  int cur = a.o_sm + pad4i(2 * Co) + 2 * pad4i(Co) + pad4i(Hs) + (MMA_NT / 32) * 32;
+  int cur = a.o_sm + pad4i(2 * Co) + 2 * pad4i(Co) + pad4i(Hs);
   for (int f = 0; f < CB_COUNT; ++f)
     if (z[f]) { a.res[f] = cur; cur += z[f]; }
   a.smem_floats = cur;
@@ -72,27 +78,22 @@ inline bool mix_mma_plan(MixArgs& a, int max_smem_floats) {
 }
 
 // ---- TF32 helpers ------------------------------------------------------------------------------------------------
-CG_DEV float tf32_rna(float x) {            // nearest TF32 (ties away), returned as an fp32 value with 13 zero low bits
-#ifdef CISTGCN_EMU
-  unsigned u = f32_bits(x);
-  u = (u + 0x1000u) & 0xFFFFE000u;
-  return bits_f32(u);
-#else
-  unsigned u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-#endif
-}
+// Nearest TF32 (ties away from zero), returned as an fp32 value with 13 zero low bits.  Integer rounding on the bit
+// pattern: ptxas expands cvt.rna.tf32.f32 on sm_100a into the same add / mask plus an Inf / NaN guard (5 instructions);
+// the tiles hold finite activations and weights, so the guard is dropped.
+CG_DEV float tf32_rna(float x) { return bits_f32((f32_bits(x) + 0x1000u) & 0xFFFFE000u); }
+// x = hi + lo: hi = rna_tf32(x); lo = x - hi is exact in fp32 and is handed to the tensor core as it is -- the MMA reads
+// only its upper 19 bits, i.e. truncates it to TF32 (error < 2^-10 |lo| <= 2^-21 |x|, the size of the dropped lo*lo term).
 CG_DEV void tf32_split(float x, float& hi, float& lo) {
   hi = tf32_rna(x);
-  lo = tf32_rna(x - hi);
+  lo = x - hi;
 }
 // c += a (16x8, row) * b (8x8, col); fragments as in PTX mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32
 CG_DEV void mma_tf32(float (&c)[4], const float (&a)[4], const float (&b)[2]) {
 #ifdef CISTGCN_EMU
   simt_emu::mma_m16n8k8(c, a, b);
 #else
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
                  "r"(__float_as_uint(b[0])), "r"(__float_as_uint(b[1])));
@@ -133,20 +134,33 @@ CG_DEV void mma_gemm(float (&acc)[NTP][MT][4], const float* wfrag, int KS, int K
     const int k0 = ks * 8 + q, k1 = k0 + 4;
     const float* x0 = X + (k0 < K ? k0 : 0) * LD + g;      // rows beyond K meet zero weights; keep the address inside the tile
     const float* x1 = X + (k1 < K ? k1 : 0) * LD + g;
+    // splits of all (<= NTP) tiles first, then the MMAs term by term: the three products of one accumulator are issued
+    // NTP * MT MMAs apart, so that a warp does not sit out the MMA latency between them
+    float bh[NTP][2], bl[NTP][2];
 #pragma unroll
     for (int nt = 0; nt < NTP; ++nt) {
-      if (nt < ntiles) {
-        float bh[2], bl[2];
-        tf32_split(x0[nbase + nt * NSTRIDE], bh[0], bl[0]);
-        tf32_split(x1[nbase + nt * NSTRIDE], bh[1], bl[1]);
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          mma_tf32(acc[nt][mt], al[mt], bh);
-          mma_tf32(acc[nt][mt], ah[mt], bl);
-          mma_tf32(acc[nt][mt], ah[mt], bh);
-        }
-      }
+      const int col = nt < ntiles ? nbase + nt * NSTRIDE : nbase;      // inactive tile: a valid address, no MMA
+      tf32_split(x0[col], bh[nt][0], bl[nt][0]);
+      tf32_split(x1[col], bh[nt][1], bl[nt][1]);
     }
+#pragma unroll
+    for (int nt = 0; nt < NTP; ++nt)
+      if (nt == 0 || nt < ntiles) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) mma_tf32(acc[nt][mt], al[mt], bh[nt]);
+      }
+#pragma unroll
+    for (int nt = 0; nt < NTP; ++nt)
+      if (nt == 0 || nt < ntiles) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) mma_tf32(acc[nt][mt], ah[mt], bl[nt]);
+      }
+#pragma unroll
+    for (int nt = 0; nt < NTP; ++nt)
+      if (nt == 0 || nt < ntiles) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) mma_tf32(acc[nt][mt], ah[mt], bh[nt]);
+      }
   }
 }
 
@@ -164,8 +178,9 @@ __global__ void __launch_bounds__(MMA_NT, 2) dstd_mix_mma_kernel(const MixArgs a
   constexpr int NT = MMA_NT, NW = NT / 32;
   constexpr int TV = T * V, TT = T * T, VV = V * V, VP = V | 1;
   constexpr int VVP = (VV + 3) & ~3;
-  constexpr int NTILES = (TV + 7) / 8, NTW = (NTILES + NW - 1) / NW;
-  constexpr int NTP = 2;                               // column tiles per pass of the in-place phases (register budget)
+  constexpr int NTP = 2;
+  constexpr int NTILES = (TV + 7) / 8, NTW = (((NTILES + NW - 1) / NW + NTP - 1) / NTP) * NTP;    // per warp, padded to whole passes                               // column tiles per pass of the in-place phases (register budget)
+  constexpr int LD = mma_ld(TV);                       // row stride of the XN / A tiles
   static_assert(TV % 2 == 0, "column pairs");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
   const int* d = a.d;
@@ -183,7 +198,7 @@ __global__ void __launch_bounds__(MMA_NT, 2) dstd_mix_mma_kernel(const MixArgs a
   float* semean = p;  p += pad4i(Co);
   float* gate = p;    p += pad4i(Co);
   float* hid = p;     p += pad4i(Hs);
-  float* separt = p;                                   // [NW][32] squeeze partial sums (row m of the warp's columns)
+  float* separt = ADJ;                                 // [NW][32] squeeze partial sums (row m of the warp's columns); the adjacencies are dead by then
   auto P = [&](int f) -> const float* { return smem + a.res[f]; };
   auto Pw = [&](int f) -> float* { return smem + a.res[f]; };
 
@@ -246,7 +261,7 @@ __global__ void __launch_bounds__(MMA_NT, 2) dstd_mix_mma_kernel(const MixArgs a
         }
         f[9] = sqrtf(sp);
 #pragma unroll
-        for (int c = 0; c < 10; ++c) XN[c * TV + n] = fmaf(gs[c], f[c], gb[c]);
+        for (int c = 0; c < 10; ++c) XN[c * LD + n] = fmaf(gs[c], f[c], gb[c]);
       }
     } else {
       const bool ibf = a.in_bf16 != 0;
@@ -258,12 +273,12 @@ __global__ void __launch_bounds__(MMA_NT, 2) dstd_mix_mma_kernel(const MixArgs a
           float4 v4 = ld_act4(a.in, sbase_ + (size_t)i * 4, ibf);
           const float g0 = gs[c], b0 = gb[c];
           v4.x = fmaf(g0, v4.x, b0); v4.y = fmaf(g0, v4.y, b0); v4.z = fmaf(g0, v4.z, b0); v4.w = fmaf(g0, v4.w, b0);
-          reinterpret_cast<float4*>(XN)[i] = v4;
+          *reinterpret_cast<float4*>(XN + c * LD + (i * 4 - c * TV)) = v4;
         }
       } else {
         for (int i = tid; i < Ci * TV; i += NT) {
           const int c = i / TV, n = i - c * TV, t = n / V, v = n - t * V;
-          XN[i] = fmaf(gs[c], ld_act(a.in, sbase_ + (size_t)c * sc + t * st + v * sv, ibf), gb[c]);
+          XN[c * LD + n] = fmaf(gs[c], ld_act(a.in, sbase_ + (size_t)c * sc + t * st + v * sv, ibf), gb[c]);
         }
       }
     }
@@ -276,13 +291,13 @@ __global__ void __launch_bounds__(MMA_NT, 2) dstd_mix_mma_kernel(const MixArgs a
     for (int L = 0; L < 2; ++L) {
       // ---------------- g = XN x Adj  (:110, :117, :123) -> A   (FP32 FMA: per-sample operands on both sides)
       if (L == 0) {
-        if (Ci >= 4 && ((Ci + 3) / 4) * V >= NT) gcn_space<T, V, 4, NT>(XN, ADJ, A, Ci);
-        else if (Ci >= 2) gcn_space<T, V, 2, NT>(XN, ADJ, A, Ci);
-        else gcn_space<T, V, 1, NT>(XN, ADJ, A, Ci);
+        if (Ci >= 4 && ((Ci + 3) / 4) * V >= NT) gcn_space<T, V, 4, NT, LD>(XN, ADJ, A, Ci);
+        else if (Ci >= 2) gcn_space<T, V, 2, NT, LD>(XN, ADJ, A, Ci);
+        else gcn_space<T, V, 1, NT, LD>(XN, ADJ, A, Ci);
       } else {
-        if (Ci >= 4 && ((Ci + 3) / 4) * T * 2 >= NT) gcn_time<T, V, 4, NT>(XN, ADJ, A, Ci);
-        else if (Ci >= 2) gcn_time<T, V, 2, NT>(XN, ADJ, A, Ci);
-        else gcn_time<T, V, 1, NT>(XN, ADJ, A, Ci);
+        if (Ci >= 4 && ((Ci + 3) / 4) * T * 2 >= NT) gcn_time<T, V, 4, NT, LD>(XN, ADJ, A, Ci);
+        else if (Ci >= 2) gcn_time<T, V, 2, NT, LD>(XN, ADJ, A, Ci);
+        else gcn_time<T, V, 1, NT, LD>(XN, ADJ, A, Ci);
       }
       __syncthreads();
       if (L == 0) {
@@ -312,8 +327,8 @@ __global__ void __launch_bounds__(MMA_NT, 2) dstd_mix_mma_kernel(const MixArgs a
           float acc[NTP][MT][4];
           zero_acc(acc);
           const int nb0 = warp * 8 + i0 * NS;
-          mma_gemm<NTP, MT, TV, NS>(acc, wt, KSi, Ci, A, nb0, nti);
-          if (has_res) mma_gemm<NTP, MT, TV, NS>(acc, wt + 2 * MT * KSi * 128, KSi, Ci, XN, nb0, nti);   // domain layer's residual conv
+          mma_gemm<NTP, MT, LD, NS>(acc, wt, KSi, Ci, A, nb0, nti);
+          if (has_res) mma_gemm<NTP, MT, LD, NS>(acc, wt + 2 * MT * KSi * 128, KSi, Ci, XN, nb0, nti);   // domain layer's residual conv
           __syncwarp();                                // every lane of the warp is done reading the columns it overwrites
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
@@ -327,9 +342,9 @@ __global__ void __launch_bounds__(MMA_NT, 2) dstd_mix_mma_kernel(const MixArgs a
                   const int n = nb0 + i * NS + 2 * q;
                   if (i < nti && n < TV) {
                     float x0 = acc[i][mt][2 * h] + tbm, x1 = acc[i][mt][2 * h + 1] + tbm;
-                    if (!has_res) { const float2 r = *reinterpret_cast<const float2*>(XN + m * TV + n); x0 += r.x; x1 += r.y; }
+                    if (!has_res) { const float2 r = *reinterpret_cast<const float2*>(XN + m * LD + n); x0 += r.x; x1 += r.y; }
                     x0 = prelu(x0, ta); x1 = prelu(x1, ta);
-                    *reinterpret_cast<float2*>(A + m * TV + n) = make_float2(prelu(fmaf(sc, x0, pbm), pa), prelu(fmaf(sc, x1, pbm), pa));
+                    *reinterpret_cast<float2*>(A + m * LD + n) = make_float2(prelu(fmaf(sc, x0, pbm), pa), prelu(fmaf(sc, x1, pbm), pa));
                   }
                 }
               }
@@ -339,7 +354,12 @@ __global__ void __launch_bounds__(MMA_NT, 2) dstd_mix_mma_kernel(const MixArgs a
         __syncwarp();
       }
       // ---------------- compressor, this domain's half of the K range  (:305)
-      mma_gemm<NTW, MT, TV, NS>(cacc, P(CB_CP_WT) + L * 2 * MT * KSo * 128, KSo, Co, A, warp * 8, ntiles_w);
+#pragma unroll
+      for (int i0 = 0; i0 < NTW; i0 += NTP) {
+        if (i0 < ntiles_w)
+          mma_gemm<NTP, MT, LD, NS>(*reinterpret_cast<float (*)[NTP][MT][4]>(&cacc[i0][0][0]), P(CB_CP_WT) + L * 2 * MT * KSo * 128, KSo, Co,
+                                    A, warp * 8 + i0 * NS, ntiles_w - i0);
+      }
       if (L == 0) cp_async_wait_all();
       __syncthreads();            // everyone is done reading u_L (and Adj_t has landed)
     }
@@ -358,7 +378,7 @@ __global__ void __launch_bounds__(MMA_NT, 2) dstd_mix_mma_kernel(const MixArgs a
             if (i < ntiles_w && n < TV) {
               const float v0 = prelu(cacc[i][mt][2 * h] + bias, ca), v1 = prelu(cacc[i][mt][2 * h + 1] + bias, ca);
               rs += v0 + v1;
-              *reinterpret_cast<float2*>(A + m * TV + n) = make_float2(v0, v1);
+              *reinterpret_cast<float2*>(A + m * LD + n) = make_float2(v0, v1);
             }
           }
         }
@@ -404,7 +424,7 @@ __global__ void __launch_bounds__(MMA_NT, 2) dstd_mix_mma_kernel(const MixArgs a
           float acc[NTP][MT][4];
           zero_acc(acc);
           const int nb0 = warp * 8 + i0 * NS;
-          mma_gemm<NTP, MT, TV, NS>(acc, P(CB_RS_WT), KSi, Ci, XN, nb0, nti);
+          mma_gemm<NTP, MT, LD, NS>(acc, P(CB_RS_WT), KSi, Ci, XN, nb0, nti);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
@@ -416,7 +436,7 @@ __global__ void __launch_bounds__(MMA_NT, 2) dstd_mix_mma_kernel(const MixArgs a
                 for (int i = 0; i < NTP; ++i) {
                   const int n = nb0 + i * NS + 2 * q;
                   if (i < nti && n < TV) {
-                    const float2 c2 = *reinterpret_cast<const float2*>(A + m * TV + n);
+                    const float2 c2 = *reinterpret_cast<const float2*>(A + m * LD + n);
                     const float v0 = fmaf(c2.x, gm, acc[i][mt][2 * h] + bias), v1 = fmaf(c2.y, gm, acc[i][mt][2 * h + 1] + bias);
                     if (contiguous) {
                       st_act(a.out, obase + (size_t)m * TV + n, v0, obf);
@@ -435,16 +455,17 @@ __global__ void __launch_bounds__(MMA_NT, 2) dstd_mix_mma_kernel(const MixArgs a
         }
       } else if (contiguous) {
         for (int i = tid; i < Co * TV / 4; i += NT) {
-          const float gm = gate[(i * 4) / TV];
-          const float4 c4 = reinterpret_cast<const float4*>(A)[i];
-          const float4 x4 = reinterpret_cast<const float4*>(XN)[i];
+          const int m = (i * 4) / TV, n = i * 4 - m * TV;
+          const float gm = gate[m];
+          const float4 c4 = *reinterpret_cast<const float4*>(A + m * LD + n);
+          const float4 x4 = *reinterpret_cast<const float4*>(XN + m * LD + n);
           st_act4(a.out, obase + (size_t)i * 4,
                   make_float4(fmaf(c4.x, gm, x4.x), fmaf(c4.y, gm, x4.y), fmaf(c4.z, gm, x4.z), fmaf(c4.w, gm, x4.w)), obf);
         }
       } else {
         for (int i = tid; i < Co * TV; i += NT) {
           const int m = i / TV, n = i - m * TV, t = n / V, v = n - t * V;
-          st_act(a.out, obase + (size_t)m * sc + t * st + v * sv, fmaf(A[i], gate[m], XN[i]), obf);
+          st_act(a.out, obase + (size_t)m * sc + t * st + v * sv, fmaf(A[m * LD + n], gate[m], XN[m * LD + n]), obf);
         }
       }
     }
