@@ -174,6 +174,7 @@ struct SplitPlan {
   cg::MixArgs m;
   int mix_nt, mix_tm, ne;
   bool mix_mma;                                               // stage 3 on 3xTF32 mma.sync (dstd_mix_mma.cuh)
+  bool mix_narrow;                                            // stage 3 warp-per-sample, streamed adjacencies (dstd_mix_narrow.cuh)
   size_t red_floats, wg_floats, adjs_floats, adjt_floats;     // scratch per sample
 };
 
@@ -191,7 +192,7 @@ bool split_plan(const int32_t* desc, SplitPlan& sp, uint32_t flags = 0) {
   memcpy(sp.m.d, desc, sizeof(sp.m.d));
   const int cap = kMaxSmemBytes / 4;
   if (!cg::reduce_plan(sp.r, cap)) return false;
-  if (!cg::adj_plan(sp.j, cap)) return false;
+  if (!cg::adj_plan(sp.j, cap, !(flags & CISTGCN_FLAG_DSTD_ADJ_FFMA))) return false;
   sp.ne = interp ? (4 * Ch + 31) / 32 : 1;
   if (sp.ne < 1) sp.ne = 1;
   // mix stage: two 256-thread CTAs per SM when the plan fits half an SM, else one 512-thread CTA
@@ -201,6 +202,11 @@ bool split_plan(const int32_t* desc, SplitPlan& sp, uint32_t flags = 0) {
   auto fits = [&](int nt, int tm) { return ((Co + tm - 1) / tm) * ng <= (tm == 8 ? 1 : 2) * (nt / 32); };
   sp.mix_nt = 0;
   sp.mix_mma = false;
+  sp.mix_narrow = false;
+  // 3 -> 3 blocks (the output block): one warp per sample, adjacencies streamed from global memory
+  if (!(flags & CISTGCN_FLAG_DSTD_MIX_FFMA) && V == 25 && (T == 22 || T == 18) && cg::mix_narrow_plan<3>(sp.m, cap)) {
+    sp.mix_narrow = true; sp.mix_nt = 32 * sp.m.nwarps; sp.mix_tm = 0;
+  } else
   // tensor-core channel mixes: the input blocks (T = 10) from 16 channels up -- below that a 16-row MMA tile is mostly
   // padding and the FFMA loops are already short
   if (!(flags & CISTGCN_FLAG_DSTD_MIX_FFMA) && T == 10 && (desc[CB_CI] >= 16 || Co >= 16) &&
@@ -232,6 +238,12 @@ size_t split_scratch_floats(const SplitPlan& sp, long long batch, bool with_adj)
 bool use_split(const int32_t* desc, uint32_t flags, SplitPlan& sp) {
   if (flags & (CISTGCN_FLAG_DSTD_FUSED | CISTGCN_FLAG_DSTD_TC)) return false;
   return split_plan(desc, sp, flags);
+}
+
+int launch_mix_narrow_shape(int T, int V, const cg::MixArgs& m, void* stream) {
+  if (T == 22 && V == 25) return cg::launch_mix_narrow_22_25(m, stream);
+  if (T == 18 && V == 25) return cg::launch_mix_narrow_18_25(m, stream);
+  return -1;
 }
 
 int launch_mix_mma_shape(int T, int V, const cg::MixArgs& m, void* stream) {
@@ -267,7 +279,8 @@ int launch_dstd_split(SplitPlan& sp, const float* weights, const float* in, floa
     { ProfScope prof(KIND_ADJ, stream); e = cg::launch_adj_##TT##_##VV(sp.j, stream); } \
     if (e) return dstd_done(e, "dstd_adj_kernel"); \
     { ProfScope prof(KIND_MIX, stream); \
-      e = sp.mix_mma ? launch_mix_mma_shape(TT, VV, sp.m, stream) \
+      e = sp.mix_narrow ? launch_mix_narrow_shape(TT, VV, sp.m, stream) \
+          : sp.mix_mma ? launch_mix_mma_shape(TT, VV, sp.m, stream) \
           : sp.mix_nt == 512 ? cg::launch_mix_##TT##_##VV##_512_8(sp.m, stream) \
           : (sp.mix_tm == 8 ? cg::launch_mix_##TT##_##VV##_256_8(sp.m, stream) : cg::launch_mix_##TT##_##VV##_256_4(sp.m, stream)); } \
     return dstd_done(e, "dstd_mix_kernel"); \

@@ -32,6 +32,7 @@ struct MixArgs {
   int in_bf16, out_bf16;   // activation tensors stored as bf16 (cistgcn_forward_bf16); strides stay in elements
   int batch;
   int o_xn, o_a, o_adj, o_sm, smem_floats;
+  int nwarps, o_warp, warp_floats;      // warp-per-sample variant (dstd_mix_narrow.cuh)
 };
 
 // Host: shared-memory plan for `nt` threads.  All matrices must be resident.

@@ -77,28 +77,7 @@ inline bool mix_mma_plan(MixArgs& a, int max_smem_floats) {
   return cur <= max_smem_floats;
 }
 
-// ---- TF32 helpers ------------------------------------------------------------------------------------------------
-// Nearest TF32 (ties away from zero), returned as an fp32 value with 13 zero low bits.  Integer rounding on the bit
-// pattern: ptxas expands cvt.rna.tf32.f32 on sm_100a into the same add / mask plus an Inf / NaN guard (5 instructions);
-// the tiles hold finite activations and weights, so the guard is dropped.
-CG_DEV float tf32_rna(float x) { return bits_f32((f32_bits(x) + 0x1000u) & 0xFFFFE000u); }
-// x = hi + lo: hi = rna_tf32(x); lo = x - hi is exact in fp32 and is handed to the tensor core as it is -- the MMA reads
-// only its upper 19 bits, i.e. truncates it to TF32 (error < 2^-10 |lo| <= 2^-21 |x|, the size of the dropped lo*lo term).
-CG_DEV void tf32_split(float x, float& hi, float& lo) {
-  hi = tf32_rna(x);
-  lo = x - hi;
-}
-// c += a (16x8, row) * b (8x8, col); fragments as in PTX mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32
-CG_DEV void mma_tf32(float (&c)[4], const float (&a)[4], const float (&b)[2]) {
-#ifdef CISTGCN_EMU
-  simt_emu::mma_m16n8k8(c, a, b);
-#else
-  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
-                 "r"(__float_as_uint(b[0])), "r"(__float_as_uint(b[1])));
-#endif
-}
+// (TF32 helpers tf32_rna / tf32_split / mma_tf32: simt.h)
 
 // Fragment-ordered hi | lo images of a k-major weight matrix W[k][Mp] (rows k0 .. k0+K-1 of it), M x K, zero padded:
 // dst[0 .. n) = hi, dst[n .. 2n) = lo, n = MT * KS * 128.

@@ -29,16 +29,17 @@ __host__ __device__ inline int rmin(int a, int b) { return a < b ? a : b; }
 __host__ __device__ inline int rmax(int a, int b) { return a > b ? a : b; }
 constexpr int RED_MAX_WARPS = 12;      // 384 threads: up to 168 registers per thread
 
-// Float offsets inside one sample's `red` record.
+// Float offsets inside one sample's `red` record.  The Map2Adj maps come first and the gate inputs (statistics, hidden
+// maps) last: stage 2 is done with the latter before it needs room for dim_seq / dim_space, which alias them.
 struct RedLayout {
   int stats, h1, h1g, tc, jc, total;
   __host__ __device__ RedLayout(int T, int V, int Cg, int Ch, bool interp) {
-    stats = 0;
-    h1 = rpad4(2 + 2 * T);
-    h1g = rpad4(Cg * V);                 // each gate's hidden map starts 16-byte aligned (stage 2 reads it with LDS.128)
-    tc = h1 + 2 * h1g;
+    tc = 0;
     jc = tc + (interp ? rpad4(2 * Ch * V) : 0);
-    total = jc + (interp ? rpad4(2 * Ch * T) : 0);
+    stats = jc + (interp ? rpad4(2 * Ch * T) : 0);
+    h1 = stats + rpad4(2 + 2 * T);
+    h1g = rpad4(Cg * V);                 // each gate's hidden map starts 16-byte aligned (stage 2 reads it with LDS.128)
+    total = h1 + 2 * h1g;
   }
 };
 

@@ -5,6 +5,7 @@
 #include "dstd_adj.cuh"
 #include "dstd_mix.cuh"
 #include "dstd_mix_mma.cuh"
+#include "dstd_mix_narrow.cuh"
 #include "dstd_reduce.cuh"
 #include "host_util.h"
 
@@ -24,5 +25,7 @@ CG_DECL_SPLIT(18, 25)
 #undef CG_DECL_SPLIT
 int launch_mix_mma_10_22(const MixArgs& a, void* stream);
 int launch_mix_mma_10_18(const MixArgs& a, void* stream);
+int launch_mix_narrow_22_25(const MixArgs& a, void* stream);
+int launch_mix_narrow_18_25(const MixArgs& a, void* stream);
 
 }  // namespace cg

@@ -49,7 +49,10 @@ extern "C" {
                                       of the three-stage reduce / adjacency / mix kernels */
 #define CISTGCN_FLAG_DSTD_TC    4  /* with DSTD_FUSED: channel mixes as tcgen05 MMAs where the shared-memory plan fits */
 #define CISTGCN_FLAG_DSTD_MIX_FFMA 8  /* three-stage path: channel mixes of stage 3 on the FP32-FMA tile loops (csrc/dstd_mix.cuh)
-                                        instead of 3xTF32 mma.sync (csrc/dstd_mix_mma.cuh, the default where Ci, Co <= 32) */
+                                        instead of 3xTF32 mma.sync (csrc/dstd_mix_mma.cuh, the default where Ci, Co <= 32) and of the
+                                        warp-per-sample streaming kernel of the 3 -> 3 output block (csrc/dstd_mix_narrow.cuh) */
+#define CISTGCN_FLAG_DSTD_ADJ_FFMA 16 /* three-stage path: Map2Adj expansor of stage 2 on the FP32-FMA column loops instead of
+                                        the chained 3xTF32 mma.sync GEMMs (csrc/dstd_adj.cuh, the default) */
 
 /* ---- one DSTD-GC block (CISTGCN.py:273-390).  *_S/_T pairs: index +0 = dsgn ("space" domain,
  *      TxT adjacency per joint), +1 = tsgn ("time" domain, VxV adjacency per frame). ---------- */

@@ -67,3 +67,71 @@ def test_emulated_mix_mma_matches_ffma_and_oracle(E, V):
     assert (ffma - ref).abs().max().item() <= G.tol(ref)
     assert not torch.equal(mma, ffma)
     assert (mma - ffma).abs().max().item() <= 0.5 * G.tol(ref)
+
+
+@pytest.mark.parametrize("E,V", [(8, 22), (16, 18)])
+def test_emulated_adj_mma_expansor_matches_ffma_and_oracle(E, V):
+    """Stage 2's Map2Adj expansor as chained 3xTF32 mma.sync GEMMs (csrc/dstd_adj.cuh: layer 1's accumulator fragment is
+    layer 2's A fragment) against the FP32-FMA column loops (CISTGCN_FLAG_DSTD_ADJ_FFMA): the sample-specific
+    adjacencies of every block (N = V, T and, in the output block, 25 and V) and the prediction."""
+    from cistgcn_b200 import _cabi
+    from cistgcn_b200.pack import F, pack_state_dict
+    model, sd, cfg = M.build(E, V, "W2")
+    x, _ = O.synth_inputs(2, cfg)
+    with torch.no_grad():
+        ref = O.forward(sd, cfg, x)
+    L = _emu.lib()
+    geom = model.geometry()
+    outs = []
+    for flags in (0, _cabi.FLAG_DSTD_ADJ_FFMA):
+        pk = pack_state_dict(sd, geom, "cpu")
+        pk.plan_c[F["CP_FLAGS"]] = flags
+        pred = torch.empty(2, geom.output_n, geom.joints, 3)
+        ws = torch.empty(L.cistgcn_workspace_bytes(pk.plan_c, 2), dtype=torch.uint8)
+        taps_struct, holders = _cabi.make_taps(geom, 2, "cpu")
+        rc = L.cistgcn_forward_f32(pk.plan_c, len(pk.plan), pk.blob.data_ptr(), x.contiguous().data_ptr(), pred.data_ptr(),
+                                   None, None, ws.data_ptr(), ws.numel(), 2, taps_struct, None)
+        _cabi.check(rc, "cistgcn_forward_f32[emu]", L)
+        outs.append((pred, holders))
+    (mma, tm), (ffma, tf) = outs
+    assert (mma - ref).abs().max().item() <= G.tol(ref)
+    assert (ffma - ref).abs().max().item() <= G.tol(ref)
+    n_adj = 0
+    for k in tm:
+        if not k.endswith("Adj"):
+            continue
+        n_adj += 1
+        a, b = tm[k], tf[k]
+        assert not torch.equal(a, b), k
+        assert (a - b).abs().max().item() <= 2e-5 * max(1e-30, b.abs().max().item()), k
+    assert n_adj >= 4
+
+
+@pytest.mark.parametrize("E,V,interp", [(8, 22, True), (8, 18, True), (8, 22, False)])
+def test_emulated_narrow_mix_matches_tile_kernel_and_oracle(E, V, interp):
+    """Stage 3 of the 3 -> 3 output block: the warp-per-sample kernel that streams the adjacencies from global memory
+    (csrc/dstd_mix_narrow.cuh) against the tile kernel (CISTGCN_FLAG_DSTD_MIX_FFMA) and the oracle, with sample-specific
+    and with static adjacencies."""
+    from cistgcn_b200 import _cabi
+    from cistgcn_b200.pack import F, pack_state_dict
+    model, sd, cfg = M.build(E, V, "W2", interp=interp)
+    x, _ = O.synth_inputs(3, cfg)
+    with torch.no_grad():
+        ref = O.forward(sd, cfg, x, interpretable_in=[interp] * 5, interpretable_out=[interp])
+    L = _emu.lib()
+    geom = model.geometry()
+    outs = []
+    for flags in (0, _cabi.FLAG_DSTD_MIX_FFMA):
+        pk = pack_state_dict(sd, geom, "cpu")
+        pk.plan_c[F["CP_FLAGS"]] = flags
+        pred = torch.empty(3, geom.output_n, geom.joints, 3)
+        ws = torch.empty(L.cistgcn_workspace_bytes(pk.plan_c, 3), dtype=torch.uint8)
+        rc = L.cistgcn_forward_f32(pk.plan_c, len(pk.plan), pk.blob.data_ptr(), x.contiguous().data_ptr(), pred.data_ptr(),
+                                   None, None, ws.data_ptr(), ws.numel(), 3, None, None)
+        _cabi.check(rc, "cistgcn_forward_f32[emu]", L)
+        outs.append(pred)
+    narrow, tile = outs
+    assert (narrow - ref).abs().max().item() <= G.tol(ref)
+    assert (tile - ref).abs().max().item() <= G.tol(ref)
+    assert not torch.equal(narrow, tile)
+    assert (narrow - tile).abs().max().item() <= 0.5 * G.tol(ref)
