@@ -47,6 +47,7 @@ FLAG_DSTD_FUSED = DEFINES["CISTGCN_FLAG_DSTD_FUSED"]
 FLAG_DSTD_TC = DEFINES["CISTGCN_FLAG_DSTD_TC"]
 FLAG_DSTD_MIX_FFMA = DEFINES["CISTGCN_FLAG_DSTD_MIX_FFMA"]
 FLAG_DSTD_ADJ_FFMA = DEFINES["CISTGCN_FLAG_DSTD_ADJ_FFMA"]
+FLAG_DSTD_REDUCE_FFMA = DEFINES["CISTGCN_FLAG_DSTD_REDUCE_FFMA"]
 PROFILE_KINDS = DEFINES["CISTGCN_PROFILE_KINDS"]
 
 

@@ -207,6 +207,18 @@ __global__ void __launch_bounds__(MMA_NT, 2) dstd_mix_mma_kernel(const MixArgs a
   const int ntiles_w = (NTILES - warp + NW - 1) / NW;
 
   for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
+    // the next sample's operands (input tile, both adjacencies) start their way from HBM into L2 now: the loads at the top
+    // of the next iteration are exposed (two samples in flight per SM), an L2 hit halves what they wait for
+    if (b + (int)gridDim.x < a.batch) {
+      const size_t bn = (size_t)b + gridDim.x;
+      if (d[CB_IN_MODE] == 1) prefetch_l2_range<NT>(a.in + bn * d[CB_IN_SB], (size_t)TV * 3 * 4);
+      else if (d[CB_IN_SV] == 1 && d[CB_IN_ST] == V && d[CB_IN_SC] == TV)
+        prefetch_l2_range<NT>(reinterpret_cast<const char*>(a.in) + bn * d[CB_IN_SB] * (a.in_bf16 ? 2 : 4), (size_t)Ci * TV * (a.in_bf16 ? 2 : 4));
+      if (interp) {
+        prefetch_l2_range<NT>(a.adj_s + bn * V * TT, (size_t)V * TT * 4);
+        prefetch_l2_range<NT>(a.adj_t + bn * T * VV, (size_t)T * VV * 4);
+      }
+    }
     // ---------------- load + global_norm (:375); block 0 builds the 10 features (:568-577); gates; Adj_s
     if (tid < 2 * Co) wg[tid] = __ldg(a.wg + (size_t)b * 2 * Co + tid);
     {

@@ -28,6 +28,13 @@ __host__ __device__ inline int rpad32(int n) { return (n + 31) & ~31; }
 __host__ __device__ inline int rmin(int a, int b) { return a < b ? a : b; }
 __host__ __device__ inline int rmax(int a, int b) { return a > b ? a : b; }
 constexpr int RED_MAX_WARPS = 12;      // 384 threads: up to 168 registers per thread
+// Row stride of the per-warp map buffer.  FFMA variant: 4 x odd, so that lanes = rows conflict only 4-way on the transposing
+// store; tensor-core variant: = 8 (mod 16), so that the accumulator-fragment stores (8 rows x 4 column pairs per
+// half-warp) are conflict free.
+__host__ __device__ constexpr int red_as(int V, bool mma) {
+  const int xs = (V + 3) & ~3;
+  return mma ? ((xs + 7) / 16) * 16 + 8 : ((xs % 8 == 4) ? xs : xs + 4);
+}
 
 // Float offsets inside one sample's `red` record.  The Map2Adj maps come first and the gate inputs (statistics, hidden
 // maps) last: stage 2 is done with the latter before it needs room for dim_seq / dim_space, which alias them.
@@ -55,12 +62,14 @@ struct ReduceArgs {
   int o_gn_s, o_gn_b, o_a0_b, o_a0_a, o_g0_b, o_g0_a, o_tc3_b, o_jc3_b;   // resident vectors
   int mp_e, mp_g, mp_c;             // row lengths: pad32(4Ch), pad32(2Cg), pad32(2Ch)
   int o_warp, warp_floats, smem_floats;
+  int mma;                          // stacked 1x1 convolutions (Map2Adj entry maps + gate conv) on 3xTF32 mma.sync
+  int ks, mte, mtg;                 // MMA variant: k steps of 8 input channels, 16-row tiles of the entry maps / the gate conv
 };
 
 // Host: shared-memory plan.  Returns false when the shape is outside this kernel's register tiling
 // (4*Ch <= 32*NE_MAX, 2*Cg <= 32, Ci <= 32) or the resident weights leave no room for >= 4 warps.
 constexpr int RED_NE_MAX = 2;
-inline bool reduce_plan(ReduceArgs& a, int max_smem_floats) {
+inline bool reduce_plan(ReduceArgs& a, int max_smem_floats, bool mma = true) {
   const int* d = a.d;
   const int Ci = d[CB_CI], T = d[CB_T], V = d[CB_V], Ch = d[CB_CH], Cg = d[CB_CG];
   const bool interp = d[CB_INTERP] != 0;
@@ -68,15 +77,19 @@ inline bool reduce_plan(ReduceArgs& a, int max_smem_floats) {
   a.mp_e = rpad32(4 * Ch); a.mp_g = rpad32(2 * Cg); a.mp_c = rpad32(2 * Ch);
   int cur = 0;
   auto take = [&](int n) { const int o = cur; cur += rpad4(n); return o; };
-  a.o_g0 = take(Ci * T * a.mp_g);
-  a.o_a0 = interp ? take(Ci * a.mp_e) : 0;
+  // tensor-core variant: the input blocks (T = 10) from 16 input channels up (K = 10 padded to 16 loses to the FFMA loops); the matrices of the stacked 1x1 convolutions
+  // are then held as fragment-ordered images [row tile][k step][lane][4]
+  a.mma = mma && T == 10 && Ci >= 16;
+  a.ks = (Ci + 7) / 8; a.mte = interp ? (4 * Ch + 15) / 16 : 0; a.mtg = (2 * Cg + 15) / 16;
+  a.o_g0 = take(a.mma ? T * a.mtg * a.ks * 128 : Ci * T * a.mp_g);
+  a.o_a0 = interp ? take(a.mma ? a.mte * a.ks * 128 : Ci * a.mp_e) : 0;
   a.o_tc3 = interp ? take(Ch * T * a.mp_c) : 0;
-  a.o_jc3 = interp ? take(Ch * V * a.mp_c) : 0;
+  a.o_jc3 = interp ? take(Ch * (a.mma ? rpad4(V) : V) * a.mp_c) : 0;     // tensor-core variant: [c'][v / 4][lane][4], v padded
   a.o_gn_s = take(Ci); a.o_gn_b = take(Ci);
   a.o_g0_b = take(a.mp_g); a.o_g0_a = take(2);
   a.o_a0_b = take(a.mp_e); a.o_a0_a = take(4);
   a.o_tc3_b = take(a.mp_c); a.o_jc3_b = take(a.mp_c);
-  const int XS = rpad4(V), XT = V | 1, AS = (rpad4(V) % 8 == 4) ? rpad4(V) : rpad4(V) + 4;
+  const int XS = rpad4(V), XT = V | 1, AS = red_as(V, a.mma != 0);
   const int rows_ag = interp ? 4 * Ch : 0;
   int region = Ci * XT;                                           // transposed slab copy (stats) aliases the map buffer
   if (rows_ag * AS > region) region = rows_ag * AS;
@@ -92,12 +105,57 @@ inline bool reduce_plan(ReduceArgs& a, int max_smem_floats) {
   return true;
 }
 
-template <int T, int V, int NE>
+// c[mt][nt] += W (fragment image of an fp32 matrix, split into hi + lo here) * slab (B fragments, already split), k step ks.
+// Row tiles go in pairs and the three products of one accumulator are issued 2 * NTL MMAs apart, smallest terms first.
+template <int MT, int NTL>
+CG_DEV void reduce_mma_rows(float (&acc)[MT][NTL][4], const float* frag, int mt_used, int KS, int ks,
+                            const float (&bh)[NTL][2], const float (&bl)[NTL][2]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int mp = 0; mp < MT; mp += 2) {
+    if (mp < mt_used) {
+      const bool two = mp + 1 < MT && mp + 1 < mt_used;
+      float ah[2][4], al[2][4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int mt = (u == 0 || two) ? mp + u : mp;
+        const float4 w4 = *reinterpret_cast<const float4*>(frag + ((mt * KS + ks) * 32 + lane) * 4);
+        tf32_split(w4.x, ah[u][0], al[u][0]); tf32_split(w4.y, ah[u][1], al[u][1]);
+        tf32_split(w4.z, ah[u][2], al[u][2]); tf32_split(w4.w, ah[u][3], al[u][3]);
+      }
+#pragma unroll
+      for (int term = 0; term < 3; ++term)
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (mp + u < MT && (u == 0 || two)) {
+#pragma unroll
+            for (int nt = 0; nt < NTL; ++nt) {
+              if (term == 0) mma_tf32(acc[mp + u][nt], al[u], bh[nt]);
+              else if (term == 1) mma_tf32(acc[mp + u][nt], ah[u], bl[nt]);
+              else mma_tf32(acc[mp + u][nt], ah[u], bh[nt]);
+            }
+          }
+    }
+  }
+}
+
+// Fragment-ordered image of an M x K matrix given as src(m, k): dst[((mt * KS + ks) * 32 + lane) * 4 + j] with
+// m = 16 mt + lane / 4 + 8 (j & 1), k = 8 ks + lane % 4 + 4 (j >> 1); zero outside the matrix.
+template <class SRC>
+CG_DEV void build_reduce_frags(float* dst, int MT, int KS, int M, int K, int nthreads, SRC src) {
+  for (int i = threadIdx.x; i < MT * KS * 128; i += nthreads) {
+    const int j = i & 3, ln = (i >> 2) & 31, tile = i >> 7, ks = tile % KS, mt = tile / KS;
+    const int m = 16 * mt + (ln >> 2) + ((j & 1) ? 8 : 0), k = 8 * ks + (ln & 3) + ((j & 2) ? 4 : 0);
+    dst[i] = (m < M && k < K) ? src(m, k) : 0.f;
+  }
+}
+
+template <int T, int V, int NE, bool MMA = false>
 __global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(const ReduceArgs a) {
   CG_DYN_SMEM(smem);
   constexpr int XS = (V + 3) & ~3;                 // slab row stride (LDS.128 broadcast reads)
   constexpr int XT = V | 1;                        // transposed-use copy: odd stride, lanes = channels read columns
-  constexpr int AS = (XS % 8 == 4) ? XS : XS + 4;  // map rows: 4 x odd, so lanes = rows conflict only 4-way on the transposing store
+  constexpr int AS = red_as(V, MMA);               // map row stride
   constexpr int V4 = XS / 4;
   constexpr int TV = T * V;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nthreads = blockDim.x;
@@ -112,16 +170,39 @@ __global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(cons
     auto cp = [&](int dst, int field, int n) {
       for (int i = threadIdx.x; i < n; i += nthreads) smem[dst + i] = __ldg(W + d[field] + i);
     };
-    cp(a.o_g0, CB_R_G0_WT, Ci * T * a.mp_g);
+    if constexpr (MMA) {
+      const int mpg_ = a.mp_g, mpe_ = a.mp_e;
+      for (int t = 0; t < T; ++t)                    // gate conv (T,1): one image per frame, rows (c*T + t) of the k-major matrix
+        build_reduce_frags(smem + a.o_g0 + t * a.mtg * a.ks * 128, a.mtg, a.ks, 2 * Cg, Ci, nthreads,
+                           [&](int m, int k) { return __ldg(W + d[CB_R_G0_WT] + (size_t)(k * T + t) * mpg_ + m); });
+      if (interp)
+        build_reduce_frags(smem + a.o_a0, a.mte, a.ks, 4 * Ch, Ci, nthreads,
+                           [&](int m, int k) { return __ldg(W + d[CB_R_A0_WT] + (size_t)k * mpe_ + m); });
+    } else {
+      cp(a.o_g0, CB_R_G0_WT, Ci * T * a.mp_g);
+      if (interp) cp(a.o_a0, CB_R_A0_WT, Ci * a.mp_e);
+    }
     cp(a.o_gn_s, CB_GN_S, Ci); cp(a.o_gn_b, CB_GN_B, Ci);
     cp(a.o_g0_b, CB_R_G0_B, a.mp_g); cp(a.o_g0_a, CB_G0_A, 2);
     if (interp) {
-      cp(a.o_a0, CB_R_A0_WT, Ci * a.mp_e);
       cp(a.o_tc3, CB_R_TC3_WT, Ch * T * a.mp_c);
-      cp(a.o_jc3, CB_R_JC3_WT, Ch * V * a.mp_c);
+      if constexpr (MMA) {
+        // joint_compress.3 weights as [c'][v / 4][lane = output][4 joints]: one conflict-free LDS.128 per four FFMAs
+        const int mpc_ = a.mp_c;
+        for (int i = threadIdx.x; i < Ch * XS * mpc_; i += nthreads) {
+          const int e = i & 3, ln = (i >> 2) % mpc_, rest = (i >> 2) / mpc_, v = 4 * (rest % V4) + e, cp_ = rest / V4;
+          smem[a.o_jc3 + i] = v < V ? __ldg(W + d[CB_R_JC3_WT] + (size_t)(cp_ * V + v) * mpc_ + ln) : 0.f;
+        }
+      } else {
+        cp(a.o_jc3, CB_R_JC3_WT, Ch * V * a.mp_c);
+      }
       cp(a.o_a0_b, CB_R_A0_B, a.mp_e); cp(a.o_a0_a, CB_A0_A, 4);
       cp(a.o_tc3_b, CB_R_TC3_B, a.mp_c); cp(a.o_jc3_b, CB_R_JC3_B, a.mp_c);
     }
+  }
+  if constexpr (MMA) {
+    // the padding joints of the map rows meet zero weights in the collapse stage: they must hold finite values
+    for (int i = threadIdx.x; i < a.nwarps * a.warp_floats; i += nthreads) smem[a.o_warp + i] = 0.f;
   }
   __syncthreads();
   const float* gs = smem + a.o_gn_s;
@@ -145,6 +226,21 @@ __global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(cons
     const int m = lane + 32 * j;
     e_b[j] = interp ? smem[a.o_a0_b + m] : 0.f;
     e_a[j] = interp ? smem[a.o_a0_a + rmin(m / rmax(Ch, 1), 3)] : 0.f;
+  }
+
+  // tensor-core variant: fragment geometry (lane = 4 g + q) and the epilogue constants of the rows this lane holds
+  constexpr int NTL = (V + 7) / 8, MTE = 2 * NE;
+  const int g = lane >> 2, q = lane & 3;
+  float me_b[MTE][2], me_a[MTE][2];
+  if constexpr (MMA) {
+#pragma unroll
+    for (int mt = 0; mt < MTE; ++mt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int m = rmin(16 * mt + g + 8 * h, rmax(4 * Ch - 1, 0));
+        me_b[mt][h] = interp ? smem[a.o_a0_b + m] : 0.f;
+        me_a[mt][h] = interp ? smem[a.o_a0_a + rmin(m / rmax(Ch, 1), 3)] : 0.f;
+      }
   }
 
   bool first_sample = true;
@@ -174,6 +270,13 @@ __global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(cons
     float acc_g[V], acc_tc[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) { acc_g[v] = 0.f; acc_tc[v] = 0.f; }
+    float mg[2][NTL][4];                                   // tensor-core variant: gate-conv accumulator fragments
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) mg[mt][nt][e] = 0.f;
 
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
@@ -269,8 +372,35 @@ __global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(cons
         if (lane == 0) { red[RL.stats + 1 + t] = s1 / Ci; red[RL.stats + 2 + T + t] = sqrtf(q2 / (Ci - 1)); }
       }
       __syncwarp();            // the transposed copy is dead: its region becomes the map buffer
-      // ---- stacked 1x1 convolutions over the slab: lanes = output channels, registers = joints
+      // ---- stacked 1x1 convolutions over the slab
       float acc_e[NE][V];
+      float me[MTE][NTL][4];
+      if constexpr (MMA) {
+        // tensor cores: rows = output channels (16 per tile), columns = joints (8 per tile), k = input channels; the slab
+        // rows are split into hi + lo once per k step and shared by the entry maps and the gate conv
+#pragma unroll
+        for (int mt = 0; mt < MTE; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < NTL; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) me[mt][nt][e] = 0.f;
+        const float* fg = wg0 + t * a.mtg * a.ks * 128;
+#pragma unroll 1
+        for (int ks = 0; ks < a.ks; ++ks) {
+          const int k0 = 8 * ks + q, k1 = k0 + 4;
+          const float* x0 = xs + (k0 < Ci ? k0 : 0) * XS + g;       // rows beyond Ci meet zero weights: any finite row
+          const float* x1 = xs + (k1 < Ci ? k1 : 0) * XS + g;
+          float bh[NTL][2], bl[NTL][2];
+#pragma unroll
+          for (int nt = 0; nt < NTL; ++nt) {                         // (columns beyond V: garbage in accumulator columns never stored)
+            tf32_split(x0[8 * nt], bh[nt][0], bl[nt][0]);
+            tf32_split(x1[8 * nt], bh[nt][1], bl[nt][1]);
+          }
+          if (interp) reduce_mma_rows<MTE, NTL>(me, wa0, a.mte, a.ks, ks, bh, bl);
+          reduce_mma_rows<2, NTL>(mg, fg, a.mtg, a.ks, ks, bh, bl);
+        }
+      } else {
+      // FP32 FMA: lanes = output channels, registers = joints
 #pragma unroll
       for (int j = 0; j < NE; ++j)
 #pragma unroll
@@ -303,6 +433,7 @@ __global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(cons
           xr += XS;
         }
       }
+      }
       if (gathered) {
         __syncwarp();            // every lane is done reading the slab: gather the next one (or the next sample's first)
         const int bn = b + gridDim.x * a.nwarps;
@@ -311,13 +442,36 @@ __global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(cons
       }
       if (interp) {
         // ---- BN + PReLU of the entry maps -> ag[m][v]  (:139-140, :147-148)
+        if constexpr (MMA) {
 #pragma unroll
-        for (int j = 0; j < NE; ++j) {
-          const int m = lane + 32 * j;
-          if (m < 4 * Ch) {
-            float* ar = ag + m * AS;
+          for (int mt = 0; mt < MTE; ++mt)
 #pragma unroll
-            for (int v = 0; v < V; ++v) ar[v] = prelu(acc_e[j][v] + e_b[j], e_a[j]);
+            for (int h = 0; h < 2; ++h) {
+              const int m = 16 * mt + g + 8 * h;
+              if (m < 4 * Ch) {
+                float* ar = ag + m * AS + 2 * q;
+#pragma unroll
+                for (int nt = 0; nt < NTL; ++nt) {
+                  const float v0 = prelu(me[mt][nt][2 * h] + me_b[mt][h], me_a[mt][h]);
+                  const float v1 = prelu(me[mt][nt][2 * h + 1] + me_b[mt][h], me_a[mt][h]);
+                  if constexpr (V % 2 == 0) {
+                    if (8 * nt + 2 * q < V) *reinterpret_cast<float2*>(ar + 8 * nt) = make_float2(v0, v1);
+                  } else {
+                    if (8 * nt + 2 * q < V) ar[8 * nt] = v0;
+                    if (8 * nt + 2 * q + 1 < V) ar[8 * nt + 1] = v1;
+                  }
+                }
+              }
+            }
+        } else {
+#pragma unroll
+          for (int j = 0; j < NE; ++j) {
+            const int m = lane + 32 * j;
+            if (m < 4 * Ch) {
+              float* ar = ag + m * AS;
+#pragma unroll
+              for (int v = 0; v < V; ++v) ar[v] = prelu(acc_e[j][v] + e_b[j], e_a[j]);
+            }
           }
         }
         __syncwarp();
@@ -339,6 +493,17 @@ __global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(cons
             const float wtv = wt[cp_ * T * mpc];
 #pragma unroll
             for (int v = 0; v < V; ++v) acc_tc[v] = fmaf(wtv, xa[v], acc_tc[v]);
+            if constexpr (MMA) {
+              const float* wjr = wjc + ((size_t)cp_ * V4 * mpc + lane) * 4;
+              float j0 = 0.f, j1 = 0.f, j2 = 0.f, j3 = 0.f;
+#pragma unroll
+              for (int i = 0; i < V4; ++i) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wjr + (size_t)i * mpc * 4);
+                j0 = fmaf(w4.x, xg[4 * i], j0); j1 = fmaf(w4.y, xg[4 * i + 1], j1);
+                j2 = fmaf(w4.z, xg[4 * i + 2], j2); j3 = fmaf(w4.w, xg[4 * i + 3], j3);
+              }
+              jsum += (j0 + j1) + (j2 + j3);
+            } else {
             const float* wjr = wj + cp_ * V * mpc;
             float j0 = 0.f, j1 = 0.f;
 #pragma unroll
@@ -348,6 +513,7 @@ __global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(cons
             }
             if (V & 1) j0 = fmaf(wjr[(V - 1) * mpc], xg[V - 1], j0);
             jsum += j0 + j1;
+            }
           }
           if (lane < 2 * Ch) red[RL.jc + lane * T + t] = jsum + smem[a.o_jc3_b + lane];
         }
@@ -367,7 +533,23 @@ __global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(cons
       if (lane == 0) { red[RL.stats] = s1 / Ci; red[RL.stats + 1 + T] = sqrtf(q2 / (Ci - 1)); }
     }
     // gate conv (T,1) + BN + PReLU -> h1 (:323-326); staged through shared memory for coalesced stores
-    if (lane < 2 * Cg) {
+    if constexpr (MMA) {
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int m = 16 * mt + g + 8 * h;
+          if (m < 2 * Cg) {
+            const float bb = smem[a.o_g0_b + m], sl = smem[a.o_g0_a + m / Cg];
+            float* ar = ag + m * AS + 2 * q;
+#pragma unroll
+            for (int nt = 0; nt < NTL; ++nt) {
+              if (8 * nt + 2 * q < V) ar[8 * nt] = prelu(mg[mt][nt][2 * h] + bb, sl);
+              if (8 * nt + 2 * q + 1 < V) ar[8 * nt + 1] = prelu(mg[mt][nt][2 * h + 1] + bb, sl);
+            }
+          }
+        }
+    } else if (lane < 2 * Cg) {
       const float bb = smem[a.o_g0_b + lane], sl = smem[a.o_g0_a + lane / Cg];
       float* ar = ag + lane * AS;
 #pragma unroll
@@ -395,7 +577,10 @@ __global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(cons
 
 template <int T, int V, int NE>
 inline int launch_reduce_impl(const ReduceArgs& a, void* stream) {
-  return launch_warp_per_sample(dstd_reduce_kernel<T, V, NE>, a, stream);
+  if constexpr (T == 10) {
+    if (a.mma) return launch_warp_per_sample(dstd_reduce_kernel<T, V, NE, true>, a, stream);
+  }
+  return launch_warp_per_sample(dstd_reduce_kernel<T, V, NE, false>, a, stream);
 }
 
 }  // namespace cg

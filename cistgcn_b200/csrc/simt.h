@@ -158,6 +158,18 @@ CG_DEV void lds_vec(const float* p, float (&w)[N_]) {
   }
 }
 
+// L2 prefetch of `bytes` bytes at p, one 128-byte line per thread and round (NT threads cooperate); a hint, no dependency.
+template <int NT>
+CG_DEV void prefetch_l2_range(const void* p, size_t bytes) {
+#ifndef CISTGCN_EMU
+  const char* c = reinterpret_cast<const char*>(p);
+  for (size_t off = (size_t)threadIdx.x * 128; off < bytes; off += (size_t)NT * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
+#else
+  (void)p; (void)bytes;
+#endif
+}
+
 // ---- TF32 helpers ------------------------------------------------------------------------------------------------
 // Nearest TF32 (ties away from zero), returned as an fp32 value with 13 zero low bits.  Integer rounding on the bit
 // pattern: ptxas expands cvt.rna.tf32.f32 on sm_100a into the same add / mask plus an Inf / NaN guard (5 instructions);

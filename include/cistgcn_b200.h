@@ -53,6 +53,8 @@ extern "C" {
                                         warp-per-sample streaming kernel of the 3 -> 3 output block (csrc/dstd_mix_narrow.cuh) */
 #define CISTGCN_FLAG_DSTD_ADJ_FFMA 16 /* three-stage path: Map2Adj expansor of stage 2 on the FP32-FMA column loops instead of
                                         the chained 3xTF32 mma.sync GEMMs (csrc/dstd_adj.cuh, the default) */
+#define CISTGCN_FLAG_DSTD_REDUCE_FFMA 32 /* three-stage path: stacked 1x1 convolutions of stage 1 (Map2Adj entry maps, gate conv) on
+                                        the FP32-FMA lane-per-channel loops instead of 3xTF32 mma.sync (csrc/dstd_reduce.cuh) */
 
 /* ---- one DSTD-GC block (CISTGCN.py:273-390).  *_S/_T pairs: index +0 = dsgn ("space" domain,
  *      TxT adjacency per joint), +1 = tsgn ("time" domain, VxV adjacency per frame). ---------- */

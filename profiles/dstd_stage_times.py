@@ -36,7 +36,7 @@ for which, i in blocks:
     raw = d[F["CB_IN_MODE"]] == 1
     x = torch.randn(B, 10, V, 3, device=dev) if raw else torch.randn(B, ci * T * Vb, device=dev)
     out = torch.empty(B, co * T * Vb, device=dev)
-    for flags, label in ((0, "split"), (_cabi.FLAG_DSTD_MIX_FFMA | _cabi.FLAG_DSTD_ADJ_FFMA, "split, FFMA mix+adj"), (_cabi.FLAG_DSTD_FUSED, "fused")):
+    for flags, label in ((0, "split"), (_cabi.FLAG_DSTD_MIX_FFMA | _cabi.FLAG_DSTD_ADJ_FFMA | _cabi.FLAG_DSTD_REDUCE_FFMA, "split, all FFMA"), (_cabi.FLAG_DSTD_FUSED, "fused")):
         if only and flags:
             continue
         nb = L.cistgcn_dstd_block_workspace_bytes(d, B) if not (flags & _cabi.FLAG_DSTD_FUSED) else 0

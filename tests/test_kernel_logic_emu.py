@@ -135,3 +135,38 @@ def test_emulated_narrow_mix_matches_tile_kernel_and_oracle(E, V, interp):
     assert (tile - ref).abs().max().item() <= G.tol(ref)
     assert not torch.equal(narrow, tile)
     assert (narrow - tile).abs().max().item() <= 0.5 * G.tol(ref)
+
+
+@pytest.mark.parametrize("E,V,interp", [(32, 22, True), (16, 18, True), (8, 22, True), (16, 22, False)])
+def test_emulated_reduce_mma_matches_ffma_and_oracle(E, V, interp):
+    """Stage 1's stacked 1x1 convolutions (Map2Adj entry maps + the gate conv (T,1)) on 3xTF32 mma.sync
+    (csrc/dstd_reduce.cuh, MMA variant) against the lane-per-channel FFMA loops (CISTGCN_FLAG_DSTD_REDUCE_FFMA): gate
+    vectors w1 / w2, adjacencies and the prediction; two row tiles (E = 32), one (E = 16, 8), K padded (E = 8: first
+    block Ci = 10 -> 16) and blocks without Map2Adj."""
+    from cistgcn_b200 import _cabi
+    from cistgcn_b200.pack import F, pack_state_dict
+    model, sd, cfg = M.build(E, V, "W2", interp=interp)
+    x, _ = O.synth_inputs(2, cfg)
+    with torch.no_grad():
+        ref = O.forward(sd, cfg, x, interpretable_in=[interp] * 5, interpretable_out=[interp])
+    L = _emu.lib()
+    geom = model.geometry()
+    outs = []
+    for flags in (0, _cabi.FLAG_DSTD_REDUCE_FFMA):
+        pk = pack_state_dict(sd, geom, "cpu")
+        pk.plan_c[F["CP_FLAGS"]] = flags
+        pred = torch.empty(2, geom.output_n, geom.joints, 3)
+        ws = torch.empty(L.cistgcn_workspace_bytes(pk.plan_c, 2), dtype=torch.uint8)
+        taps_struct, holders = _cabi.make_taps(geom, 2, "cpu")
+        rc = L.cistgcn_forward_f32(pk.plan_c, len(pk.plan), pk.blob.data_ptr(), x.contiguous().data_ptr(), pred.data_ptr(),
+                                   None, None, ws.data_ptr(), ws.numel(), 2, taps_struct, None)
+        _cabi.check(rc, "cistgcn_forward_f32[emu]", L)
+        outs.append((pred, holders))
+    (mma, tm), (ffma, tf) = outs
+    assert (mma - ref).abs().max().item() <= G.tol(ref)
+    assert (ffma - ref).abs().max().item() <= G.tol(ref)
+    assert not torch.equal(mma, ffma)
+    for k in tm:
+        if k.startswith("st_gcnns.") and (k.endswith(".w1") or k.endswith(".w2") or (interp and k.endswith("Adj"))):
+            a, b = tm[k], tf[k]
+            assert (a - b).abs().max().item() <= 5e-5 * max(1e-30, b.abs().max().item()), k
