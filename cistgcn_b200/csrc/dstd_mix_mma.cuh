@@ -67,8 +67,9 @@ inline bool mix_mma_plan(MixArgs& a, int max_smem_floats) {
   // (the B fragments of the last, partial column tile read the row padding behind column T*V: column-local garbage in
   // accumulator columns that are never stored)
   a.o_adj = a.o_a + pad4i(cmax * LD);
-  // adjacency region; the squeeze partial sums [NW][32] alias its start (both adjacencies are dead by then)
-  const int adj = imax(imax(pad4i(T * T * (V | 1)), T * pad4i(V * V)), (MMA_NT / 32) * 32);
+  // adjacency region; the squeeze partial sums [NW][32] alias it behind Adj_s (Adj_t is dead by then)
+  // (the next sample's Adj_s is copied in behind the second domain's channel mix, so the partials sit behind it)
+  const int adj = imax(imax(pad4i(T * T * (V | 1)) + (MMA_NT / 32) * 32, T * pad4i(V * V)), (MMA_NT / 32) * 32);
   a.o_sm = a.o_adj + adj;
   int cur = a.o_sm + pad4i(2 * Co) + 2 * pad4i(Co) + pad4i(Hs);
   for (int f = 0; f < CB_COUNT; ++f)
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(MMA_NT, 2) dstd_mix_mma_kernel(const MixArgs a
   float* semean = p;  p += pad4i(Co);
   float* gate = p;    p += pad4i(Co);
   float* hid = p;     p += pad4i(Hs);
-  float* separt = ADJ;                                 // [NW][32] squeeze partial sums (row m of the warp's columns); the adjacencies are dead by then
+  float* separt = ADJ + pad4i(TT * VP);                // [NW][32] squeeze partial sums (row m of the warp's columns); Adj_t is dead by then
   auto P = [&](int f) -> const float* { return smem + a.res[f]; };
   auto Pw = [&](int f) -> float* { return smem + a.res[f]; };
 
@@ -206,9 +207,19 @@ __global__ void __launch_bounds__(MMA_NT, 2) dstd_mix_mma_kernel(const MixArgs a
   constexpr int NS = NW * 8;
   const int ntiles_w = (NTILES - warp + NW - 1) / NW;
 
+  // ---- operands fetched a sample ahead
+  // Adj_s (V,T,T) -> [t][q][v] with an odd row stride, as 4-byte cp.async gathers (no register staging)
+  auto adj_s_fetch = [&](int bb) {
+    const float* as = interp ? a.adj_s + (size_t)bb * V * TT : W + d[CB_ADJ_S];
+    for (int i = tid; i < V * TT; i += NT) { const int v = i / TT, r = i - v * TT; cp_async4(ADJ + r * VP + v, as + i); }
+    cp_async_commit();
+  };
+  bool adj_ahead = false;                              // CTA-uniform
+
   for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
-    // the next sample's operands (input tile, both adjacencies) start their way from HBM into L2 now: the loads at the top
-    // of the next iteration are exposed (two samples in flight per SM), an L2 hit halves what they wait for
+    // the next sample's operands (input tile, both adjacencies) start their way from HBM into L2 now: the tile load at the
+    // top of the next iteration is exposed (two samples in flight per SM), an L2 hit halves what it waits for.  (Loading the
+    // next tile into registers behind the squeeze-excitation was tried: at the 128-register cap it spilled and cost 9 %.)
     if (b + (int)gridDim.x < a.batch) {
       const size_t bn = (size_t)b + gridDim.x;
       if (d[CB_IN_MODE] == 1) prefetch_l2_range<NT>(a.in + bn * d[CB_IN_SB], (size_t)TV * 3 * 4);
@@ -221,10 +232,7 @@ __global__ void __launch_bounds__(MMA_NT, 2) dstd_mix_mma_kernel(const MixArgs a
     }
     // ---------------- load + global_norm (:375); block 0 builds the 10 features (:568-577); gates; Adj_s
     if (tid < 2 * Co) wg[tid] = __ldg(a.wg + (size_t)b * 2 * Co + tid);
-    {
-      const float* as = interp ? a.adj_s + (size_t)b * V * TT : W + d[CB_ADJ_S];     // (V,T,T) -> [t][q][v], odd row stride
-      for (int i = tid; i < V * TT; i += NT) { const int v = i / TT, r = i - v * TT; ADJ[r * VP + v] = __ldg(as + i); }
-    }
+    if (!adj_ahead) adj_s_fetch(b);                    // first sample of the CTA; later ones were fetched a sample ahead
     if (d[CB_IN_MODE] == 1) {
       const float* src = a.in + (size_t)b * d[CB_IN_SB];
       float* raw = A;
@@ -273,6 +281,7 @@ __global__ void __launch_bounds__(MMA_NT, 2) dstd_mix_mma_kernel(const MixArgs a
         }
       }
     }
+    cp_async_wait_all();                               // Adj_s
     __syncthreads();
 
     float cacc[NTW][MT][4];                            // compressor accumulators over both domains (:305)
@@ -291,6 +300,11 @@ __global__ void __launch_bounds__(MMA_NT, 2) dstd_mix_mma_kernel(const MixArgs a
         else gcn_time<T, V, 1, NT, LD>(XN, ADJ, A, Ci);
       }
       __syncthreads();
+      if (L == 1) {
+        // Adj_t is dead: the NEXT sample's Adj_s comes in behind this domain's channel mix, the compressor and the SE
+        adj_ahead = b + (int)gridDim.x < a.batch;
+        if (adj_ahead) adj_s_fetch(b + (int)gridDim.x);
+      }
       if (L == 0) {
         // Adj_s is dead: bring Adj_t in behind the channel mix ((T,V,V) rows padded to a float4)
         const float* at = interp ? a.adj_t + (size_t)b * T * VV : W + d[CB_ADJ_T];

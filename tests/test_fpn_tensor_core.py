@@ -191,3 +191,48 @@ def test_dstd_mix_mma_channel_mixes_match_oracle(E, V, weights, scale):
     assert (ffma - ref).abs().max().item() <= G.tol(ref)
     assert not torch.equal(mma, ffma)
     assert (mma - ffma).abs().max().item() <= 0.5 * G.tol(ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("E,V", [(32, 22), (16, 18), (8, 22), (64, 18)])
+@pytest.mark.parametrize("weights,scale", [("W1", "unit"), ("W2", "unit"), ("W1", "mm")])
+@pytest.mark.parametrize("which", ["adj", "reduce", "narrow"])
+def test_dstd_stage_variants_match_oracle_and_each_other(E, V, weights, scale, which):
+    """Three-stage path, one stage at a time switched back to its FP32-FMA / tile implementation:
+      adj     Map2Adj expansor as chained 3xTF32 mma.sync GEMMs (csrc/dstd_adj.cuh) vs the FFMA column loops
+      reduce  stacked 1x1 convolutions of stage 1 on 3xTF32 mma.sync (csrc/dstd_reduce.cuh, Ci >= 16) vs lane-per-channel FFMA
+      narrow  3 -> 3 output block: warp-per-sample streaming kernel (csrc/dstd_mix_narrow.cuh) vs the tile kernel
+    Both forwards stay inside the fp32 tolerance against the oracle, agree to a fraction of it, and (where the variant is
+    reachable at this width) differ in the last bits, i.e. the other kernel really ran.  The adjacency taps are compared
+    relatively (they are ~1e-9 at default init).  E = 64 blocks run on the fused kernel except the output block."""
+    import _golden as G
+    from cistgcn_b200 import _cabi
+    dev = "cuda:0"
+    flag = {"adj": _cabi.FLAG_DSTD_ADJ_FFMA, "reduce": _cabi.FLAG_DSTD_REDUCE_FFMA, "narrow": _cabi.FLAG_DSTD_MIX_FFMA}[which]
+    model, sd, cfg = M.build(E, V, weights)
+    x, _ = O.synth_inputs(40, cfg, scale=scale)
+    with torch.no_grad():
+        ref = O.forward(sd, cfg, x)
+    model = model.to(dev)
+    outs = []
+    for flags in (0, flag):
+        model.kernel_flags = flags
+        model.enable_taps(True)
+        pred = model(x.to(dev))[0].cpu()
+        taps = {k: v.cpu().clone() for k, v in model.last_taps.items() if k.endswith("Adj")}
+        model.enable_taps(False)
+        outs.append((pred, taps))
+    model.kernel_flags = 0
+    (new, tn), (old, to) = outs
+    assert torch.isfinite(new).all()
+    assert (new - ref).abs().max().item() <= G.tol(ref)
+    assert (old - ref).abs().max().item() <= G.tol(ref)
+    assert (new - old).abs().max().item() <= 0.5 * G.tol(ref)
+    reachable = {"adj": True, "narrow": True, "reduce": E in (16, 32)}[which]      # reduce MMA needs 16 <= Ci <= 32
+    if reachable and weights == "W2":               # (at default init the adjacency products vanish in fp32: only W2 can tell)
+        assert not torch.equal(new, old)
+    if which == "adj":
+        assert any(not torch.equal(tn[k], to[k]) for k in tn)
+    for k in tn:
+        a, b = tn[k], to[k]
+        assert (a - b).abs().max().item() <= 1e-4 * max(1e-30, b.abs().max().item()), k

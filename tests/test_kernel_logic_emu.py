@@ -69,7 +69,7 @@ def test_emulated_mix_mma_matches_ffma_and_oracle(E, V):
     assert (mma - ffma).abs().max().item() <= 0.5 * G.tol(ref)
 
 
-@pytest.mark.parametrize("E,V", [(8, 22), (16, 18)])
+@pytest.mark.parametrize("E,V", [(8, 18)])
 def test_emulated_adj_mma_expansor_matches_ffma_and_oracle(E, V):
     """Stage 2's Map2Adj expansor as chained 3xTF32 mma.sync GEMMs (csrc/dstd_adj.cuh: layer 1's accumulator fragment is
     layer 2's A fragment) against the FP32-FMA column loops (CISTGCN_FLAG_DSTD_ADJ_FFMA): the sample-specific
@@ -107,7 +107,7 @@ def test_emulated_adj_mma_expansor_matches_ffma_and_oracle(E, V):
     assert n_adj >= 4
 
 
-@pytest.mark.parametrize("E,V,interp", [(8, 22, True), (8, 18, True), (8, 22, False)])
+@pytest.mark.parametrize("E,V,interp", [(8, 18, True), (8, 22, False)])
 def test_emulated_narrow_mix_matches_tile_kernel_and_oracle(E, V, interp):
     """Stage 3 of the 3 -> 3 output block: the warp-per-sample kernel that streams the adjacencies from global memory
     (csrc/dstd_mix_narrow.cuh) against the tile kernel (CISTGCN_FLAG_DSTD_MIX_FFMA) and the oracle, with sample-specific
@@ -137,12 +137,11 @@ def test_emulated_narrow_mix_matches_tile_kernel_and_oracle(E, V, interp):
     assert (narrow - tile).abs().max().item() <= 0.5 * G.tol(ref)
 
 
-@pytest.mark.parametrize("E,V,interp", [(32, 22, True), (16, 18, True), (8, 22, True), (16, 22, False)])
+@pytest.mark.parametrize("E,V,interp", [(32, 22, True), (16, 18, False)])
 def test_emulated_reduce_mma_matches_ffma_and_oracle(E, V, interp):
     """Stage 1's stacked 1x1 convolutions (Map2Adj entry maps + the gate conv (T,1)) on 3xTF32 mma.sync
     (csrc/dstd_reduce.cuh, MMA variant) against the lane-per-channel FFMA loops (CISTGCN_FLAG_DSTD_REDUCE_FFMA): gate
-    vectors w1 / w2, adjacencies and the prediction; two row tiles (E = 32), one (E = 16, 8), K padded (E = 8: first
-    block Ci = 10 -> 16) and blocks without Map2Adj."""
+    vectors w1 / w2, adjacencies and the prediction; two row tiles (E = 32), one (E = 16), and blocks without Map2Adj."""
     from cistgcn_b200 import _cabi
     from cistgcn_b200.pack import F, pack_state_dict
     model, sd, cfg = M.build(E, V, "W2", interp=interp)
