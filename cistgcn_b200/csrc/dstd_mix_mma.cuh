@@ -215,6 +215,20 @@ __global__ void __launch_bounds__(MMA_NT, 2) dstd_mix_mma_kernel(const MixArgs a
     cp_async_commit();
   };
   bool adj_ahead = false;                              // CTA-uniform
+  // channels per thread of the adjacency products: every thread runs ceil(items / NT) items of tc channels one after the
+  // other, so the phase lasts rounds * tc; ties go to the wider tile (fewer operand loads per FMA).  32 channels: tc = 3
+  // (242 / 220 items, one round) instead of two rounds of 2.
+  auto pick_tc = [&](int per_ctile) {
+    if (Ci < 16) return Ci >= 2 ? 2 : 1;               // measured: at 10 channels one round of 2 beats one round of 1 (operand loads)
+    int best = 1, cost = 1 << 30;
+    for (int tc = 1; tc <= 4; ++tc) {
+      const int items = ((Ci + tc - 1) / tc) * per_ctile, c = ((items + NT - 1) / NT) * tc;
+      if (c <= cost) { cost = c; best = tc; }
+    }
+    return best;
+  };
+  constexpr int GT_TW = (V % 11 == 0) ? 11 : ((V % 9 == 0) ? 9 : ((V % 5 == 0) ? 5 : 1));   // gcn_time's column tile
+  const int tc_space = pick_tc(V), tc_time = pick_tc(T * (V / GT_TW));
 
   for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
     // the next sample's operands (input tile, both adjacencies) start their way from HBM into L2 now: the tile load at the
@@ -291,13 +305,19 @@ __global__ void __launch_bounds__(MMA_NT, 2) dstd_mix_mma_kernel(const MixArgs a
     for (int L = 0; L < 2; ++L) {
       // ---------------- g = XN x Adj  (:110, :117, :123) -> A   (FP32 FMA: per-sample operands on both sides)
       if (L == 0) {
-        if (Ci >= 4 && ((Ci + 3) / 4) * V >= NT) gcn_space<T, V, 4, NT, LD>(XN, ADJ, A, Ci);
-        else if (Ci >= 2) gcn_space<T, V, 2, NT, LD>(XN, ADJ, A, Ci);
-        else gcn_space<T, V, 1, NT, LD>(XN, ADJ, A, Ci);
+        switch (tc_space) {
+          case 4: gcn_space<T, V, 4, NT, LD>(XN, ADJ, A, Ci); break;
+          case 3: gcn_space<T, V, 3, NT, LD>(XN, ADJ, A, Ci); break;
+          case 2: gcn_space<T, V, 2, NT, LD>(XN, ADJ, A, Ci); break;
+          default: gcn_space<T, V, 1, NT, LD>(XN, ADJ, A, Ci);
+        }
       } else {
-        if (Ci >= 4 && ((Ci + 3) / 4) * T * 2 >= NT) gcn_time<T, V, 4, NT, LD>(XN, ADJ, A, Ci);
-        else if (Ci >= 2) gcn_time<T, V, 2, NT, LD>(XN, ADJ, A, Ci);
-        else gcn_time<T, V, 1, NT, LD>(XN, ADJ, A, Ci);
+        switch (tc_time) {
+          case 4: gcn_time<T, V, 4, NT, LD>(XN, ADJ, A, Ci); break;
+          case 3: gcn_time<T, V, 3, NT, LD>(XN, ADJ, A, Ci); break;
+          case 2: gcn_time<T, V, 2, NT, LD>(XN, ADJ, A, Ci); break;
+          default: gcn_time<T, V, 1, NT, LD>(XN, ADJ, A, Ci);
+        }
       }
       __syncthreads();
       if (L == 1) {
