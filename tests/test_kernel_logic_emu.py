@@ -145,7 +145,8 @@ def test_emulated_reduce_mma_matches_ffma_and_oracle(E, V, interp):
     from cistgcn_b200 import _cabi
     from cistgcn_b200.pack import F, pack_state_dict
     model, sd, cfg = M.build(E, V, "W2", interp=interp)
-    x, _ = O.synth_inputs(2, cfg)
+    nb = 1 if E >= 32 else 2
+    x, _ = O.synth_inputs(nb, cfg)
     with torch.no_grad():
         ref = O.forward(sd, cfg, x, interpretable_in=[interp] * 5, interpretable_out=[interp])
     L = _emu.lib()
@@ -154,11 +155,11 @@ def test_emulated_reduce_mma_matches_ffma_and_oracle(E, V, interp):
     for flags in (0, _cabi.FLAG_DSTD_REDUCE_FFMA):
         pk = pack_state_dict(sd, geom, "cpu")
         pk.plan_c[F["CP_FLAGS"]] = flags
-        pred = torch.empty(2, geom.output_n, geom.joints, 3)
-        ws = torch.empty(L.cistgcn_workspace_bytes(pk.plan_c, 2), dtype=torch.uint8)
-        taps_struct, holders = _cabi.make_taps(geom, 2, "cpu")
+        pred = torch.empty(nb, geom.output_n, geom.joints, 3)
+        ws = torch.empty(L.cistgcn_workspace_bytes(pk.plan_c, nb), dtype=torch.uint8)
+        taps_struct, holders = _cabi.make_taps(geom, nb, "cpu")
         rc = L.cistgcn_forward_f32(pk.plan_c, len(pk.plan), pk.blob.data_ptr(), x.contiguous().data_ptr(), pred.data_ptr(),
-                                   None, None, ws.data_ptr(), ws.numel(), 2, taps_struct, None)
+                                   None, None, ws.data_ptr(), ws.numel(), nb, taps_struct, None)
         _cabi.check(rc, "cistgcn_forward_f32[emu]", L)
         outs.append((pred, holders))
     (mma, tm), (ffma, tf) = outs
