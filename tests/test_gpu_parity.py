@@ -157,6 +157,27 @@ def test_batch_independence_across_chunks():
     assert (first[:64].cpu() - ref).abs().max().item() <= G.tol(ref)
 
 
+@pytest.mark.parametrize("E,V", [(32, 22), (16, 18)])
+def test_replicated_samples_are_bit_identical_on_the_tensor_core_path(E, V):
+    """Race / stale-shared-memory detector for the warp-per-sample and tensor-core kernels (E >= 16: MMA variants of all
+    three DSTD-GC stages): the same 251 samples replicated over 6 000 rows land in different warps, CTAs and prefetch
+    slots, yet every copy must be bit-identical, and so must a second run."""
+    model, sd, cfg = M.build(E, V, "W2")
+    base, _ = O.synth_inputs(251, cfg)
+    B = 6000
+    idx = torch.arange(B) % 251
+    x = base[idx].contiguous().to(DEV)
+    model = model.to(DEV)
+    pred = model(x)[0]
+    first = pred[:251]
+    for k in range(1, B // 251):
+        assert torch.equal(pred[k * 251:(k + 1) * 251], first), k
+    assert torch.equal(model(x)[0], pred)
+    with torch.no_grad():
+        ref = O.forward(sd, cfg, base[:32])
+    assert (first[:32].cpu() - ref).abs().max().item() <= G.tol(ref)
+
+
 def test_full_size_batch_64k_e32():
     """BASELINE configs[1] size (E=32, H36M shape, batch 65536): finite outputs, linear MPJPE bookkeeping
     (sum of per-chunk frame sums == stand-alone MPJPE kernel), and a 64-sample spot check vs the oracle."""
