@@ -12,10 +12,17 @@
 //            register tile over the V joints: per input channel one conflict-free weight LDS per output + V/4 broadcast
 //            LDS.128 of the slab row feed 3*V FFMAs.  The gate conv (T,1) is the same GEMM with per-frame weights,
 //            accumulated over the slabs in registers.
+//            MMA variant (T = 10, Ci >= 16): the same GEMMs as 3xTF32 mma.sync.m16n8k8 -- rows = output channels,
+//            columns = joints, k = input channels; the slab rows are split into hi + lo once per k step and shared by
+//            the entry maps and the gate conv; the weights are ONE fp32 fragment image per matrix, split in the loop
+//            (a second, lo image would cost resident warps); the accumulator fragments go to the map buffer with
+//            conflict-free 64-bit stores (row stride = 8 mod 16).
 //   collapse lanes = the 2*Ch outputs (both domains) of time_compress.3 (accumulated over slabs) and
-//            joint_compress.3 (complete per slab).
-// Output per sample (the `red` record, float offsets from RedLayout): stats [2+2T], h1 [2*Cg][V] (after BN + PReLU),
-// tc [2*Ch][V] and jc [2*Ch][T] (after BN).  Stage 2 (dstd_adj.cuh) turns them into the gates and the adjacencies.
+//            joint_compress.3 (complete per slab; MMA variant: its weights as [c'][v / 4][lane][4], one LDS.128 per
+//            four FFMAs on four independent chains).
+// Output per sample (the `red` record, float offsets from RedLayout): tc [2*Ch][V] and jc [2*Ch][T] (after BN), then
+// stats [2+2T] and h1 [2*Cg][V] (after BN + PReLU) -- the gate inputs come last because stage 2 (dstd_adj.cuh), which
+// turns the record into the gates and the adjacencies, reuses their room for dim_seq / dim_space.
 #pragma once
 #include "../../include/cistgcn_b200.h"
 #include "host_util.h"
