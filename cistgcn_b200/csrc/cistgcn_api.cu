@@ -192,7 +192,7 @@ bool split_plan(const int32_t* desc, SplitPlan& sp, uint32_t flags = 0) {
   memcpy(sp.m.d, desc, sizeof(sp.m.d));
   const int cap = kMaxSmemBytes / 4;
   if (!cg::reduce_plan(sp.r, cap, !(flags & CISTGCN_FLAG_DSTD_REDUCE_FFMA))) return false;
-  if (!cg::adj_plan(sp.j, cap, !(flags & CISTGCN_FLAG_DSTD_ADJ_FFMA))) return false;
+  if (!((!(flags & CISTGCN_FLAG_DSTD_ADJ_FFMA) && cg::adj_plan(sp.j, cap, true)) || cg::adj_plan(sp.j, cap, false))) return false;
   sp.ne = interp ? (4 * Ch + 31) / 32 : 1;
   if (sp.ne < 1) sp.ne = 1;
   // mix stage: two 256-thread CTAs per SM when the plan fits half an SM, else one 512-thread CTA
