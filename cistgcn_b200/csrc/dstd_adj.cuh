@@ -228,7 +228,7 @@ CG_DEV void expansor_mma_step(float (&acc)[2][NKS][4], const float (&ah)[2][4], 
 // Same contract as expansor_warp.  Rows of the MMA tiles = map columns: a round covers 32 columns (two 16-row tiles);
 // lane = 4 g + q owns rows g and g + 8 of each tile.
 template <int N, int NCOLS, class OFN, class STORE>
-CG_DEV void expansor_mma_warp(const float* f1, const float* f2, const float* b0, float a0, OFN o_at, STORE store) {
+CG_DEV void expansor_mma_warp(const float* f1_, const float* f2_, const float* b0, float a0, OFN o_at, STORE store) {
   constexpr int NKS = (N + 7) / 8;
   const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
 #pragma unroll 1
@@ -240,8 +240,9 @@ CG_DEV void expansor_mma_warp(const float* f1, const float* f2, const float* b0,
       active[u] = c0 + 8 * u + g < NCOLS;
       col[u] = active[u] ? c0 + 8 * u + g : NCOLS - 1;
     }
-    f1 = opaque_ptr(f1);
-    f2 = opaque_ptr(f2);
+    const int oz = opaque_zero();                       // the fragment images are re-read every round, not hoisted out of it
+    const float* f1 = f1_ + oz;
+    const float* f2 = f2_ + oz;
     float acc[2][NKS][4];
 #pragma unroll
     for (int tl = 0; tl < 2; ++tl)

@@ -39,6 +39,16 @@ CG_DEV const T* opaque_ptr(const T* p) {
   return p;
 }
 
+// Same purpose for SHARED-memory operands: an opaque zero to add to the pointer.  Laundering the pointer itself makes it a
+// generic pointer (LD with 64-bit address arithmetic instead of LDS); laundering an integer offset keeps its address space.
+CG_DEV int opaque_zero() {
+  int z = 0;
+#ifndef CISTGCN_EMU
+  asm volatile("" : "+r"(z));
+#endif
+  return z;
+}
+
 // ---- bf16 storage of inter-kernel activations (cistgcn_forward_bf16): plain bit manipulation, no cuda_bf16.h, so the
 // same code runs under the SIMT emulator.  Round-to-nearest-even; NaN payloads are not preserved (activations are finite).
 CG_DEV unsigned f32_bits(float v) { unsigned u; memcpy(&u, &v, 4); return u; }

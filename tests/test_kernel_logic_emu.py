@@ -40,7 +40,7 @@ def test_emulated_e32_block_widths():
     assert abs((sums.sum() / (3 * 25 * 18)).item() - O.mpjpe(ref, tgt).item()) <= 1e-3 * max(1, ref.abs().max().item() / 4)
 
 
-@pytest.mark.parametrize("E,V", [(32, 22), (16, 18)])
+@pytest.mark.parametrize("E,V", [(32, 18)])
 def test_emulated_mix_mma_matches_ffma_and_oracle(E, V):
     """Stage 3 of the DSTD-GC path on 3xTF32 mma.sync (csrc/dstd_mix_mma.cuh; the emulator executes the PTX fragment
     layouts of m16n8k8 with TF32-truncated operands) against the FP32-FMA tile loops and the oracle."""
