@@ -90,7 +90,7 @@ inline bool reduce_plan(ReduceArgs& a, int max_smem_floats, bool mma = true) {
   a.ks = (Ci + 7) / 8; a.mte = interp ? (4 * Ch + 15) / 16 : 0; a.mtg = (2 * Cg + 15) / 16;
   a.o_g0 = take(a.mma ? T * a.mtg * a.ks * 128 : Ci * T * a.mp_g);
   a.o_a0 = interp ? take(a.mma ? a.mte * a.ks * 128 : Ci * a.mp_e) : 0;
-  a.o_tc3 = interp ? take(Ch * T * a.mp_c) : 0;
+  a.o_tc3 = interp ? take(a.mma ? T * 2 * ((Ch + 7) / 8) * 128 : Ch * T * a.mp_c) : 0;   // tensor-core variant: [t][domain][k step][lane][4]
   a.o_jc3 = interp ? take(Ch * (a.mma ? rpad4(V) : V) * a.mp_c) : 0;     // tensor-core variant: [c'][v / 4][lane][4], v padded
   a.o_gn_s = take(Ci); a.o_gn_b = take(Ci);
   a.o_g0_b = take(a.mp_g); a.o_g0_a = take(2);
@@ -192,7 +192,17 @@ __global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(cons
     cp(a.o_gn_s, CB_GN_S, Ci); cp(a.o_gn_b, CB_GN_B, Ci);
     cp(a.o_g0_b, CB_R_G0_B, a.mp_g); cp(a.o_g0_a, CB_G0_A, 2);
     if (interp) {
-      cp(a.o_tc3, CB_R_TC3_WT, Ch * T * a.mp_c);
+      if constexpr (MMA) {
+        // time_compress.3 (T,1): per frame and domain one 16 x Ch fragment image (rows = outputs o, k = input channel c')
+        const int mpc_ = a.mp_c, ksc = (Ch + 7) / 8;
+        for (int tl = 0; tl < T * 2; ++tl) {
+          const int t = tl >> 1, L = tl & 1;
+          build_reduce_frags(smem + a.o_tc3 + tl * ksc * 128, 1, ksc, Ch, Ch, nthreads,
+                             [&](int m, int k) { return __ldg(W + d[CB_R_TC3_WT] + (size_t)(k * T + t) * mpc_ + L * Ch + m); });
+        }
+      } else {
+        cp(a.o_tc3, CB_R_TC3_WT, Ch * T * a.mp_c);
+      }
       if constexpr (MMA) {
         // joint_compress.3 weights as [c'][v / 4][lane = output][4 joints]: one conflict-free LDS.128 per four FFMAs
         const int mpc_ = a.mp_c;
@@ -277,6 +287,13 @@ __global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(cons
     float acc_g[V], acc_tc[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) { acc_g[v] = 0.f; acc_tc[v] = 0.f; }
+    float mtc[2][NTL][4];                                  // tensor-core variant: time_compress.3 accumulators, per domain
+#pragma unroll
+    for (int L = 0; L < 2; ++L)
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) mtc[L][nt][e] = 0.f;
     float mg[2][NTL][4];                                   // tensor-core variant: gate-conv accumulator fragments
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -482,8 +499,42 @@ __global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(cons
           }
         }
         __syncwarp();
-        // ---- collapsing convolutions (:141-142, :149-150): lanes = outputs (domain L3, channel o)
-        {
+        // ---- collapsing convolutions (:141-142, :149-150)
+        if constexpr (MMA) {
+          // time_compress.3 on the tensor cores: per domain rows = outputs (Ch <= 16: one tile), k = the Ch map rows,
+          // columns = joints; both domains share the MMA stream so that one accumulator is revisited 2 * NTL MMAs later
+          const int ksc = (Ch + 7) / 8;
+          const float* ft = wtc + t * 2 * ksc * 128;
+#pragma unroll 1
+          for (int ks = 0; ks < ksc; ++ks) {
+            const int k0 = 8 * ks + q, k1 = k0 + 4;
+            float ah[2][4], al[2][4], bh[2][NTL][2], bl[2][NTL][2];
+#pragma unroll
+            for (int L = 0; L < 2; ++L) {
+              const float4 w4 = *reinterpret_cast<const float4*>(ft + ((L * ksc + ks) * 32 + lane) * 4);
+              tf32_split(w4.x, ah[L][0], al[L][0]); tf32_split(w4.y, ah[L][1], al[L][1]);
+              tf32_split(w4.z, ah[L][2], al[L][2]); tf32_split(w4.w, ah[L][3], al[L][3]);
+              const float* r0 = ag + (2 * L * Ch + (k0 < Ch ? k0 : 0)) * AS + g;    // rows beyond Ch meet zero weights
+              const float* r1 = ag + (2 * L * Ch + (k1 < Ch ? k1 : 0)) * AS + g;
+#pragma unroll
+              for (int nt = 0; nt < NTL; ++nt) {
+                tf32_split(r0[8 * nt], bh[L][nt][0], bl[L][nt][0]);
+                tf32_split(r1[8 * nt], bh[L][nt][1], bl[L][nt][1]);
+              }
+            }
+#pragma unroll
+            for (int term = 0; term < 3; ++term)
+#pragma unroll
+              for (int L = 0; L < 2; ++L)
+#pragma unroll
+                for (int nt = 0; nt < NTL; ++nt) {
+                  if (term == 0) mma_tf32(mtc[L][nt], al[L], bh[L][nt]);
+                  else if (term == 1) mma_tf32(mtc[L][nt], ah[L], bl[L][nt]);
+                  else mma_tf32(mtc[L][nt], ah[L], bh[L][nt]);
+                }
+          }
+        }
+        {                                                           // lanes = outputs (domain L3, channel o)
           const float* wt = wtc + t * mpc + lane;                   // row (c'*T + t)
           const float* wj = wjc + lane;                             // row (c'*V + v)
           float jsum = 0.f;
@@ -492,14 +543,18 @@ __global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(cons
             float xa[XS], xg[XS];
 #pragma unroll
             for (int i = 0; i < V4; ++i) {
-              const float4 q4 = *reinterpret_cast<const float4*>(arow_tc + cp_ * AS + 4 * i);
-              xa[4 * i] = q4.x; xa[4 * i + 1] = q4.y; xa[4 * i + 2] = q4.z; xa[4 * i + 3] = q4.w;
+              if constexpr (!MMA) {
+                const float4 q4 = *reinterpret_cast<const float4*>(arow_tc + cp_ * AS + 4 * i);
+                xa[4 * i] = q4.x; xa[4 * i + 1] = q4.y; xa[4 * i + 2] = q4.z; xa[4 * i + 3] = q4.w;
+              }
               const float4 g4 = *reinterpret_cast<const float4*>(arow_jc + cp_ * AS + 4 * i);
               xg[4 * i] = g4.x; xg[4 * i + 1] = g4.y; xg[4 * i + 2] = g4.z; xg[4 * i + 3] = g4.w;
             }
-            const float wtv = wt[cp_ * T * mpc];
+            if constexpr (!MMA) {
+              const float wtv = wt[cp_ * T * mpc];
 #pragma unroll
-            for (int v = 0; v < V; ++v) acc_tc[v] = fmaf(wtv, xa[v], acc_tc[v]);
+              for (int v = 0; v < V; ++v) acc_tc[v] = fmaf(wtv, xa[v], acc_tc[v]);
+            }
             if constexpr (MMA) {
               const float* wjr = wjc + ((size_t)cp_ * V4 * mpc + lane) * 4;
               float j0 = 0.f, j1 = 0.f, j2 = 0.f, j3 = 0.f;
@@ -569,7 +624,23 @@ __global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(cons
     }
     __syncwarp();
     if (interp) {
-      if (lane < 2 * Ch) {
+      if constexpr (MMA) {
+#pragma unroll
+        for (int L = 0; L < 2; ++L)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int o = g + 8 * h;
+            if (o < Ch) {
+              const float bb = smem[a.o_tc3_b + L * Ch + o];
+              float* ar = ag + (L * Ch + o) * AS + 2 * q;
+#pragma unroll
+              for (int nt = 0; nt < NTL; ++nt) {
+                if (8 * nt + 2 * q < V) ar[8 * nt] = mtc[L][nt][2 * h] + bb;
+                if (8 * nt + 2 * q + 1 < V) ar[8 * nt + 1] = mtc[L][nt][2 * h + 1] + bb;
+              }
+            }
+          }
+      } else if (lane < 2 * Ch) {
         const float bb = smem[a.o_tc3_b + lane];
         float* ar = ag + lane * AS;
 #pragma unroll
