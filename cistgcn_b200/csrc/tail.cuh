@@ -29,7 +29,7 @@ struct TailArgs {
 inline void tail_plan(TailArgs& a) {
   const int To = a.t[CT_TOUT], V = a.t[CT_V], H = a.t[CT_HID];
   a.smem_floats = pad4i(To * V * 3) + 3 * pad4i(4 * H) + pad4i(3 * H) + pad4i(3 * To) + pad4i(V) + pad4i(To) +
-                  3 * pad4i(To * V) + pad4i(3 * To * V) + 4 * pad4i(To) + 2 * 8 + 2 * pad4i(To);
+                  3 * pad4i(To * V) + pad4i(3 * To * V) + 4 * pad4i(To) + 2 * 8 + 2 * pad4i(To) + pad4i(To) + (TAIL_NT / 32) * 32;
 }
 
 __global__ void __launch_bounds__(TAIL_NT, 3) tail_kernel(const TailArgs a) {
@@ -60,8 +60,11 @@ __global__ void __launch_bounds__(TAIL_NT, 3) tail_kernel(const TailArgs a) {
   float* e1 = p;     p += 8;
   float* e2 = p;     p += 8;
   float* fsum = p;   p += pad4i(To);          // per-frame error partials of this sample
+  float* d2 = p;     p += pad4i(To);          // norm_map.0 applied to the displacement vector
+  float* zsl = p;    p += (NT / 32) * 32;     // per-warp, per-slice sums of z
   double facc = 0.0;                          // thread tid < To accumulates frame tid over this CTA's samples
 
+  const bool slice_sums = H <= NT && NT % H == 0 && ((NT / H) & (NT / H - 1)) == 0 && NT / H <= 32;
   for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
     const float* x7 = a.x7 + (size_t)b * NZ;
     for (int i = tid; i < NZ; i += NT) z[i] = x7[i];
@@ -72,11 +75,25 @@ __global__ void __launch_bounds__(TAIL_NT, 3) tail_kernel(const TailArgs a) {
     // monotone in z (slope a >= 0) or V-shaped (a < 0), so its maximum over the positions is attained where z is
     // smallest or largest -- exactly, rounding included.  Only the extremes of z are needed, not a pass per channel.
     {
-      float lo = INFINITY, hi = -INFINITY;
-      for (int i = tid; i < NZ; i += NT) { const float zv = z[i]; lo = fminf(lo, zv); hi = fmaxf(hi, zv); }
+      // (the same pass sums z per float4 slice i % nsub -- a thread's float4s all fall into slice tid % nsub -- for
+      // context_conv3 below, where every one of the H channels of a slice would otherwise add up the same values)
+      float lo = INFINITY, hi = -INFINITY, szp = 0.f;
+      const float4* z4 = reinterpret_cast<const float4*>(z);
+      const int n4 = NZ >> 2;
+      for (int i = tid; i < n4; i += NT) {
+        const float4 q = z4[i];
+        lo = fminf(fminf(lo, q.x), fminf(fminf(q.y, q.z), q.w));
+        hi = fmaxf(fmaxf(hi, q.x), fmaxf(fmaxf(q.y, q.z), q.w));
+        szp += (q.x + q.y) + (q.z + q.w);
+      }
+      if (tid == 0) for (int i = n4 << 2; i < NZ; ++i) { lo = fminf(lo, z[i]); hi = fmaxf(hi, z[i]); szp += z[i]; }   // slice 0 takes the tail
       lo = -warp_max(-lo);
       hi = warp_max(hi);
       if ((tid & 31) == 0) { yv[tid >> 5] = lo; yv[NT / 32 + (tid >> 5)] = hi; }      // yv is free until the next phase
+      if (slice_sums) {
+        for (int o = 16; o >= NT / H; o >>= 1) szp += __shfl_xor_sync(0xffffffffu, szp, o);
+        if ((tid & 31) < NT / H) zsl[(tid >> 5) * 32 + (tid & 31)] = szp;
+      }
     }
     __syncthreads();
     {
@@ -97,24 +114,27 @@ __global__ void __launch_bounds__(TAIL_NT, 3) tail_kernel(const TailArgs a) {
         const int n4 = NZ >> 2;
         if (s3 != 0.f && fabsf(th) < 1e30f) {
           float sz = 0.f, sc = 0.f;
-          int cnt = 0;
           const float4* z4 = reinterpret_cast<const float4*>(z);
+          const int cnt = 4 * ((n4 - sub + nsub - 1) / nsub) + (sub == 0 ? NZ - (n4 << 2) : 0);
+          if (slice_sums) {
+#pragma unroll
+            for (int w = 0; w < NT / 32; ++w) sz += zsl[w * 32 + sub];
+          } else {
+            for (int i = sub; i < n4; i += nsub) { const float4 q = z4[i]; sz += (q.x + q.y) + (q.z + q.w); }
+            if (sub == 0) for (int i = n4 << 2; i < NZ; ++i) sz += z[i];
+          }
           if (s3 > 0.f) {
             for (int i = sub; i < n4; i += nsub) {
               const float4 q = z4[i];
-              sz += (q.x + q.y) + (q.z + q.w);
               sc += (fmaxf(q.x, th) + fmaxf(q.y, th)) + (fmaxf(q.z, th) + fmaxf(q.w, th));
-              cnt += 4;
             }
-            if (sub == 0) for (int i = n4 << 2; i < NZ; ++i) { sz += z[i]; sc += fmaxf(z[i], th); ++cnt; }
+            if (sub == 0) for (int i = n4 << 2; i < NZ; ++i) sc += fmaxf(z[i], th);
           } else {
             for (int i = sub; i < n4; i += nsub) {
               const float4 q = z4[i];
-              sz += (q.x + q.y) + (q.z + q.w);
               sc += (fminf(q.x, th) + fminf(q.y, th)) + (fminf(q.z, th) + fminf(q.w, th));
-              cnt += 4;
             }
-            if (sub == 0) for (int i = n4 << 2; i < NZ; ++i) { sz += z[i]; sc += fminf(z[i], th); ++cnt; }
+            if (sub == 0) for (int i = n4 << 2; i < NZ; ++i) sc += fminf(z[i], th);
           }
           const float nb = (float)cnt * b3;
           sm = fmaf(a3, fmaf(s3, sz, nb), (1.f - a3) * fmaf(s3, sc, nb));
@@ -134,7 +154,20 @@ __global__ void __launch_bounds__(TAIL_NT, 3) tail_kernel(const TailArgs a) {
           float wr[32];
 #pragma unroll
           for (int r = 0; r < 32; ++r) wr[r] = r < To ? w2[r * pad8i(H)] : 0.f;
-          for (int col = c_begin; col + 1 < c_end; col += 2) {
+          int col = c_begin;
+          for (; col + 3 < c_end; col += 4) {                                   // four columns per pass: two loads in flight per FMA quad
+            float acc0 = b2, acc1 = b2, acc2 = b2, acc3 = b2;
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              if (r < To) {
+                const float2 q = *reinterpret_cast<const float2*>(z + r * V3 + col);
+                const float2 u = *reinterpret_cast<const float2*>(z + r * V3 + col + 2);
+                acc0 = fmaf(wr[r], q.x, acc0); acc1 = fmaf(wr[r], q.y, acc1);
+                acc2 = fmaf(wr[r], u.x, acc2); acc3 = fmaf(wr[r], u.y, acc3);
+              }
+            mx2 = fmaxf(mx2, fmaxf(fmaxf(prelu(acc0, a2), prelu(acc1, a2)), fmaxf(prelu(acc2, a2), prelu(acc3, a2))));
+          }
+          for (; col + 1 < c_end; col += 2) {
             float acc0 = b2, acc1 = b2;
 #pragma unroll
             for (int r = 0; r < 32; ++r)
@@ -196,13 +229,18 @@ __global__ void __launch_bounds__(TAIL_NT, 3) tail_kernel(const TailArgs a) {
     }
     __syncthreads();
     // ---- norm_map on seq_joints = disp (x) joints: Conv1d(k=1)+BN+PReLU, SE1d, Conv1d+BN+PReLU (:443-451, 471-472)
+    // seq_joints[f][v] = disp[f] * joints[v] is rank one, so the first Conv1d factors: sum_f w[fo][f] disp[f] joints[v] =
+    // joints[v] * d2[fo] -- To MACs per output frame instead of per output element
+    for (int fo = tid; fo < To; fo += NT) {
+      const float* wt = W + t[CT_N0_WT] + fo;
+      float acc = 0.f;
+      for (int f = 0; f < To; ++f) acc = fmaf(wt[f * Top], disp[f], acc);
+      d2[fo] = acc;
+    }
+    __syncthreads();
     for (int i = tid; i < To * V; i += NT) {
       const int fo = i / V, v = i - fo * V;
-      const float* wt = W + t[CT_N0_WT] + fo;
-      float acc = W[t[CT_N0_B] + fo];
-      const float jv = joints[v];
-      for (int f = 0; f < To; ++f) acc = fmaf(wt[f * Top], disp[f] * jv, acc);
-      n1[i] = prelu(acc, W[t[CT_N0_A]]);
+      n1[i] = prelu(fmaf(joints[v], d2[fo], W[t[CT_N0_B] + fo]), W[t[CT_N0_A]]);
     }
     __syncthreads();
     for (int f = tid; f < To; f += NT) {
