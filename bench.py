@@ -413,14 +413,19 @@ def run_native(args, rank, world, local_rank):
         e2e_step()
     e2e_drain()
     barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    e2e_drain()
-    ev1.record()
-    barrier()
-    ms_e2e = max_over_ranks(ev0.elapsed_time(ev1))
+    def e2e_timed():
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e2e_drain()
+        ev1.record()
+        barrier()
+        return max_over_ranks(ev0.elapsed_time(ev1))
+
+    ms_e2e = e2e_timed()
+    if ms_e2e < 200.0:          # a K-step region this short (small batches) is at the mercy of one host hiccup: median of 5
+        ms_e2e = sorted([ms_e2e] + [e2e_timed() for _ in range(4)])[2]
     e2e_value = global_B * args.steps / (ms_e2e / 1e3)
     if mode == "forward":
         checksum = float(pred_pin[:16].double().abs().sum())          # the D2H result is really read
