@@ -29,7 +29,11 @@ namespace cg {
 
 constexpr int ADJ_CPL = 2;            // expansor columns per lane and weight-row read
 constexpr int ADJ_MAX_WARPS = 8;      // 256 threads: up to 255 registers per thread (the 25-wide expansor columns need ~200)
+#ifdef CISTGCN_EMU
+constexpr int ADJ_MMA_MAX_WARPS = 4;  // emulator: one OS thread per CUDA thread -- keep the CTAs small
+#else
 constexpr int ADJ_MMA_MAX_WARPS = 16; // tensor-core expansor: 512 threads, up to 128 registers per thread
+#endif
 
 struct AdjArgs {
   int d[CB_COUNT];

@@ -22,7 +22,11 @@
 
 namespace cg {
 
+#ifdef CISTGCN_EMU
+constexpr int MIXN_MAX_WARPS = 4;           // emulator: one OS thread per CUDA thread -- keep the CTAs small
+#else
 constexpr int MIXN_MAX_WARPS = 16;          // 512 threads: up to 128 registers per thread
+#endif
 
 // Host: plan of the narrow variant (extends MixArgs: nwarps / o_warp / warp_floats).  False when the block is not narrow.
 template <int C>
