@@ -32,7 +32,7 @@ inline void tail_plan(TailArgs& a) {
                   3 * pad4i(To * V) + pad4i(3 * To * V) + 4 * pad4i(To) + 2 * 8 + 2 * pad4i(To) + pad4i(To) + (TAIL_NT / 32) * 32;
 }
 
-__global__ void __launch_bounds__(TAIL_NT, 3) tail_kernel(const TailArgs a) {
+__global__ void __launch_bounds__(TAIL_NT, 4) tail_kernel(const TailArgs a) {
   CG_DYN_SMEM(smem);
   constexpr int NT = TAIL_NT;
   const int tid = threadIdx.x;
