@@ -103,7 +103,13 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.first = index, [], None, 0
+
+    def mark(self):
+        """The timed region starts now: only rows that arrive from here on are reported.  (The process itself is started
+        before the warm-up steps: NVML initialisation on a fresh box takes a few hundred ms and must not overlap the timed
+        region.)"""
+        self.first = len(self.rows)
 
     def run(self):
         try:
@@ -121,8 +127,10 @@ class ClockSampler(threading.Thread):
         if self.proc is not None:
             self.proc.terminate()
         self.join(timeout=2)
-        sm = [int(r[0]) for r in self.rows if r[0].isdigit()]
-        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        rows = self.rows[self.first:] or self.rows
+        self.rows = rows
+        sm = [int(r[0]) for r in rows if r[0].isdigit()]
+        mx = [int(r[1]) for r in rows if r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[2 + i] == "Active" for r in self.rows)]
         return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
@@ -315,12 +323,13 @@ def run_native(args, rank, world, local_rank):
     # benchmark batches; small batches are L2-flushed between steps)
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev) if B * 10 * V * 3 * 4 < 160e6 else None
     l2_policy = "inputs_larger_than_L2" if flush is None else "L2 flushed between steps (192 MB memset, outside the events)"
-    for _ in range(max(args.warmup, 3)):
-        step(x, tgt)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step(x, tgt)
+    barrier()
+    sampler.mark()
     lib.cistgcn_profile_enable(1)
     if flush is None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -560,12 +569,13 @@ def run_train(args, rank, world, local_rank):
         return float(t.item())
 
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    for _ in range(max(args.warmup, 3)):                     # (with --graph: step 1 eager, step 2 captures, step 3.. replay)
-        tr.step(x, tgt)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):                     # (with --graph: step 1 eager, step 2 captures, step 3.. replay)
+        tr.step(x, tgt)
+    barrier()
+    sampler.mark()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     ar = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
