@@ -61,6 +61,7 @@ template <int T, int V, int C>
 __global__ void __launch_bounds__(32 * MIXN_MAX_WARPS, 1) dstd_mix_narrow_kernel(const MixArgs a) {
   CG_DYN_SMEM(smem);
   constexpr int TV = T * V, TT = T * T, VV = V * V, Cop = 8;
+  constexpr int PF_AHEAD = 4;              // slices between the L2 prefetch and the register loads (one slice ahead of use)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nthreads = blockDim.x;
   const int* d = a.d;
   const float* __restrict__ W = a.w;
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(32 * MIXN_MAX_WARPS, 1) dstd_mix_narrow_kernel
       for (int t = 0; t < T; ++t) cur[t] = __ldg(as + t * T);
 #pragma unroll 1
       for (int v = 0; v < V; ++v) {
+        if (v + PF_AHEAD < V) prefetch_l2_warp(as - (lane < T ? lane : T - 1) + (v + PF_AHEAD) * TT, TT * 4);
         if (v + 1 < V) {
           const float* an = as + (v + 1) * TT;
 #pragma unroll
@@ -181,6 +183,7 @@ __global__ void __launch_bounds__(32 * MIXN_MAX_WARPS, 1) dstd_mix_narrow_kernel
       for (int v = 0; v < V; ++v) cur[v] = __ldg(at + v * V);
 #pragma unroll 1
       for (int t = 0; t < T; ++t) {
+        if (t + PF_AHEAD < T) prefetch_l2_warp(at - (lane < V ? lane : V - 1) + (t + PF_AHEAD) * VV, VV * 4);
         if (t + 1 < T) {
           const float* an = at + (t + 1) * VV;
 #pragma unroll

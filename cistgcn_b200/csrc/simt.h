@@ -180,6 +180,17 @@ CG_DEV void prefetch_l2_range(const void* p, size_t bytes) {
 #endif
 }
 
+// Warp-level variant: the 32 lanes cover `bytes` bytes at p with one 128-byte line each per round.
+CG_DEV void prefetch_l2_warp(const void* p, int bytes) {
+#ifndef CISTGCN_EMU
+  const char* c = reinterpret_cast<const char*>(p);
+  for (int off = (threadIdx.x & 31) * 128; off < bytes; off += 32 * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
+#else
+  (void)p; (void)bytes;
+#endif
+}
+
 // ---- TF32 helpers ------------------------------------------------------------------------------------------------
 // Nearest TF32 (ties away from zero), returned as an fp32 value with 13 zero low bits.  Integer rounding on the bit
 // pattern: ptxas expands cvt.rna.tf32.f32 on sm_100a into the same add / mask plus an Inf / NaN guard (5 instructions);
