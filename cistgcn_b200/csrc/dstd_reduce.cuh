@@ -341,8 +341,20 @@ __global__ void __launch_bounds__(32 * RED_MAX_WARPS, 1) dstd_reduce_kernel(cons
         __syncwarp();
         if (!ibf) {
           if (lane < V) {
-#pragma unroll 8
-            for (int c = 0; c < Ci; ++c) {
+            int c = 0;
+#pragma unroll 2
+            for (; c + 4 <= Ci; c += 4) {                        // scale / shift of four channels per 128-bit load
+              const float4 s4 = *reinterpret_cast<const float4*>(gs + c);
+              const float4 b4 = *reinterpret_cast<const float4*>(gb + c);
+              const float sc4[4] = {s4.x, s4.y, s4.z, s4.w}, sh4[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float val = fmaf(sc4[i], xs[(c + i) * XS + lane], sh4[i]);
+                xs[(c + i) * XS + lane] = val;
+                ag[(c + i) * XT + lane] = val;
+              }
+            }
+            for (; c < Ci; ++c) {
               const float val = fmaf(gs[c], xs[c * XS + lane], gb[c]);
               xs[c * XS + lane] = val;
               ag[c * XT + lane] = val;
